@@ -1,0 +1,188 @@
+/*
+ * ruf_b200.h -- C ABI of libruf_b200.so, the B200 (sm_100a) implementation of the per-frame
+ * hot path of blodow/realtime_urdf_filter:
+ *
+ *   upload depth -> pose-transform link meshes -> rasterise virtual z-buffer ->
+ *   per-pixel  sensor > virtual - max_diff  -> filtered depth + 0/255 mask
+ *
+ * Every entry point names the piece of the reference it replaces (paths relative to the
+ * reference checkout).  Plain pointers and sizes only; no C++/torch types; nothing throws
+ * across this boundary -- every function returns a ruf_status and ruf_last_error() holds
+ * the text.  All matrices are column-major double[16] exactly as the reference hands them
+ * to glMultMatrixd (tf::Transform::getOpenGLMatrix layout).
+ *
+ * There is NO CPU fallback: every compute entry point fails with RUF_ERR_CUDA when no
+ * CUDA device / kernel image for sm_100a is available.
+ *
+ * Threading: a context owns one CUDA stream and is not thread-safe; distinct contexts are
+ * independent (one per camera stream / per GPU).  There is no process-global state
+ * (the reference has function-local statics, src/urdf_filter.cpp:210,240,358,388,549).
+ */
+#ifndef RUF_B200_H
+#define RUF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RUF_API
+#else
+#define RUF_API __attribute__((visibility("default")))
+#endif
+
+typedef struct ruf_context ruf_context;
+
+typedef enum ruf_status {
+  RUF_OK = 0,
+  RUF_ERR_INVALID = -1,   /* bad argument                                               */
+  RUF_ERR_CUDA = -2,      /* CUDA runtime error / no device (text in ruf_last_error)    */
+  RUF_ERR_NO_MODEL = -3,  /* filter called before ruf_set_model (reference: returns     */
+                          /* silently when renderers_ is empty, src/urdf_filter.cpp:222) */
+  RUF_ERR_OVERFLOW = -4,  /* an internal bin/record buffer was too small for a frame;    */
+                          /* host-buffer calls grow and retry, device calls report this  */
+  RUF_ERR_NOMEM = -5
+} ruf_status;
+
+/* Depth encodings of sensor_msgs/Image as handled by filter_callback,
+ * src/urdf_filter.cpp:280-289 (input) and :309-316 (output keeps the input encoding). */
+typedef enum ruf_encoding {
+  RUF_ENC_F32_M = 0,      /* 32FC1, metres, NaN = invalid                                */
+  RUF_ENC_U16_MM = 1      /* 16UC1, millimetres, 0 = invalid; x*0.001f in,               */
+                          /* saturate(round_half_even(x*1000.f)) out (cv::Mat::convertTo) */
+} ruf_encoding;
+
+/* ------------------------------------------------------------------------------------ */
+/* Context (replaces initGL / initFrameBufferObject / the FBO + shader objects,           */
+/* src/urdf_filter.cpp:386-456, src/FrameBufferObject.cpp, src/shader_wrapper.cpp)        */
+/* ------------------------------------------------------------------------------------ */
+
+/* device: CUDA ordinal.  width/height: image size (1..4096).  z_near/z_far: the clip planes
+ * (reference hard-codes 0.1 / 8, src/urdf_filter.cpp:53-54); they feed the shader's
+ * to_linear_depth and the background quad at 0.99*z_far (:591-596). */
+RUF_API int ruf_create(ruf_context **ctx, int device, int width, int height,
+                       double z_near, double z_far);
+RUF_API int ruf_destroy(ruf_context *ctx);
+
+/* Text of the last error on this context (ctx == NULL: last error of a failed ruf_create
+ * on the calling thread).  Never NULL. */
+RUF_API const char *ruf_last_error(const ruf_context *ctx);
+
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own
+ * stream for all subsequent work.  NULL restores the internal stream. */
+RUF_API int ruf_set_stream(ruf_context *ctx, void *cuda_stream);
+RUF_API int ruf_sync(ruf_context *ctx);   /* wait; returns deferred RUF_ERR_OVERFLOW if any */
+
+/* ------------------------------------------------------------------------------------ */
+/* Model (replaces VBO/IBO creation: RenderableBox::createBoxVBO src/renderable.cpp:133-170,*/
+/* SubMesh::init :339-350, and the implicit geometry of glutSolid* :83,96,129)            */
+/* ------------------------------------------------------------------------------------ */
+
+/* Static triangle soup in object space.  tri_xyz: T*9 floats (3 vertices x xyz), tri_part:
+ * T indices in [0, n_parts) selecting the model matrix of the drawn part (one per
+ * glDraw* / glutSolid* call of the reference: a box link contributes two parts, F4).
+ * Host pointers; copied to the device.  Calling it again replaces the model. */
+RUF_API int ruf_set_model(ruf_context *ctx, const float *tri_xyz, const uint32_t *tri_part,
+                          int64_t n_tris, int n_parts);
+/* Same, from device memory of the context's device (e.g. after an NCCL broadcast). */
+RUF_API int ruf_set_model_device(ruf_context *ctx, const void *d_tri_xyz, const void *d_tri_part,
+                                 int64_t n_tris, int n_parts);
+
+/* Capacity control for device-resident batches: max frames per call, and (0 = automatic)
+ * per-frame capacities of the internal visible-triangle and tile-bin buffers. */
+RUF_API int ruf_reserve(ruf_context *ctx, int max_batch, int64_t rec_capacity, int64_t bin_capacity);
+
+/* ------------------------------------------------------------------------------------ */
+/* The per-frame path                                                                     */
+/* ------------------------------------------------------------------------------------ */
+
+/* One frame, HOST buffers, synchronous: replaces RealtimeURDFFilter::filter
+ * (src/urdf_filter.cpp:207-267) = textureBufferFromDepthBuffer (:332-353) + render (:503-744)
+ * including both glGetTexImage readbacks (:729-735).
+ *   depth_in   W*H elements of `enc`, row-major, contiguous
+ *   proj       getProjectionMatrix output (:459-501)
+ *   view       MODELVIEW before the draw loop = LookAt * offset^-1 * camera_transform' (:583-614)
+ *   part_model n_parts matrices: link_to_fixed * link_offset [* glTranslate/glScale suffix]
+ *              (src/renderable.cpp:59-68, 95, 128, 427)
+ *   max_diff / replace_value   the shader uniforms (:629-630)
+ *   depth_out  W*H elements of `enc` (gl_FragData[1].r; re-encoded like :309-312 for U16)
+ *   mask_out   W*H bytes 0/255 (gl_FragData[3].r read as GL_UNSIGNED_BYTE) or NULL
+ *              (= need_mask_ false, :226-230) */
+RUF_API int ruf_filter(ruf_context *ctx, const void *depth_in, int enc,
+                       const double *proj, const double *view, const double *part_model,
+                       float max_diff, float replace_value,
+                       void *depth_out, uint8_t *mask_out);
+
+/* n_frames frames, DEVICE buffers, asynchronous on the context's stream (throughput path).
+ * d_depth_in / d_depth_out / d_mask_out: n_frames contiguous images.  d_proj: 16 doubles
+ * shared by the batch.  d_view: n_frames*16.  d_part_model: n_frames*n_parts*16.
+ * d_mask_out may be NULL.  d_zbuf_out (optional, debug): n_frames*W*H float window-space z
+ * of the virtual depth buffer (1.0f = nothing drawn).  The workspace grows to n_frames on
+ * demand (ruf_reserve pre-sizes it); n_frames <= 65535. */
+RUF_API int ruf_filter_batch_device(ruf_context *ctx, int n_frames, const void *d_depth_in, int enc,
+                                    const double *d_proj, const double *d_view,
+                                    const double *d_part_model,
+                                    float max_diff, float replace_value,
+                                    void *d_depth_out, uint8_t *d_mask_out, float *d_zbuf_out);
+
+/* n_frames frames, HOST buffers (pinned for full speed: ruf_host_alloc), synchronous; the
+ * batch is cut into chunks whose H2D copy, kernels and D2H copy overlap on three streams. */
+RUF_API int ruf_filter_batch_host(ruf_context *ctx, int n_frames, const void *depth_in, int enc,
+                                  const double *proj, const double *view, const double *part_model,
+                                  float max_diff, float replace_value,
+                                  void *depth_out, uint8_t *mask_out);
+
+RUF_API int ruf_host_alloc(void **ptr, size_t bytes);   /* cudaHostAlloc (pinned) */
+RUF_API int ruf_host_free(void *ptr);
+
+/* Counters of the most recent completed call (debug / bench bookkeeping). */
+typedef struct ruf_stats {
+  int64_t frames;            /* frames in the last call                                  */
+  int64_t kernel_launches;   /* kernels launched by the last call                        */
+  int64_t visible_tris;      /* sum over frames of window-space triangles kept by setup   */
+  int64_t binned_refs;       /* sum over frames of (triangle, tile) references            */
+  int64_t big_tris;          /* sum over frames of triangles routed to the per-frame list */
+  int64_t h2d_bytes, d2h_bytes;
+} ruf_stats;
+RUF_API int ruf_get_stats(ruf_context *ctx, ruf_stats *out);
+
+/* ------------------------------------------------------------------------------------ */
+/* Host-side matrices (double precision, same operation order as the reference + tf/GLU)  */
+/* ------------------------------------------------------------------------------------ */
+
+/* getProjectionMatrix, src/urdf_filter.cpp:459-501.  P = CameraInfo.P (3x4 row-major). */
+RUF_API void ruf_projection_matrix(const double *P, int width, int height,
+                                   double z_near, double z_far,
+                                   double *glTf, double *camera_tx, double *camera_ty);
+/* gluLookAt(0,0,0, 0,0,1, 0,1,0), src/urdf_filter.cpp:587. */
+RUF_API void ruf_lookat(double *m);
+/* LookAt * inverse(camera_offset) * camera_transform shifted by tx/ty, :583-614.
+ * Quaternions are (x,y,z,w); cam_q/cam_t = lookupTransform(cam_frame, fixed_frame). */
+RUF_API void ruf_view_matrix(const double *offset_q, const double *offset_t,
+                             const double *cam_q, const double *cam_t,
+                             double camera_tx, double camera_ty, double *view);
+/* link_to_fixed * link_offset (normalised quaternion, src/urdf_renderer.cpp:160-164)
+ * [* suffix], src/renderable.cpp:59-68.  suffix may be NULL. */
+RUF_API void ruf_part_model(const double *link_q, const double *link_t,
+                            const double *off_q, const double *off_t,
+                            const double *suffix, double *model);
+
+/* ------------------------------------------------------------------------------------ */
+/* Geometry of the primitive renderables (9 floats per triangle)                          */
+/* ------------------------------------------------------------------------------------ */
+RUF_API int ruf_box_triangles(float dimx, float dimy, float dimz, float *out);      /* 12, renderable.cpp:135-164 */
+RUF_API int ruf_cube_triangles(float size, float *out);                             /* 12, glutSolidCube :129 */
+RUF_API int ruf_sphere_triangles(float radius, int slices, int stacks, float *out); /* glutSolidSphere :83 */
+RUF_API int ruf_cylinder_triangles(float radius, float height, int slices, int stacks, float *out); /* :96 */
+RUF_API int ruf_sphere_triangle_count(int slices, int stacks);
+RUF_API int ruf_cylinder_triangle_count(int slices, int stacks);
+
+RUF_API const char *ruf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUF_B200_H */

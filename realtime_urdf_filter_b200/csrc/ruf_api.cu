@@ -1,0 +1,477 @@
+// ruf_api.cu -- the extern "C" boundary of libruf_b200.so (include/ruf_b200.h): context,
+// device memory, streams, host<->device staging and the launch sequence.  No arithmetic of the
+// path lives here except the three scalar shader constants.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ruf_b200.h"
+#include "ruf_device.cuh"
+
+using namespace ruf;
+
+struct ruf_context {
+  int device = 0;
+  int W = 0, H = 0;
+  double z_near = 0.1, z_far = 8.0;
+  std::string err;
+
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;       // copy streams of the host-batch pipeline
+
+  // model
+  long long n_tris = 0;
+  int n_parts = 0;
+  float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;
+
+  // workspace
+  int max_batch = 0;            // frames the workspace is sized for
+  int want_batch = 0;           // set by ruf_reserve
+  long long want_rec = 0, want_bin = 0;
+  Dims dims{};
+  Workspace ws{};
+  double *d_lookat = nullptr;
+
+  // host-call staging (device side + pinned side)
+  int stage_frames = 0;         // frames per staging slot
+  void *d_in[2] = {nullptr, nullptr};
+  void *d_out[2] = {nullptr, nullptr};
+  uint8_t *d_mask[2] = {nullptr, nullptr};
+  double *d_mats[2] = {nullptr, nullptr};
+  double *h_mats[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2]{}, ev_k[2]{}, ev_out[2]{};
+  uint32_t *h_status = nullptr;  // pinned
+
+  ruf_stats stats{};
+  int last_frames = 0;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(ruf_context *c, int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define RUF_CUDA(c, call)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail((c), RUF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+static void free_workspace(ruf_context *c)
+{
+  cudaFree(c->ws.mvp); cudaFree(c->ws.ctr); cudaFree(c->ws.recs); cudaFree(c->ws.big); cudaFree(c->ws.bins);
+  c->ws.mvp = nullptr; c->ws.ctr = nullptr; c->ws.recs = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
+  c->max_batch = 0;
+}
+
+static void free_staging(ruf_context *c)
+{
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(c->d_in[i]); cudaFree(c->d_out[i]); cudaFree(c->d_mask[i]); cudaFree(c->d_mats[i]);
+    if (c->h_mats[i]) cudaFreeHost(c->h_mats[i]);
+    c->d_in[i] = c->d_out[i] = nullptr; c->d_mask[i] = nullptr; c->d_mats[i] = nullptr; c->h_mats[i] = nullptr;
+  }
+  c->stage_frames = 0;
+}
+
+static int ensure_workspace(ruf_context *c, int frames)
+{
+  if (c->n_tris < 0 || !c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  if (frames < c->want_batch) frames = c->want_batch;
+  const long long base_rec = c->n_tris + 2 + c->n_tris / 8 + 4096;
+  long long cap_rec = c->want_rec > 0 ? c->want_rec : base_rec;
+  long long cap_bin = c->want_bin > 0 ? c->want_bin : 2 * cap_rec + 32LL * c->dims.ntiles;
+  if (cap_rec > 0x7fffffffLL || cap_bin > 0x7fffffffLL) return fail(c, RUF_ERR_INVALID, "capacity too large");
+  if (c->max_batch >= frames && c->dims.cap_rec == (uint32_t)cap_rec && c->dims.cap_bin == (uint32_t)cap_bin)
+    return RUF_OK;
+  RUF_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_workspace(c);
+  c->dims.cap_rec = (uint32_t)cap_rec;
+  c->dims.cap_bin = (uint32_t)cap_bin;
+  c->dims.ctr_stride = (uint32_t)((kCtrTiles + 3 * c->dims.ntiles + 3) & ~3);
+  const size_t f = (size_t)frames;
+  RUF_CUDA(c, cudaMalloc(&c->ws.mvp, f * (c->n_parts + 1) * 16 * sizeof(float)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * c->dims.ctr_stride * sizeof(uint32_t)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.recs, f * cap_rec * sizeof(TriRec)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.big, f * kBigCapacity * sizeof(TriRec)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * cap_bin * sizeof(TriRec)));
+  c->max_batch = frames;
+  return RUF_OK;
+}
+
+static size_t elem_size(int enc) { return enc == RUF_ENC_U16_MM ? 2 : 4; }
+
+static int ensure_staging(ruf_context *c, int frames)
+{
+  if (c->stage_frames >= frames) return RUF_OK;
+  RUF_CUDA(c, cudaDeviceSynchronize());
+  free_staging(c);
+  const size_t px = (size_t)c->W * c->H * frames;
+  const size_t mats = (size_t)(16 + 16 * (size_t)frames * (1 + c->n_parts)) * sizeof(double);
+  for (int i = 0; i < 2; ++i) {
+    RUF_CUDA(c, cudaMalloc(&c->d_in[i], px * 4));
+    RUF_CUDA(c, cudaMalloc(&c->d_out[i], px * 4));
+    RUF_CUDA(c, cudaMalloc(&c->d_mask[i], px));
+    RUF_CUDA(c, cudaMalloc(&c->d_mats[i], mats));
+    RUF_CUDA(c, cudaHostAlloc(&c->h_mats[i], mats, cudaHostAllocDefault));
+  }
+  c->stage_frames = frames;
+  return RUF_OK;
+}
+
+static ShaderParams shader_params(const ruf_context *c, float max_diff, float replace_value)
+{
+  // to_linear_depth of include/shaders/urdf_filter.frag:14-17 with the float uniforms z_near/z_far
+  const float zn = (float)c->z_near, zf = (float)c->z_far;
+  volatile float a = zn * zf, b = zn - zf, e = zf - zn;
+  ShaderParams sp;
+  sp.k1 = a / b;
+  sp.k2 = zf / e;
+  sp.max_diff = max_diff;
+  sp.replace_value = replace_value;
+  return sp;
+}
+
+static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const double *d_proj,
+                  const double *d_view, const double *d_model, float max_diff, float replace_value,
+                  void *d_out, uint8_t *d_mask, float *d_zbuf, cudaStream_t s)
+{
+  FrameBuffers fb;
+  fb.depth_in = d_in; fb.depth_out = d_out; fb.mask_out = d_mask; fb.zbuf_out = d_zbuf;
+  const uintptr_t al = (uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_zbuf;
+  fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (((uintptr_t)d_mask & 7) == 0);
+  const ShaderParams sp = shader_params(c, max_diff, replace_value);
+  Model m{c->v0, c->v1, c->v2};
+  const float bg_z = (float)(c->z_far * 0.99);   // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
+  int launches = 0;
+  cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, bg_z, enc,
+                                sp, fb, s, &launches);
+  if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  c->stats.kernel_launches += launches;
+  return RUF_OK;
+}
+
+extern "C" {
+
+int ruf_create(ruf_context **out, int device, int width, int height, double z_near, double z_far)
+{
+  if (!out) return fail(nullptr, RUF_ERR_INVALID, "ctx is NULL");
+  *out = nullptr;
+  if (width < 1 || height < 1 || width > 4096 || height > 4096)
+    return fail(nullptr, RUF_ERR_INVALID, "image size %dx%d outside 1..4096", width, height);
+  if (!(z_near > 0.0) || !(z_far > z_near)) return fail(nullptr, RUF_ERR_INVALID, "need 0 < z_near < z_far");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, RUF_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, RUF_ERR_INVALID, "device %d out of range", device);
+  ruf_context *c = new (std::nothrow) ruf_context;
+  if (!c) return fail(nullptr, RUF_ERR_NOMEM, "out of host memory");
+  c->device = device; c->W = width; c->H = height; c->z_near = z_near; c->z_far = z_far;
+  auto bail = [&](const char *what, cudaError_t err) {
+    int rc = fail(nullptr, RUF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    ruf_destroy(c);
+    return rc;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = check_kernel_image()) != cudaSuccess)
+    return bail("no sm_100a kernel image for this device (libruf_b200 targets B200 only)", e);
+  if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  c->stream = c->own_stream;
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  }
+  if ((e = cudaMalloc(&c->ws.status, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(c->ws.status, 0, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaHostAlloc(&c->h_status, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  *c->h_status = 0;
+  double la[16];
+  ruf_lookat(la);
+  if ((e = cudaMalloc(&c->d_lookat, sizeof(la))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemcpy(c->d_lookat, la, sizeof(la), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+
+  Dims &d = c->dims;
+  d.W = width; d.H = height;
+  d.tiles_x = (width + kTileW - 1) / kTileW;
+  d.tiles_y = (height + kTileH - 1) / kTileH;
+  d.ntiles = d.tiles_x * d.tiles_y;
+  d.halfw = 0.5f * (float)width;
+  d.halfh = 0.5f * (float)height;
+  d.guard_x = kGuardPx / d.halfw;
+  d.guard_y = kGuardPx / d.halfh;
+  d.n_tris = -1;
+  *out = c;
+  return RUF_OK;
+}
+
+int ruf_destroy(ruf_context *c)
+{
+  if (!c) return RUF_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_workspace(c);
+  free_staging(c);
+  cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2);
+  cudaFree(c->ws.status); cudaFree(c->d_lookat);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+  }
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  delete c;
+  return RUF_OK;
+}
+
+const char *ruf_last_error(const ruf_context *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int ruf_set_stream(ruf_context *c, void *cuda_stream)
+{
+  if (!c) return RUF_ERR_INVALID;
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return RUF_OK;
+}
+
+static int check_status(ruf_context *c, cudaStream_t s)
+{
+  RUF_CUDA(c, cudaMemcpyAsync(c->h_status, c->ws.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  RUF_CUDA(c, cudaStreamSynchronize(s));
+  const uint32_t flags = *c->h_status;
+  if (flags) {
+    RUF_CUDA(c, cudaMemsetAsync(c->ws.status, 0, sizeof(uint32_t), s));
+    // grow so that the caller's retry fits
+    if (flags & kFlagRecOverflow) c->want_rec = 2LL * c->dims.cap_rec;
+    c->want_bin = 2LL * c->dims.cap_bin;
+    return fail(c, RUF_ERR_OVERFLOW, "internal %s buffer overflow (capacity doubled for the next call)",
+                (flags & kFlagRecOverflow) ? "record" : "bin");
+  }
+  return RUF_OK;
+}
+
+int ruf_sync(ruf_context *c)
+{
+  if (!c) return RUF_ERR_INVALID;
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  return check_status(c, c->stream);
+}
+
+static int set_model_common(ruf_context *c, const float *d_xyz, const uint32_t *d_part, int64_t n_tris, int n_parts)
+{
+  cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2);
+  c->v0 = c->v1 = c->v2 = nullptr;
+  const size_t n = (size_t)(n_tris > 0 ? n_tris : 1);
+  RUF_CUDA(c, cudaMalloc(&c->v0, n * sizeof(float4)));
+  RUF_CUDA(c, cudaMalloc(&c->v1, n * sizeof(float4)));
+  RUF_CUDA(c, cudaMalloc(&c->v2, n * sizeof(float4)));
+  cudaError_t e = launch_pack_model(d_xyz, d_part, n_tris, c->v0, c->v1, c->v2, c->stream);
+  if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "pack kernel: %s", cudaGetErrorString(e));
+  RUF_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_tris = n_tris; c->n_parts = n_parts;
+  c->dims.n_tris = n_tris; c->dims.n_parts = n_parts;
+  free_workspace(c);
+  free_staging(c);
+  c->want_rec = c->want_bin = 0;
+  return RUF_OK;
+}
+
+int ruf_set_model(ruf_context *c, const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (n_tris < 0 || n_parts < 0 || n_parts > (1 << 20) || (n_tris > 0 && (!tri_xyz || !tri_part)) || n_tris > (1LL << 30))
+    return fail(c, RUF_ERR_INVALID, "bad model arguments");
+  for (int64_t t = 0; t < n_tris; ++t)
+    if (tri_part[t] >= (uint32_t)n_parts) return fail(c, RUF_ERR_INVALID, "tri_part[%lld] = %u >= n_parts", (long long)t, tri_part[t]);
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  float *d_xyz = nullptr; uint32_t *d_part = nullptr;
+  if (n_tris > 0) {
+    RUF_CUDA(c, cudaMalloc(&d_xyz, (size_t)n_tris * 9 * sizeof(float)));
+    RUF_CUDA(c, cudaMalloc(&d_part, (size_t)n_tris * sizeof(uint32_t)));
+    RUF_CUDA(c, cudaMemcpy(d_xyz, tri_xyz, (size_t)n_tris * 9 * sizeof(float), cudaMemcpyHostToDevice));
+    RUF_CUDA(c, cudaMemcpy(d_part, tri_part, (size_t)n_tris * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  int rc = set_model_common(c, d_xyz, d_part, n_tris, n_parts);
+  cudaFree(d_xyz); cudaFree(d_part);
+  return rc;
+}
+
+int ruf_set_model_device(ruf_context *c, const void *d_tri_xyz, const void *d_tri_part, int64_t n_tris, int n_parts)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (n_tris < 0 || n_parts < 0 || (n_tris > 0 && (!d_tri_xyz || !d_tri_part)) || n_tris > (1LL << 30))
+    return fail(c, RUF_ERR_INVALID, "bad model arguments");
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  return set_model_common(c, (const float *)d_tri_xyz, (const uint32_t *)d_tri_part, n_tris, n_parts);
+}
+
+int ruf_reserve(ruf_context *c, int max_batch, int64_t rec_capacity, int64_t bin_capacity)
+{
+  if (!c || max_batch < 1 || max_batch > 65535) return c ? fail(c, RUF_ERR_INVALID, "max_batch out of range") : RUF_ERR_INVALID;
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  c->want_batch = max_batch;
+  c->want_rec = rec_capacity; c->want_bin = bin_capacity;
+  if (c->max_batch > max_batch) free_workspace(c);
+  return ensure_workspace(c, max_batch);
+}
+
+int ruf_filter_batch_device(ruf_context *c, int n_frames, const void *d_depth_in, int enc, const double *d_proj,
+                            const double *d_view, const double *d_part_model, float max_diff, float replace_value,
+                            void *d_depth_out, uint8_t *d_mask_out, float *d_zbuf_out)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (n_frames < 1 || !d_depth_in || !d_depth_out || !d_proj || !d_view || (c->n_parts > 0 && !d_part_model) ||
+      (enc != RUF_ENC_F32_M && enc != RUF_ENC_U16_MM))
+    return fail(c, RUF_ERR_INVALID, "bad arguments");
+  if (!c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  if (n_frames > 65535) return fail(c, RUF_ERR_INVALID, "n_frames > 65535");
+  int rc = ensure_workspace(c, n_frames);
+  if (rc != RUF_OK) return rc;
+  c->stats = ruf_stats{};
+  c->stats.frames = n_frames;
+  c->last_frames = n_frames;
+  return launch(c, n_frames, d_depth_in, enc, d_proj, d_view, d_part_model, max_diff, replace_value, d_depth_out,
+                d_mask_out, d_zbuf_out, c->stream);
+}
+
+// One pass of the chunked host pipeline.  Chunk k: H2D on s_in (slot k&1) -> kernels on the
+// context stream -> D2H on s_out.  Slots are recycled under event dependencies.
+static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int enc, const double *proj,
+                         const double *view, const double *part_model, float max_diff, float replace_value,
+                         void *depth_out, uint8_t *mask_out, int chunk)
+{
+  const size_t es = elem_size(enc);
+  const size_t img = (size_t)c->W * c->H;
+  const int P = c->n_parts;
+  const int nchunks = (n_frames + chunk - 1) / chunk;
+  cudaStream_t sk = c->stream;
+  for (int k = 0; k < nchunks; ++k) {
+    const int slot = k & 1;
+    const int f0 = k * chunk;
+    const int nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
+    if (k >= 2) {
+      // slot reuse: input slot free once chunk k-2's kernels ran; pinned matrices likewise
+      RUF_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_k[slot], 0));
+      RUF_CUDA(c, cudaEventSynchronize(c->ev_in[slot]));   // h_mats[slot] was consumed by its H2D
+    }
+    double *hm = c->h_mats[slot];
+    std::memcpy(hm, proj, 16 * sizeof(double));
+    std::memcpy(hm + 16, view + 16 * (size_t)f0, 16 * sizeof(double) * nf);
+    if (P > 0) std::memcpy(hm + 16 + 16 * (size_t)nf, part_model + 16 * (size_t)f0 * P, 16 * sizeof(double) * (size_t)nf * P);
+    const size_t mat_bytes = (16 + 16 * (size_t)nf * (1 + P)) * sizeof(double);
+    RUF_CUDA(c, cudaMemcpyAsync(c->d_mats[slot], hm, mat_bytes, cudaMemcpyHostToDevice, c->s_in));
+    RUF_CUDA(c, cudaMemcpyAsync(c->d_in[slot], (const char *)depth_in + f0 * img * es, nf * img * es,
+                                cudaMemcpyHostToDevice, c->s_in));
+    RUF_CUDA(c, cudaEventRecord(c->ev_in[slot], c->s_in));
+    c->stats.h2d_bytes += (int64_t)(mat_bytes + nf * img * es);
+
+    RUF_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[slot], 0));
+    if (k >= 2) RUF_CUDA(c, cudaStreamWaitEvent(sk, c->ev_out[slot], 0));   // output slot drained
+    double *dm = c->d_mats[slot];
+    int rc = launch(c, nf, c->d_in[slot], enc, dm, dm + 16, dm + 16 + 16 * (size_t)nf, max_diff, replace_value,
+                    c->d_out[slot], mask_out ? c->d_mask[slot] : nullptr, nullptr, sk);
+    if (rc != RUF_OK) return rc;
+    RUF_CUDA(c, cudaEventRecord(c->ev_k[slot], sk));
+
+    RUF_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[slot], 0));
+    RUF_CUDA(c, cudaMemcpyAsync((char *)depth_out + f0 * img * es, c->d_out[slot], nf * img * es,
+                                cudaMemcpyDeviceToHost, c->s_out));
+    c->stats.d2h_bytes += (int64_t)(nf * img * es);
+    if (mask_out) {
+      RUF_CUDA(c, cudaMemcpyAsync(mask_out + f0 * img, c->d_mask[slot], nf * img, cudaMemcpyDeviceToHost, c->s_out));
+      c->stats.d2h_bytes += (int64_t)(nf * img);
+    }
+    RUF_CUDA(c, cudaEventRecord(c->ev_out[slot], c->s_out));
+  }
+  RUF_CUDA(c, cudaStreamSynchronize(c->s_out));
+  return check_status(c, sk);
+}
+
+int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, int enc, const double *proj,
+                          const double *view, const double *part_model, float max_diff, float replace_value,
+                          void *depth_out, uint8_t *mask_out)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (n_frames < 1 || !depth_in || !depth_out || !proj || !view || (c->n_parts > 0 && !part_model) ||
+      (enc != RUF_ENC_F32_M && enc != RUF_ENC_U16_MM))
+    return fail(c, RUF_ERR_INVALID, "bad arguments");
+  if (!c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  int chunk = n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1);
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    int rc = ensure_workspace(c, chunk);
+    if (rc != RUF_OK) return rc;
+    rc = ensure_staging(c, chunk);
+    if (rc != RUF_OK) return rc;
+    c->stats = ruf_stats{};
+    c->stats.frames = n_frames;
+    c->last_frames = (n_frames % chunk) ? (n_frames % chunk) : chunk;
+    rc = host_pipeline(c, n_frames, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
+                       mask_out, chunk);
+    if (rc != RUF_ERR_OVERFLOW) return rc;   // overflow: capacities were doubled, run again
+  }
+  return fail(c, RUF_ERR_OVERFLOW, "internal buffers still too small after 8 attempts");
+}
+
+int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj, const double *view,
+               const double *part_model, float max_diff, float replace_value, void *depth_out, uint8_t *mask_out)
+{
+  return ruf_filter_batch_host(c, 1, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
+                               mask_out);
+}
+
+int ruf_host_alloc(void **ptr, size_t bytes)
+{
+  if (!ptr) return RUF_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(nullptr, RUF_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e));
+  return RUF_OK;
+}
+int ruf_host_free(void *ptr)
+{
+  if (ptr) cudaFreeHost(ptr);
+  return RUF_OK;
+}
+
+int ruf_get_stats(ruf_context *c, ruf_stats *out)
+{
+  if (!c || !out) return RUF_ERR_INVALID;
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  RUF_CUDA(c, cudaStreamSynchronize(c->stream));
+  ruf_stats s = c->stats;
+  s.visible_tris = s.binned_refs = s.big_tris = 0;
+  if (c->last_frames > 0 && c->ws.ctr) {
+    std::vector<uint32_t> h((size_t)c->last_frames * c->dims.ctr_stride);
+    RUF_CUDA(c, cudaMemcpy(h.data(), c->ws.ctr, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < c->last_frames; ++f) {
+      const uint32_t *p = h.data() + (size_t)f * c->dims.ctr_stride;
+      s.visible_tris += p[kCtrRec];
+      s.binned_refs += p[kCtrBinTotal];
+      s.big_tris += p[kCtrBig];
+    }
+  }
+  *out = s;
+  return RUF_OK;
+}
+
+}  // extern "C"
