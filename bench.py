@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""Benchmark of the URDF depth self-filter hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over RING x BATCH distinct synthetic 640x480 16UC1 depth
+frames of the PR2-like model (BASELINE.json configs[1]); each rank (GPU) processes its own
+stream of frames (weak scaling, no per-frame collective; the mesh, poses and frames are
+generated on rank 0 and broadcast once over NCCL at set-up).
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = frames/s
+through ruf_filter_batch_host with pinned HOST buffers (H2D + D2H inside the timed region);
+`roofline` = dominant kernel vs the measured HBM peak; `cpu_baseline` = the CPU oracle timed on
+this box's host cores on a bounded sample.
+
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/, OpenMP on
+all host threads) -- the reference's own GL path cannot run in this image (no libGL/Mesa/X11,
+DESIGN.md "Oracle").  This script, tests/ and __graft_entry__.smoke() are the only places
+allowed to execute oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "depth frames/sec at 640×480, PR2 URDF; achieved HBM GB/s vs peak"
+UNIT = "frames/s"
+W_IMG, H_IMG = 640, 480
+FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n_tris, n_parts, elem=2, mask=True):
+    """B = W*H*(b_in + b_out + b_mask) + T*36 + L*64 per frame."""
+    image = W_IMG * H_IMG * (elem + elem + (1 if mask else 0))
+    geometry = n_tris * 36 + n_parts * 64
+    return image, geometry
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: NVML polled from a thread during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.sm_max = None
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.thread:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the reference) on the host cores
+# --------------------------------------------------------------------------------------------
+def oracle_frames_per_s(sc, frames, depth, min_seconds, max_frames=100000):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as orc
+    from realtime_urdf_filter_b200 import synth
+    threads = orc.max_threads()
+    proj, _, _ = sc.proj()
+    views, pms = frames
+    mvps = [orc.compose_mvp(proj, views[i], pms[i], sc.n_parts) for i in range(len(views))]
+    zn, zf = np.float32(synth.Z_NEAR), np.float32(synth.Z_FAR)
+
+    def one(i):
+        j = i % len(mvps)
+        orc.filter_frame(depth[j], sc.tri, sc.tri_part, mvps[j], zn, zf, np.float32(sc.max_diff),
+                         np.float32(sc.replace_value), want_mask=True, nthreads=threads, native=True)
+    for i in range(2):
+        one(i)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        one(n)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or n >= max_frames:
+            break
+    return n / dt, threads, n, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: CPU oracle, all host threads, K steps of a bounded sample each."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as orc
+    from realtime_urdf_filter_b200 import synth
+    sc = synth.pr2_like_scene(W_IMG, H_IMG)
+    nf = 8
+    views, pms = sc.frames(list(range(nf)))
+    proj, _, _ = sc.proj()
+    threads = orc.max_threads()
+    zn, zf = np.float32(synth.Z_NEAR), np.float32(synth.Z_FAR)
+    mvps = [orc.compose_mvp(proj, views[i], pms[i], sc.n_parts) for i in range(nf)]
+    depth = []
+    for i in range(nf):
+        z = orc.render(sc.tri, sc.tri_part, mvps[i], W_IMG, H_IMG, np.float32(8.0 * 0.99),
+                       nthreads=threads, native=True)
+        depth.append(synth.synth_depth(synth.linear_depth(z), i, "u16"))
+    per_step = 16     # frames per step: bounded so that K steps finish in seconds
+
+    def step(s):
+        for i in range(per_step):
+            j = (s * per_step + i) % nf
+            orc.filter_frame(depth[j], sc.tri, sc.tri_part, mvps[j], zn, zf, np.float32(sc.max_diff),
+                             np.float32(sc.replace_value), want_mask=True, nthreads=threads, native=True)
+    for s in range(args.warmup):
+        step(s)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(s)
+    dt = time.perf_counter() - t0
+    fps = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i64 (u16 I/O)",
+        "data": "synthetic",
+        "config": {"workload": "640x480 16UC1 stream, PR2-like synthetic model "
+                               f"({sc.n_parts} parts, {sc.n_tris} triangles), mask on", "frames_per_step": per_step},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {per_step} frames, oracle/ruf_oracle.c -O3 -march=native, "
+                                   f"OpenMP over {threads} threads (the reference's GL path needs libGL/X11: absent)"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import realtime_urdf_filter_b200 as ruf
+    from realtime_urdf_filter_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, R = args.batch, args.ring
+    n_distinct = B                      # distinct poses / depth frames; ring slots hold rolled copies
+    ctx = ruf.Context(W_IMG, H_IMG, device=local_rank)
+    # a real (non-default) stream: torch events must sit on the stream the kernels run on, and the
+    # legacy default stream (handle 0) cannot be handed to ruf_set_stream (NULL = internal stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    assert stream.cuda_stream != 0
+
+    # ---- set-up on rank 0, one NCCL broadcast of mesh + poses + frames ----
+    hdr = torch.zeros(4, dtype=torch.int64, device=dev)
+    sc = None
+    if rank == 0:
+        sc = synth.pr2_like_scene(W_IMG, H_IMG)
+        views, pms = sc.frames(list(range(n_distinct)))
+        proj, _, _ = sc.proj()
+        hdr[:] = torch.tensor([sc.n_tris, sc.n_parts, 0, 0])
+    if world > 1:
+        dist.broadcast(hdr, 0)
+    T, P = int(hdr[0]), int(hdr[1])
+    d_tri = torch.empty((T, 9), dtype=torch.float32, device=dev)
+    d_part = torch.empty((T,), dtype=torch.int32, device=dev)
+    d_proj = torch.empty(16, dtype=torch.float64, device=dev)
+    d_views = torch.empty((n_distinct, 16), dtype=torch.float64, device=dev)
+    d_pms = torch.empty((n_distinct, P, 16), dtype=torch.float64, device=dev)
+    d_depth0 = torch.empty((n_distinct, H_IMG, W_IMG), dtype=torch.int16, device=dev)
+    if rank == 0:
+        d_tri.copy_(torch.from_numpy(sc.tri))
+        d_part.copy_(torch.from_numpy(sc.tri_part.view(np.int32)))
+        d_proj.copy_(torch.from_numpy(proj))
+        d_views.copy_(torch.from_numpy(views))
+        d_pms.copy_(torch.from_numpy(pms))
+    if world > 1:
+        for t in (d_tri, d_part, d_proj, d_views, d_pms):
+            dist.broadcast(t, 0)
+    torch.cuda.synchronize()
+    ctx.set_model_device(d_tri.data_ptr(), d_part.data_ptr(), T, P)
+    ctx.reserve(B)
+    max_diff, replace_value = 0.05, 5.0
+
+    # synthetic sensor frames from the virtual depth of the same poses (rank 0), then broadcast
+    if rank == 0:
+        d_z = torch.empty((n_distinct, H_IMG, W_IMG), dtype=torch.float32, device=dev)
+        d_tmp = torch.zeros((n_distinct, H_IMG, W_IMG), dtype=torch.int16, device=dev)
+        ctx.filter_batch_device(n_distinct, d_tmp.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_views.data_ptr(),
+                                d_pms.data_ptr(), max_diff, replace_value, d_depth0.data_ptr(), 0, d_z.data_ptr())
+        ctx.sync()
+        z = d_z.cpu().numpy()
+        frames_np = np.stack([synth.synth_depth(synth.linear_depth(z[i]), i, "u16") for i in range(n_distinct)])
+        d_depth0.copy_(torch.from_numpy(frames_np.view(np.int16)))
+        del d_z, d_tmp
+    if world > 1:
+        dist.broadcast(d_depth0, 0)
+
+    # ring of R batches at distinct addresses (R*B frames >> L2), contents rolled per slot
+    ring_in = torch.empty((R, B, H_IMG, W_IMG), dtype=torch.int16, device=dev)
+    ring_out = torch.empty_like(ring_in)
+    ring_mask = torch.empty((R, B, H_IMG, W_IMG), dtype=torch.uint8, device=dev)
+    ring_views = torch.empty((R, B, 16), dtype=torch.float64, device=dev)
+    ring_pms = torch.empty((R, B, P, 16), dtype=torch.float64, device=dev)
+    for r in range(R):
+        sh = (r * 7 + rank * 3) % n_distinct
+        ring_in[r] = torch.roll(d_depth0, sh, 0)
+        ring_views[r] = torch.roll(d_views, sh, 0)
+        ring_pms[r] = torch.roll(d_pms, sh, 0)
+    torch.cuda.synchronize()
+
+    def step():
+        for r in range(R):
+            ctx.filter_batch_device(B, ring_in[r].data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(),
+                                    ring_views[r].data_ptr(), ring_pms[r].data_ptr(), max_diff, replace_value,
+                                    ring_out[r].data_ptr(), ring_mask[r].data_ptr(), 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    ctx.set_profiling(True)
+    ctx.stage_times(reset=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    ctx.sync()        # raises on deferred overflow
+    stage_ms, seqs = ctx.stage_times(reset=True)
+    ctx.set_profiling(False)
+    stats = ctx.stats()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    frames_per_step = R * B
+    value = world * frames_per_step * args.steps / (ms * 1e-3)
+
+    # ---- e2e: pinned host buffers through ruf_filter_batch_host (H2D + D2H inside the region) ----
+    n_e2e = args.e2e_frames
+    h_in = torch.empty((n_e2e, H_IMG, W_IMG), dtype=torch.int16).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    h_mask = torch.empty((n_e2e, H_IMG, W_IMG), dtype=torch.uint8).pin_memory()
+    reps = (n_e2e + n_distinct - 1) // n_distinct
+    h_in.copy_(d_depth0.cpu().repeat(reps, 1, 1)[:n_e2e])
+    e_views = d_views.cpu().repeat(reps, 1)[:n_e2e].contiguous().numpy()
+    e_pms = d_pms.cpu().repeat(reps, 1, 1)[:n_e2e].contiguous().numpy()
+    e_proj = d_proj.cpu().numpy()
+    lib = ruf.load()
+
+    def e2e_step():
+        rc = lib.ruf_filter_batch_host(ctx._h, n_e2e, h_in.data_ptr(), ruf.ENC_U16_MM, e_proj.ctypes.data,
+                                       e_views.ctypes.data, e_pms.ctypes.data, max_diff, replace_value,
+                                       h_out.data_ptr(), h_mask.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.ruf_last_error(ctx._h).decode())
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    e2e_stats = ctx.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()          # synchronous: returns after the last D2H landed
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e2e * e2e_steps / float(e2e_s.item())
+    # sanity: the e2e output equals the device-path output for the same frames
+    same = bool(torch.equal(h_out[:B].to(dev), torch.roll(ring_out[0], -((rank * 3) % n_distinct), 0)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peak()
+    img_b, geo_b = algorithmic_bytes(T, P)
+    dom = max(stage_ms, key=stage_ms.get)
+    frames_timed = seqs * B
+    share = {k: v / max(sum(stage_ms.values()), 1e-12) for k, v in stage_ms.items()}
+    kernel_bytes = {"setup": geo_b, "raster_filter": img_b}.get(dom, img_b + geo_b)
+    dom_avg_ms = stage_ms[dom] / max(seqs, 1)
+    achieved = kernel_bytes * B / (dom_avg_ms * 1e-3) / 1e9
+    path_gbs = (img_b + geo_b) * frames_per_step * args.steps / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sc_cpu = sc
+        fps, threads, n, dt = oracle_frames_per_s(sc_cpu, (views, pms), frames_np, args.cpu_seconds)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n} frames of the same workload in {dt:.1f} s, oracle/ruf_oracle.c -O3 -march=native, "
+                         f"OpenMP over {threads} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+i64 (u16 I/O)", "data": "synthetic",
+        "config": {
+            "workload": f"640x480 16UC1 stream, PR2-like synthetic model ({P} parts, {T} triangles), mask on "
+                        "(BASELINE.json configs[1])",
+            "frames_per_step": frames_per_step, "frames_per_launch": B, "launch_sequences_per_step": R,
+            "l2_policy": f"inputs larger than L2: ring of {R} x {B} distinct-address frames = "
+                         f"{R * B * img_b / 1e6:.0f} MB of image traffic per step vs 126 MB L2",
+            "threshold_m": max_diff, "replace_value_m": replace_value, "near_far_m": [0.1, 8.0],
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
+                "frames_per_step": n_e2e, "steps": e2e_steps, "api": "ruf_filter_batch_host (pinned host buffers)",
+                "matches_device_path": same},
+        "gpu_launches": int(args.steps * R * 5),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": f"ruf_{dom}_kernel", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": kernel_bytes * B, "avg_launch_ms": dom_avg_ms,
+                     "kernel_share_of_step": share[dom],
+                     "stage_ms_per_launch": {k: v / max(seqs, 1) for k, v in stage_ms.items()},
+                     "path_achieved_gbs": path_gbs, "path_frac": path_gbs / peak,
+                     "path_bytes_per_frame": img_b + geo_b},
+        "cpu_baseline": cpu,
+        "clocks": clocks.summary(),
+        "stats_last_launch": {k: stats[k] for k in ("visible_tris", "binned_refs", "big_tris")},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per launch sequence")
+    ap.add_argument("--ring", type=int, default=16, help="launch sequences (distinct buffers) per step")
+    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__,
+               *sys.argv[1:]]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,7 +72,8 @@ RUF_API int ruf_destroy(ruf_context *ctx);
 RUF_API const char *ruf_last_error(const ruf_context *ctx);
 
 /* Use a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own
- * stream for all subsequent work.  NULL restores the internal stream. */
+ * stream for all subsequent work.  NULL restores the internal stream (so the legacy default
+ * stream, whose handle is 0, cannot be selected: pass a created stream). */
 RUF_API int ruf_set_stream(ruf_context *ctx, void *cuda_stream);
 RUF_API int ruf_sync(ruf_context *ctx);   /* wait; returns deferred RUF_ERR_OVERFLOW if any */
 
@@ -148,6 +149,14 @@ typedef struct ruf_stats {
   int64_t h2d_bytes, d2h_bytes;
 } ruf_stats;
 RUF_API int ruf_get_stats(ruf_context *ctx, ruf_stats *out);
+
+/* Per-kernel device timing (the analogue of the reference's gettimeofday bookkeeping around
+ * filter(), src/urdf_filter.cpp:239-266, but per stage and on the device).  When enabled every
+ * launch sequence is bracketed by CUDA events on the launching stream.  ruf_get_stage_times
+ * synchronises, then returns the accumulated milliseconds of the five kernels in launch order
+ * {pose, setup, scan, bin, raster+filter} and the number of launch sequences they cover. */
+RUF_API int ruf_set_profiling(ruf_context *ctx, int enable);
+RUF_API int ruf_get_stage_times(ruf_context *ctx, double *ms5, int64_t *calls, int reset);
 
 /* ------------------------------------------------------------------------------------ */
 /* Host-side matrices (double precision, same operation order as the reference + tf/GLU)  */

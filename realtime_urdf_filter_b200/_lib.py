@@ -59,6 +59,8 @@ SIGNATURES = {
     "ruf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ruf_host_free": (C.c_int, [C.c_void_p]),
     "ruf_get_stats": (C.c_int, [C.c_void_p, C.POINTER(RufStats)]),
+    "ruf_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "ruf_get_stage_times": (C.c_int, [C.c_void_p, _c_double_p, C.POINTER(C.c_int64), C.c_int]),
     "ruf_projection_matrix": (None, [_c_double_p, C.c_int, C.c_int, C.c_double, C.c_double, _c_double_p,
                                      _c_double_p, _c_double_p]),
     "ruf_lookat": (None, [_c_double_p]),
@@ -286,6 +288,18 @@ class Context:
             self._h, n_frames, C.c_void_p(d_depth_in), enc, C.c_void_p(d_proj), C.c_void_p(d_view),
             C.c_void_p(d_part_model or 0), max_diff, replace_value, C.c_void_p(d_depth_out),
             C.c_void_p(d_mask_out or 0), C.c_void_p(d_zbuf_out or 0)))
+
+    STAGES = ("pose", "setup", "scan", "bin", "raster_filter")
+
+    def set_profiling(self, enable: bool):
+        self._check(self._lib.ruf_set_profiling(self._h, int(enable)))
+
+    def stage_times(self, reset: bool = True):
+        """-> ({stage: accumulated ms}, launch sequences covered)."""
+        ms = np.zeros(5)
+        calls = C.c_int64(0)
+        self._check(self._lib.ruf_get_stage_times(self._h, _dp(ms), C.byref(calls), int(reset)))
+        return dict(zip(self.STAGES, ms.tolist())), calls.value
 
     def stats(self) -> dict:
         s = RufStats()

@@ -47,6 +47,13 @@ struct ruf_context {
 
   ruf_stats stats{};
   int last_frames = 0;
+
+  // optional per-kernel timing (ruf_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;     // 6 events per recorded launch sequence
+  size_t ev_used = 0;                   // events in use since the last ruf_get_stage_times
+  double stage_ms[kNumStages] = {0, 0, 0, 0, 0};
+  int64_t stage_calls = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -157,8 +164,20 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
   Model m{c->v0, c->v1, c->v2};
   const float bg_z = (float)(c->z_far * 0.99);   // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
   int launches = 0;
+  cudaEvent_t *ev = nullptr;
+  if (c->profiling) {
+    if (c->ev_used + 6 > c->ev_pool.size()) {
+      for (int i = 0; i < 6; ++i) {
+        cudaEvent_t x;
+        if (cudaEventCreate(&x) != cudaSuccess) return fail(c, RUF_ERR_CUDA, "cudaEventCreate failed");
+        c->ev_pool.push_back(x);
+      }
+    }
+    ev = c->ev_pool.data() + c->ev_used;
+    c->ev_used += 6;
+  }
   cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, bg_z, enc,
-                                sp, fb, s, &launches);
+                                sp, fb, s, &launches, ev);
   if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   c->stats.kernel_launches += launches;
   return RUF_OK;
@@ -237,6 +256,7 @@ int ruf_destroy(ruf_context *c)
     if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
   }
+  for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -438,6 +458,36 @@ int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj
 {
   return ruf_filter_batch_host(c, 1, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
                                mask_out);
+}
+
+int ruf_set_profiling(ruf_context *c, int enable)
+{
+  if (!c) return RUF_ERR_INVALID;
+  c->profiling = enable != 0;
+  return RUF_OK;
+}
+
+int ruf_get_stage_times(ruf_context *c, double *ms, int64_t *calls, int reset)
+{
+  if (!c || !ms) return RUF_ERR_INVALID;
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  RUF_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i + 6 <= c->ev_used; i += 6) {
+    for (int k = 0; k < kNumStages; ++k) {
+      float t = 0.f;
+      RUF_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[i + k], c->ev_pool[i + k + 1]));
+      c->stage_ms[k] += t;
+    }
+    ++c->stage_calls;
+  }
+  c->ev_used = 0;
+  for (int k = 0; k < kNumStages; ++k) ms[k] = c->stage_ms[k];
+  if (calls) *calls = c->stage_calls;
+  if (reset) {
+    for (int k = 0; k < kNumStages; ++k) c->stage_ms[k] = 0;
+    c->stage_calls = 0;
+  }
+  return RUF_OK;
 }
 
 int ruf_host_alloc(void **ptr, size_t bytes)

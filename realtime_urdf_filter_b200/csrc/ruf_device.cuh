@@ -32,6 +32,7 @@ constexpr int kBigTiles = 12;                   // bbox touching more tiles -> p
 constexpr int kBigCapacity = 1024;              // entries of the per-frame big list
 constexpr int kSmallArea = 48;                  // clipped bbox area handled by one lane
 
+constexpr int kNumStages = 5;                   // pose, setup, scan, bin, raster+filter
 constexpr uint32_t kFlagRecOverflow = 1u;
 constexpr uint32_t kFlagBinOverflow = 2u;
 
@@ -102,6 +103,7 @@ cudaError_t launch_pack_model(const float *d_tri_xyz, const uint32_t *d_tri_part
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
                           const double *d_proj, const double *d_view, const double *d_part_model,
                           const double *d_lookat, float bg_z, int enc, const ShaderParams &sp,
-                          const FrameBuffers &fb, cudaStream_t s, int *n_launches);
+                          const FrameBuffers &fb, cudaStream_t s, int *n_launches,
+                          cudaEvent_t *stage_events /* null or 6 events: before K0, after K0..K4 */);
 
 }  // namespace ruf

@@ -723,25 +723,29 @@ cudaError_t check_kernel_image()
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
                           const double *d_proj, const double *d_view, const double *d_part_model,
                           const double *d_lookat, float bg_z, int enc, const ShaderParams &sp,
-                          const FrameBuffers &fb, cudaStream_t s, int *n_launches)
+                          const FrameBuffers &fb, cudaStream_t s, int *n_launches, cudaEvent_t *ev)
 {
   cudaError_t err;
   int launches = 0;
   err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_frames * d.ctr_stride * sizeof(uint32_t), s);
   if (err != cudaSuccess) return err;
+  if (ev) cudaEventRecord(ev[0], s);
   {
     long long total = (long long)n_frames * (d.n_parts + 1) * 16;
     unsigned blocks = (unsigned)((total + 255) / 256);
     ruf_pose_kernel<<<blocks, 256, 0, s>>>(d_proj, d_view, d_part_model, d_lookat, d.n_parts, n_frames, ws.mvp);
     ++launches;
+    if (ev) cudaEventRecord(ev[1], s);
   }
   {
     dim3 grid((unsigned)((d.n_tris + 2 + 255) / 256), (unsigned)n_frames);
     ruf_setup_kernel<<<grid, 256, 0, s>>>(m, ws.mvp, d, bg_z, ws.recs, ws.big, ws.ctr);
     ++launches;
+    if (ev) cudaEventRecord(ev[2], s);
   }
   ruf_scan_kernel<<<(unsigned)n_frames, 256, 0, s>>>(d, ws.ctr, ws.status);
   ++launches;
+  if (ev) cudaEventRecord(ev[3], s);
   {
     unsigned per_frame = (unsigned)((d.cap_rec + 255) / 256);
     if (per_frame > 48) per_frame = 48;
@@ -749,6 +753,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     dim3 grid(per_frame, (unsigned)n_frames);
     ruf_bin_kernel<<<grid, 256, 0, s>>>(d, ws.recs, ws.bins, ws.ctr);
     ++launches;
+    if (ev) cudaEventRecord(ev[4], s);
   }
   {
     dim3 grid((unsigned)d.ntiles, (unsigned)n_frames);
@@ -757,6 +762,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     else
       ruf_raster_filter_kernel<0><<<grid, kRasterThreads, 0, s>>>(d, ws.big, ws.bins, ws.ctr, sp, fb);
     ++launches;
+    if (ev) cudaEventRecord(ev[5], s);
   }
   if (n_launches) *n_launches = launches;
   return cudaGetLastError();

@@ -424,11 +424,15 @@ def synth_depth(virt_m, frame, enc="u16", bg_m=7.92):
     d += rng.normal(0.0, 0.003, d.shape)
     # occluder blobs: 5 % of the area as discs
     n_blobs = max(1, int(0.05 * H * W / (math.pi * 12 * 12)))
-    yy, xx = np.mgrid[0:H, 0:W]
+    rad = 12
+    oy, ox = np.mgrid[-rad:rad + 1, -rad:rad + 1]
+    disc = (oy * oy + ox * ox) <= rad * rad
     for _ in range(n_blobs):
-        cy, cx = rng.integers(0, H), rng.integers(0, W)
-        m = (yy - cy) ** 2 + (xx - cx) ** 2 <= 12 * 12
-        d[m] = np.maximum(0.2, d[m] - 0.3)
+        cy, cx = int(rng.integers(0, H)), int(rng.integers(0, W))
+        y0, y1, x0, x1 = max(cy - rad, 0), min(cy + rad + 1, H), max(cx - rad, 0), min(cx + rad + 1, W)
+        m = disc[y0 - cy + rad:y1 - cy + rad, x0 - cx + rad:x1 - cx + rad]
+        sub = d[y0:y1, x0:x1]
+        sub[m] = np.maximum(0.2, sub[m] - 0.3)
     far = rng.random(d.shape) < 0.02
     d[far] = rng.uniform(7.9, 9.5, int(far.sum()))
     invalid = rng.random(d.shape) < 0.10

@@ -47,8 +47,10 @@ def test_zbuf_bit_exact_device_batch():
     d_proj = torch.from_numpy(proj).to(dev)
     d_view = torch.from_numpy(np.stack([f["view"] for f in frames])).to(dev)
     d_pm = torch.from_numpy(np.stack([f["pm"] for f in frames])).to(dev)
-    with _ctx(sc) as ctx:
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)
+    stream.wait_stream(torch.cuda.current_stream())
+    with _ctx(sc) as ctx, torch.cuda.stream(stream):
+        ctx.set_stream(stream.cuda_stream)
         ctx.filter_batch_device(len(ks), d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(),
                                 d_pm.data_ptr(), sc.max_diff, sc.replace_value, d_out.data_ptr(),
                                 d_mask.data_ptr(), d_z.data_ptr())
