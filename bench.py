@@ -215,32 +215,18 @@ def run_b200(args, rank, world, local_rank):
     ctx.set_stream(stream.cuda_stream)
     assert stream.cuda_stream != 0
 
-    # ---- set-up on rank 0, one NCCL broadcast of mesh + poses + frames ----
-    hdr = torch.zeros(4, dtype=torch.int64, device=dev)
-    sc = None
+    # ---- set-up on rank 0, then one NCCL broadcast per static buffer (mesh, poses) ----
+    from realtime_urdf_filter_b200 import sharding
+    sc, arrays = None, None
     if rank == 0:
         sc = synth.pr2_like_scene(W_IMG, H_IMG)
         views, pms = sc.frames(list(range(n_distinct)))
         proj, _, _ = sc.proj()
-        hdr[:] = torch.tensor([sc.n_tris, sc.n_parts, 0, 0])
-    if world > 1:
-        dist.broadcast(hdr, 0)
-    T, P = int(hdr[0]), int(hdr[1])
-    d_tri = torch.empty((T, 9), dtype=torch.float32, device=dev)
-    d_part = torch.empty((T,), dtype=torch.int32, device=dev)
-    d_proj = torch.empty(16, dtype=torch.float64, device=dev)
-    d_views = torch.empty((n_distinct, 16), dtype=torch.float64, device=dev)
-    d_pms = torch.empty((n_distinct, P, 16), dtype=torch.float64, device=dev)
+        arrays = {"tri": sc.tri, "tri_part": sc.tri_part.view(np.int32), "proj": proj, "views": views, "pms": pms}
+    got = sharding.broadcast_arrays(arrays, 0, dev, rank)
+    d_tri, d_part, d_proj, d_views, d_pms = got["tri"], got["tri_part"], got["proj"], got["views"], got["pms"]
+    T, P = int(d_tri.shape[0]), int(d_pms.shape[1])
     d_depth0 = torch.empty((n_distinct, H_IMG, W_IMG), dtype=torch.int16, device=dev)
-    if rank == 0:
-        d_tri.copy_(torch.from_numpy(sc.tri))
-        d_part.copy_(torch.from_numpy(sc.tri_part.view(np.int32)))
-        d_proj.copy_(torch.from_numpy(proj))
-        d_views.copy_(torch.from_numpy(views))
-        d_pms.copy_(torch.from_numpy(pms))
-    if world > 1:
-        for t in (d_tri, d_part, d_proj, d_views, d_pms):
-            dist.broadcast(t, 0)
     torch.cuda.synchronize()
     ctx.set_model_device(d_tri.data_ptr(), d_part.data_ptr(), T, P)
     ctx.reserve(B)
@@ -258,7 +244,7 @@ def run_b200(args, rank, world, local_rank):
         d_depth0.copy_(torch.from_numpy(frames_np.view(np.int16)))
         del d_z, d_tmp
     if world > 1:
-        dist.broadcast(d_depth0, 0)
+        dist.broadcast(d_depth0.view(torch.uint8), 0)
 
     # ring of R batches at distinct addresses (R*B frames >> L2), contents rolled per slot
     ring_in = torch.empty((R, B, H_IMG, W_IMG), dtype=torch.int16, device=dev)

@@ -273,6 +273,21 @@ def example_scene(width=640, height=480):
                  label="urdf/example.urdf.xml, static pose")
 
 
+def example_urdf_xml():
+    """A URDF text equivalent to the reference's urdf/example.urdf.xml (two 4 x 0.5 x 2 box walls hanging
+    off `world` by fixed joints at (0,5,0), yaw +-pi/4), generated here rather than copied; it keeps the
+    stray '>' after </visual> that the original has, which a tolerant parser must skip."""
+    def wall(n):
+        return (f'  <link name="wall{n}">\n    <visual>\n      <geometry><box size="4 0.5 2" /></geometry>\n'
+                f'    </visual>>\n    <collision>\n      <geometry><box size="4 0.5 2" /></geometry>\n'
+                f'    </collision>>\n  </link>\n')
+    def joint(n, yaw):
+        return (f'  <joint name="wall{n}_joint" type="fixed">\n    <origin xyz="0 5 0" rpy="0 0 {yaw}"/>\n'
+                f'    <parent link="world"/>\n    <child link="wall{n}"/>\n  </joint>\n')
+    return ('<robot name="example">\n  <link name="world"/>\n' + wall(1) + wall(2) + joint(1, "0.785398163")
+            + joint(2, "-0.785398163") + '</robot>\n')
+
+
 # ------------------------------------------------------------------------------------------------
 # C2: PR2-like articulated robot
 # ------------------------------------------------------------------------------------------------

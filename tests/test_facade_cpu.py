@@ -1,0 +1,112 @@
+"""Host facade pieces that need no GPU: URDF subset parser, renderable construction (box F4 doubles,
+cylinder/sphere tessellation + suffix matrices, scale, ignore list, geometry_type), STL loader."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from realtime_urdf_filter_b200 import facade, synth
+
+
+def test_example_urdf_parts_match_scene():
+    tri, part, pm = facade.parse_urdf(synth.example_urdf_xml(), "visual")
+    sc = synth.example_scene()
+    assert np.array_equal(tri, sc.tri) and np.array_equal(part, sc.tri_part)
+    assert pm.shape == (4, 16)
+    # identity TF: part 0 = identity, part 1 = glScalef(4, 0.5, 2)
+    assert np.array_equal(pm[0], np.eye(4).reshape(-1))
+    assert np.array_equal(pm[1], synth.scale_suffix(4, 0.5, 2))
+
+
+def test_geometry_type_and_ignore_and_scale():
+    xml = synth.example_urdf_xml()
+    t_col, _, _ = facade.parse_urdf(xml, "collision")
+    assert len(t_col) == 48
+    t_ign, _, pm = facade.parse_urdf(xml, "", ignore=["wall2"])
+    assert len(t_ign) == 24 and pm.shape[0] == 2
+    t2, _, pm2 = facade.parse_urdf(xml, "visual", scale=0.5)
+    assert np.array_equal(t2[:12], orc.box_triangles(2, 0.25, 1))
+    assert np.array_equal(t2[12:24], orc.cube_triangles(2))
+    assert np.array_equal(pm2[1], synth.scale_suffix(2, 0.25, 1))
+    t_bad, _, _ = facade.parse_urdf(xml, "nonsense")        # ROS_FATAL + nothing rendered
+    assert len(t_bad) == 0
+
+
+def test_primitives_origin_and_suffix():
+    xml = """<?xml version="1.0"?>
+    <!-- comment -->
+    <robot name="p">
+      <link name="a"><visual><origin xyz="0.1 0.2 0.3" rpy="0.1 -0.2 0.3"/><geometry><cylinder radius="0.2" length="1.0"/></geometry></visual>
+                     <visual><geometry><sphere radius="0.25"/></geometry></visual></link>
+      <link name="b"/>
+    </robot>"""
+    tri, part, pm = facade.parse_urdf(xml, "visual")
+    assert len(tri) == 220 + 180 and pm.shape == (2, 16)
+    assert np.array_equal(tri[:220], orc.cylinder_triangles(0.2, 1.0))
+    assert np.array_equal(tri[220:], orc.sphere_triangles(0.25))
+    # cylinder: link_offset * glTranslatef(0,0,-length/2)
+    r, p, y = 0.1, -0.2, 0.3
+    R = synth.rpy_matrix(r, p, y)
+    M = pm[0].reshape(4, 4).T
+    assert np.allclose(M[:3, :3], R, atol=1e-12)
+    assert np.allclose(M[:3, 3], np.array([0.1, 0.2, 0.3]) + R @ np.array([0, 0, -0.5]), atol=1e-12)
+    # bit-exact against the oracle's link_model with the same quaternion
+    q = synth.quat_from_matrix(R)
+    want = orc.link_model((0, 0, 0, 1), (0, 0, 0), q, (0.1, 0.2, 0.3), synth.translate_suffix(0, 0, -0.5))
+    assert np.allclose(pm[0], want, atol=1e-15)
+
+
+def test_malformed_urdf_is_rejected():
+    for bad in ["", "<robot", "<notrobot/>", "<robot><link></link></robot>",
+                '<robot><link name="a"><visual><geometry><cone/></geometry></visual></link></robot>']:
+        with pytest.raises(ValueError):
+            facade.parse_urdf(bad)
+
+
+def _write_binary_stl(path, tris, header=b"binary"):
+    with open(path, "wb") as f:
+        f.write(header.ljust(80, b" "))
+        f.write(struct.pack("<I", len(tris)))
+        for t in tris:
+            f.write(struct.pack("<12fH", 0, 0, 1, *t, 0))
+
+
+def test_stl_loader_binary_ascii_and_solid_prefixed_binary(tmp_path):
+    tris = np.random.default_rng(3).normal(size=(7, 9)).astype(np.float32)
+    os.makedirs(tmp_path / "pkg" / "meshes")
+    _write_binary_stl(tmp_path / "pkg" / "meshes" / "a.stl", tris)
+    _write_binary_stl(tmp_path / "pkg" / "meshes" / "solid.stl", tris, header=b"solid but binary")   # README.md:121-141
+    with open(tmp_path / "pkg" / "meshes" / "ascii.stl", "w") as f:
+        f.write("solid x\n")
+        for t in tris:
+            f.write("facet normal 0 0 1\n outer loop\n")
+            for k in range(3):
+                f.write("  vertex %r %r %r\n" % tuple(float(v) for v in t[3 * k:3 * k + 3]))
+            f.write(" endloop\nendfacet\n")
+        f.write("endsolid x\n")
+    for name in ("a.stl", "solid.stl", "ascii.stl"):
+        xml = f'''<robot name="m"><link name="l"><visual><geometry>
+                  <mesh filename="package://pkg/meshes/{name}" scale="0.001 0.002 0.003"/></geometry></visual></link></robot>'''
+        tri, part, pm = facade.parse_urdf(xml, "", resource_root=str(tmp_path))
+        assert np.array_equal(tri, tris), name
+        assert np.array_equal(pm[0], synth.scale_suffix(np.float32(0.001), np.float32(0.002), np.float32(0.003)))
+    # a missing mesh logs an error and yields an empty renderable, it does not abort the model
+    xml = '<robot name="m"><link name="l"><visual><geometry><mesh filename="package://pkg/nope.stl"/></geometry></visual></link></robot>'
+    tri, _, pm = facade.parse_urdf(xml, "", resource_root=str(tmp_path))
+    assert len(tri) == 0 and pm.shape[0] == 1
+
+
+def test_constructor_reads_params_and_logs_fatal_on_missing():
+    with facade.FilterNode({"fixed_frame": "/world", "camera_frame": "/cam", "depth_distance_threshold": 0.05,
+                            "filter_replace_value": 5.0}, []) as n:
+        assert n.get("depth_distance_threshold") == 0.05 and n.get("filter_replace_value") == 5.0
+        assert n.get("far_plane") == 8.0 and n.get("near_plane") == 0.1
+        assert "FATAL" not in n.log()
+        g = n.projection(640, 480, [525, 0, 319.5, -39.375, 0, 525, 239.5, 0, 0, 0, 1, 0])
+        assert np.array_equal(g, orc.projection_matrix([525, 0, 319.5, -39.375, 0, 525, 239.5, 0, 0, 0, 1, 0], 640, 480)[0])
+        assert n.get("camera_tx") == 0.075
+    with facade.FilterNode({}, []) as n:          # missing required params: FATAL logs, construction continues
+        log = n.log()
+        assert log.count("FATAL") == 3 and n.get("filter_replace_value") == 0.0

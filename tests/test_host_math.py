@@ -1,0 +1,69 @@
+"""Product host-side matrices and tessellations (libruf_b200.so, CPU code) against the oracle,
+bit for bit.  These are the doubles the reference computes on the host before glMultMatrixd."""
+import numpy as np
+
+import oracle_py as orc
+import realtime_urdf_filter_b200 as ruf
+from realtime_urdf_filter_b200 import synth
+
+
+def _rq(rng):
+    q = rng.normal(size=4)
+    return q / np.linalg.norm(q)
+
+
+def test_projection_lookat_bit_exact():
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        P = np.zeros(12)
+        P[0], P[5], P[2], P[6] = rng.uniform(200, 1200, 2).tolist() + rng.uniform(100, 900, 2).tolist()
+        P[3], P[7] = rng.uniform(-50, 50, 2)
+        W, H = int(rng.integers(64, 2000)), int(rng.integers(64, 1200))
+        a, atx, aty = ruf.projection_matrix(P, W, H)
+        b, btx, bty = orc.projection_matrix(P, W, H)
+        assert np.array_equal(a, b) and atx == btx and aty == bty
+    assert np.array_equal(ruf.lookat().view(np.uint64), orc.lookat().view(np.uint64))     # incl. signed zeros
+
+
+def test_view_and_part_model_bit_exact():
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        oq, cq, lq = _rq(rng), _rq(rng), _rq(rng)
+        fq = rng.normal(size=4) * rng.uniform(0.1, 3)      # un-normalised URDF origin quaternion
+        ot, ct, lt, ft = (rng.normal(size=3) for _ in range(4))
+        tx, ty = rng.normal(size=2) * 0.05
+        assert np.array_equal(ruf.view_matrix(oq, ot, cq, ct, tx, ty), orc.view_matrix(oq, ot, cq, ct, tx, ty))
+        sfx = synth.scale_suffix(*rng.uniform(0.001, 3, 3)) if rng.random() < 0.5 else None
+        assert np.array_equal(ruf.part_model(lq, lt, fq, ft, sfx), orc.link_model(lq, lt, fq, ft, sfx))
+
+
+def test_view_matrix_semantics():
+    # identity everything -> view == LookAt ; camera offset is applied inverted
+    v = ruf.view_matrix((0, 0, 0, 1), (0, 0, 0), (0, 0, 0, 1), (0, 0, 0))
+    assert np.array_equal(v, ruf.lookat())
+    v = ruf.view_matrix((0, 0, 0, 1), (1, 2, 3), (0, 0, 0, 1), (0, 0, 0)).reshape(4, 4).T
+    assert np.allclose(v[:3, 3], [1.0, -2.0, 3.0])      # LookAt * translate(-offset) = diag(-1,1,-1) * (-1,-2,-3)
+    # tx shifts the camera origin along its own x axis (src/urdf_filter.cpp:607-608)
+    v = ruf.view_matrix((0, 0, 0, 1), (0, 0, 0), (0, 0, 0, 1), (0, 0, 0), 0.075, 0.0).reshape(4, 4).T
+    assert np.allclose(v[:3, 3], [-0.075, 0.0, 0.0])
+
+
+def test_primitives_bit_exact():
+    for dims in [(4, 0.5, 2), (0.1, 0.2, 0.3), (1, 1, 1)]:
+        assert np.array_equal(ruf.box_triangles(*dims), orc.box_triangles(*dims))
+        assert np.array_equal(ruf.cube_triangles(dims[0]), orc.cube_triangles(dims[0]))
+    for r in (0.05, 0.3, 1.7):
+        assert np.array_equal(ruf.sphere_triangles(r), orc.sphere_triangles(r))
+        assert np.array_equal(ruf.cylinder_triangles(r, 2 * r + 0.1), orc.cylinder_triangles(r, 2 * r + 0.1))
+    assert ruf.sphere_triangles(1.0, 6, 4).shape[0] == 2 * 6 + 2 * 6 * 2
+    assert ruf.cylinder_triangles(1.0, 1.0, 5, 3).shape[0] == 2 * 5 + 2 * 5 * 3
+
+
+def test_synth_scenes_shape():
+    sc = synth.pr2_like_scene()
+    assert 85 <= sc.n_parts <= 92 and abs(sc.n_tris - 90000) <= 900     # ~88 parts, 90k +- 1 %
+    assert sc.tri_part.max() == sc.n_parts - 1
+    view, pm = sc.frame(0)
+    assert view.shape == (16,) and pm.shape == (sc.n_parts, 16)
+    ex = synth.example_scene()
+    assert ex.n_tris == 48 and ex.n_parts == 4
