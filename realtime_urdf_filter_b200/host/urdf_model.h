@@ -82,7 +82,7 @@ class URDFRenderer {
   const std::vector<RenderablePart> &parts() const { return parts_; }
   const std::vector<float> &triangles() const { return tri_; }          // 9 floats per triangle
   const std::vector<uint32_t> &triangle_parts() const { return tri_part_; }
-  size_t num_renderables() const { return link_q_.size(); }
+  size_t num_renderables() const { return renderable_name_.size(); }
   bool ok() const { return ok_; }
 
  private:
