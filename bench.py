@@ -340,7 +340,7 @@ def run_b200(args, rank, world, local_rank):
     dom = max(stage_ms, key=stage_ms.get)
     frames_timed = seqs * B
     share = {k: v / max(sum(stage_ms.values()), 1e-12) for k, v in stage_ms.items()}
-    kernel_bytes = {"setup": geo_b, "raster_filter": img_b}.get(dom, img_b + geo_b)
+    kernel_bytes = {"setup_bin": geo_b, "raster_filter": img_b}.get(dom, img_b + geo_b)
     dom_avg_ms = stage_ms[dom] / max(seqs, 1)
     achieved = kernel_bytes * B / (dom_avg_ms * 1e-3) / 1e9
     path_gbs = (img_b + geo_b) * frames_per_step * args.steps / (ms * 1e-3) / 1e9
@@ -375,7 +375,7 @@ def run_b200(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
                 "frames_per_step": n_e2e, "steps": e2e_steps, "api": "ruf_filter_batch_host (pinned host buffers)",
                 "matches_device_path": same},
-        "gpu_launches": int(args.steps * R * 5),
+        "gpu_launches": int(args.steps * R * 4),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": f"ruf_{dom}_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kernel_bytes * B, "avg_launch_ms": dom_avg_ms,

@@ -93,8 +93,8 @@ RUF_API int ruf_set_model_device(ruf_context *ctx, const void *d_tri_xyz, const 
                                  int64_t n_tris, int n_parts);
 
 /* Capacity control for device-resident batches: max frames per call, and (0 = automatic)
- * per-frame capacities of the internal visible-triangle and tile-bin buffers. */
-RUF_API int ruf_reserve(ruf_context *ctx, int max_batch, int64_t rec_capacity, int64_t bin_capacity);
+ * per-frame capacities of the internal big-triangle list and tile-reference buffer. */
+RUF_API int ruf_reserve(ruf_context *ctx, int max_batch, int64_t big_capacity, int64_t bin_capacity);
 
 /* ------------------------------------------------------------------------------------ */
 /* The per-frame path                                                                     */
@@ -143,7 +143,7 @@ RUF_API int ruf_host_free(void *ptr);
 typedef struct ruf_stats {
   int64_t frames;            /* frames in the last call                                  */
   int64_t kernel_launches;   /* kernels launched by the last call                        */
-  int64_t visible_tris;      /* sum over frames of window-space triangles kept by setup   */
+  int64_t visible_tris;      /* sum over frames of triangles kept (binned) by setup        */
   int64_t binned_refs;       /* sum over frames of (triangle, tile) references            */
   int64_t big_tris;          /* sum over frames of triangles routed to the per-frame list */
   int64_t h2d_bytes, d2h_bytes;
@@ -153,10 +153,10 @@ RUF_API int ruf_get_stats(ruf_context *ctx, ruf_stats *out);
 /* Per-kernel device timing (the analogue of the reference's gettimeofday bookkeeping around
  * filter(), src/urdf_filter.cpp:239-266, but per stage and on the device).  When enabled every
  * launch sequence is bracketed by CUDA events on the launching stream.  ruf_get_stage_times
- * synchronises, then returns the accumulated milliseconds of the five kernels in launch order
- * {pose, setup, scan, bin, raster+filter} and the number of launch sequences they cover. */
+ * synchronises, then returns the accumulated milliseconds of the four kernels in launch order
+ * {pose, setup+bin, raster+filter, status} and the number of launch sequences they cover. */
 RUF_API int ruf_set_profiling(ruf_context *ctx, int enable);
-RUF_API int ruf_get_stage_times(ruf_context *ctx, double *ms5, int64_t *calls, int reset);
+RUF_API int ruf_get_stage_times(ruf_context *ctx, double *ms4, int64_t *calls, int reset);
 
 /* ------------------------------------------------------------------------------------ */
 /* Host-side matrices (double precision, same operation order as the reference + tf/GLU)  */

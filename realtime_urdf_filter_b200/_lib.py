@@ -245,8 +245,8 @@ class Context:
                                                    int(n_tris), int(n_parts)))
         self.n_parts, self.n_tris = int(n_parts), int(n_tris)
 
-    def reserve(self, max_batch: int, rec_capacity: int = 0, bin_capacity: int = 0):
-        self._check(self._lib.ruf_reserve(self._h, max_batch, rec_capacity, bin_capacity))
+    def reserve(self, max_batch: int, big_capacity: int = 0, bin_capacity: int = 0):
+        self._check(self._lib.ruf_reserve(self._h, max_batch, big_capacity, bin_capacity))
 
     def _enc_dtype(self, enc):
         return np.uint16 if enc == ENC_U16_MM else np.float32
@@ -289,14 +289,14 @@ class Context:
             C.c_void_p(d_part_model or 0), max_diff, replace_value, C.c_void_p(d_depth_out),
             C.c_void_p(d_mask_out or 0), C.c_void_p(d_zbuf_out or 0)))
 
-    STAGES = ("pose", "setup", "scan", "bin", "raster_filter")
+    STAGES = ("pose", "setup_bin", "raster_filter", "status")
 
     def set_profiling(self, enable: bool):
         self._check(self._lib.ruf_set_profiling(self._h, int(enable)))
 
     def stage_times(self, reset: bool = True):
         """-> ({stage: accumulated ms}, launch sequences covered)."""
-        ms = np.zeros(5)
+        ms = np.zeros(len(self.STAGES))
         calls = C.c_int64(0)
         self._check(self._lib.ruf_get_stage_times(self._h, _dp(ms), C.byref(calls), int(reset)))
         return dict(zip(self.STAGES, ms.tolist())), calls.value

@@ -30,7 +30,7 @@ struct ruf_context {
   // workspace
   int max_batch = 0;            // frames the workspace is sized for
   int want_batch = 0;           // set by ruf_reserve
-  long long want_rec = 0, want_bin = 0;
+  long long want_big = 0, want_bin = 0;
   Dims dims{};
   Workspace ws{};
   double *d_lookat = nullptr;
@@ -50,9 +50,9 @@ struct ruf_context {
 
   // optional per-kernel timing (ruf_set_profiling)
   bool profiling = false;
-  std::vector<cudaEvent_t> ev_pool;     // 6 events per recorded launch sequence
+  std::vector<cudaEvent_t> ev_pool;     // kNumStages + 1 events per recorded launch sequence
   size_t ev_used = 0;                   // events in use since the last ruf_get_stage_times
-  double stage_ms[kNumStages] = {0, 0, 0, 0, 0};
+  double stage_ms[kNumStages] = {0, 0, 0, 0};
   int64_t stage_calls = 0;
 };
 
@@ -79,8 +79,8 @@ static int fail(ruf_context *c, int code, const char *fmt, ...)
 
 static void free_workspace(ruf_context *c)
 {
-  cudaFree(c->ws.mvp); cudaFree(c->ws.ctr); cudaFree(c->ws.recs); cudaFree(c->ws.big); cudaFree(c->ws.bins);
-  c->ws.mvp = nullptr; c->ws.ctr = nullptr; c->ws.recs = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
+  cudaFree(c->ws.mvp); cudaFree(c->ws.ctr); cudaFree(c->ws.table); cudaFree(c->ws.big); cudaFree(c->ws.bins);
+  c->ws.mvp = nullptr; c->ws.ctr = nullptr; c->ws.table = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
   c->max_batch = 0;
 }
 
@@ -98,22 +98,23 @@ static int ensure_workspace(ruf_context *c, int frames)
 {
   if (c->n_tris < 0 || !c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
   if (frames < c->want_batch) frames = c->want_batch;
-  const long long base_rec = c->n_tris + 2 + c->n_tris / 8 + 4096;
-  long long cap_rec = c->want_rec > 0 ? c->want_rec : base_rec;
-  long long cap_bin = c->want_bin > 0 ? c->want_bin : 2 * cap_rec + 32LL * c->dims.ntiles;
-  if (cap_rec > 0x7fffffffLL || cap_bin > 0x7fffffffLL) return fail(c, RUF_ERR_INVALID, "capacity too large");
-  if (c->max_batch >= frames && c->dims.cap_rec == (uint32_t)cap_rec && c->dims.cap_bin == (uint32_t)cap_bin)
+  // per-frame capacities: tile references (typically ~0.3 T; a triangle can reference up to kBigTiles
+  // tiles) and the big list; both grow by doubling after an overflow (check_status)
+  long long cap_bin = c->want_bin > 0 ? c->want_bin : c->n_tris + c->n_tris / 2 + 16LL * c->dims.ntiles + 4096;
+  long long cap_big = c->want_big > 0 ? c->want_big : 1024;
+  if (cap_big > 0x7fffffffLL || cap_bin > 0x7fffffffLL) return fail(c, RUF_ERR_INVALID, "capacity too large");
+  if (c->max_batch >= frames && c->dims.cap_big == (uint32_t)cap_big && c->dims.cap_bin == (uint32_t)cap_bin)
     return RUF_OK;
   RUF_CUDA(c, cudaStreamSynchronize(c->stream));
   free_workspace(c);
-  c->dims.cap_rec = (uint32_t)cap_rec;
+  c->dims.cap_big = (uint32_t)cap_big;
   c->dims.cap_bin = (uint32_t)cap_bin;
-  c->dims.ctr_stride = (uint32_t)((kCtrTiles + 3 * c->dims.ntiles + 3) & ~3);
+  c->dims.n_setup_ctas = (int)((c->n_tris + 2 + kSetupTris - 1) / kSetupTris);
   const size_t f = (size_t)frames;
   RUF_CUDA(c, cudaMalloc(&c->ws.mvp, f * (c->n_parts + 1) * 16 * sizeof(float)));
-  RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * c->dims.ctr_stride * sizeof(uint32_t)));
-  RUF_CUDA(c, cudaMalloc(&c->ws.recs, f * cap_rec * sizeof(TriRec)));
-  RUF_CUDA(c, cudaMalloc(&c->ws.big, f * kBigCapacity * sizeof(TriRec)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * kCtrWords * sizeof(uint32_t)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.table, f * c->dims.ntiles * c->dims.n_setup_ctas * sizeof(uint2)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.big, f * cap_big * sizeof(TriRec)));
   RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * cap_bin * sizeof(TriRec)));
   c->max_batch = frames;
   return RUF_OK;
@@ -166,15 +167,15 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
   int launches = 0;
   cudaEvent_t *ev = nullptr;
   if (c->profiling) {
-    if (c->ev_used + 6 > c->ev_pool.size()) {
-      for (int i = 0; i < 6; ++i) {
+    if (c->ev_used + kNumStages + 1 > c->ev_pool.size()) {
+      for (int i = 0; i < kNumStages + 1; ++i) {
         cudaEvent_t x;
         if (cudaEventCreate(&x) != cudaSuccess) return fail(c, RUF_ERR_CUDA, "cudaEventCreate failed");
         c->ev_pool.push_back(x);
       }
     }
     ev = c->ev_pool.data() + c->ev_used;
-    c->ev_used += 6;
+    c->ev_used += kNumStages + 1;
   }
   cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, bg_z, enc,
                                 sp, fb, s, &launches, ev);
@@ -237,6 +238,11 @@ int ruf_create(ruf_context **out, int device, int width, int height, double z_ne
   d.guard_x = kGuardPx / d.halfw;
   d.guard_y = kGuardPx / d.halfh;
   d.n_tris = -1;
+  if (d.ntiles > kMaxTiles || d.tiles_x > 256 || d.tiles_y > 256) {
+    fail(nullptr, RUF_ERR_INVALID, "image of %dx%d needs %d tiles (limit %d)", width, height, d.ntiles, kMaxTiles);
+    ruf_destroy(c);
+    return RUF_ERR_INVALID;
+  }
   *out = c;
   return RUF_OK;
 }
@@ -281,10 +287,10 @@ static int check_status(ruf_context *c, cudaStream_t s)
   if (flags) {
     RUF_CUDA(c, cudaMemsetAsync(c->ws.status, 0, sizeof(uint32_t), s));
     // grow so that the caller's retry fits
-    if (flags & kFlagRecOverflow) c->want_rec = 2LL * c->dims.cap_rec;
-    c->want_bin = 2LL * c->dims.cap_bin;
-    return fail(c, RUF_ERR_OVERFLOW, "internal %s buffer overflow (capacity doubled for the next call)",
-                (flags & kFlagRecOverflow) ? "record" : "bin");
+    if (flags & kFlagBigOverflow) c->want_big = 4LL * c->dims.cap_big;
+    if (flags & kFlagBinOverflow) c->want_bin = 2LL * c->dims.cap_bin;
+    return fail(c, RUF_ERR_OVERFLOW, "internal %s buffer overflow (capacity raised for the next call)",
+                (flags & kFlagBigOverflow) ? "big-list" : "tile-reference");
   }
   return RUF_OK;
 }
@@ -311,7 +317,7 @@ static int set_model_common(ruf_context *c, const float *d_xyz, const uint32_t *
   c->dims.n_tris = n_tris; c->dims.n_parts = n_parts;
   free_workspace(c);
   free_staging(c);
-  c->want_rec = c->want_bin = 0;
+  c->want_big = c->want_bin = 0;
   return RUF_OK;
 }
 
@@ -349,7 +355,7 @@ int ruf_reserve(ruf_context *c, int max_batch, int64_t rec_capacity, int64_t bin
   if (!c || max_batch < 1 || max_batch > 65535) return c ? fail(c, RUF_ERR_INVALID, "max_batch out of range") : RUF_ERR_INVALID;
   RUF_CUDA(c, cudaSetDevice(c->device));
   c->want_batch = max_batch;
-  c->want_rec = rec_capacity; c->want_bin = bin_capacity;
+  c->want_big = rec_capacity; c->want_bin = bin_capacity;
   if (c->max_batch > max_batch) free_workspace(c);
   return ensure_workspace(c, max_batch);
 }
@@ -472,7 +478,7 @@ int ruf_get_stage_times(ruf_context *c, double *ms, int64_t *calls, int reset)
   if (!c || !ms) return RUF_ERR_INVALID;
   RUF_CUDA(c, cudaSetDevice(c->device));
   RUF_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (size_t i = 0; i + 6 <= c->ev_used; i += 6) {
+  for (size_t i = 0; i + kNumStages + 1 <= c->ev_used; i += kNumStages + 1) {
     for (int k = 0; k < kNumStages; ++k) {
       float t = 0.f;
       RUF_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[i + k], c->ev_pool[i + k + 1]));
@@ -511,12 +517,12 @@ int ruf_get_stats(ruf_context *c, ruf_stats *out)
   ruf_stats s = c->stats;
   s.visible_tris = s.binned_refs = s.big_tris = 0;
   if (c->last_frames > 0 && c->ws.ctr) {
-    std::vector<uint32_t> h((size_t)c->last_frames * c->dims.ctr_stride);
+    std::vector<uint32_t> h((size_t)c->last_frames * kCtrWords);
     RUF_CUDA(c, cudaMemcpy(h.data(), c->ws.ctr, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (int f = 0; f < c->last_frames; ++f) {
-      const uint32_t *p = h.data() + (size_t)f * c->dims.ctr_stride;
-      s.visible_tris += p[kCtrRec];
-      s.binned_refs += p[kCtrBinTotal];
+      const uint32_t *p = h.data() + (size_t)f * kCtrWords;
+      s.visible_tris += p[kCtrKept];
+      s.binned_refs += p[kCtrRef];
       s.big_tris += p[kCtrBig];
     }
   }

@@ -2,12 +2,13 @@
 //
 // Pipeline per batch of frames (DESIGN.md "Kernels"):
 //   K0 ruf_pose_kernel      fp64  P * V_f * M_{f,p}  -> fp32 MVP table     (vertex-stage matrices)
-//   K1 ruf_setup_kernel     one thread / (frame, triangle): vertex shader, clip, viewport,
-//                           snap, setup, cull, count tile references
-//   K2 ruf_scan_kernel      per-frame exclusive scan of the tile counters
-//   K3 ruf_bin_kernel       copy each kept record into the bins of the tiles it touches
-//   K4 ruf_raster_filter_kernel   one CTA / (frame, 64x32 tile): TMA-staged bins -> smem
-//                           z-tile (min) -> fused fragment shader + encode + store
+//   K1 ruf_setup_bin_kernel one CTA / (frame, 512 triangles): vertex shader, clip, viewport, snap,
+//                           setup, cull; CTA-local tile binning in shared memory; tile-sorted
+//                           records + a (start,count) table entry per (tile, CTA)
+//   K2 ruf_raster_filter_kernel   one CTA / (frame, 64x32 tile): gathers its segments with bulk
+//                           async copies (TMA) into smem -> smem z-tile (min) -> fused fragment
+//                           shader + encode + store
+//   K3 ruf_status_kernel    folds per-frame overflow flags into the sticky status word
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,14 +27,21 @@ constexpr int kMaxPoly = 12;
 constexpr int kTileW = 64;
 constexpr int kTileH = 32;
 constexpr int kTilePix = kTileW * kTileH;       // 2048
-constexpr int kRasterThreads = 256;             // 8 pixels of one tile row per thread
-constexpr int kChunk = 256;                     // records per TMA stage (one per thread)
+constexpr int kRasterThreads = 256;             // consumer threads: 8 pixels of one tile row each
+constexpr int kRasterBlock = kRasterThreads + 32;   // + one producer warp (bulk async copies)
+constexpr int kChunk = 256;                     // records per ring stage (one per consumer thread)
+constexpr int kStages = 2;                      // ring depth (a stage is released as soon as its records sit in registers)
 constexpr int kBigTiles = 12;                   // bbox touching more tiles -> per-frame "big" list
-constexpr int kBigCapacity = 1024;              // entries of the per-frame big list
-constexpr int kSmallArea = 48;                  // clipped bbox area handled by one lane
+constexpr int kMaxUnits = 16;                   // row-block units (1 row x 8 samples) per record dealt to lanes;
+                                                // larger records are rasterised by the whole warp
+constexpr int kSetupThreads = 256;
+constexpr int kTrisPerThread = 2;
+constexpr int kSetupTris = kSetupThreads * kTrisPerThread;   // triangles per setup CTA
+constexpr int kSegCap = 512;                    // table entries gathered per round by a raster CTA
+constexpr int kMaxTiles = 4096;
 
-constexpr int kNumStages = 5;                   // pose, setup, scan, bin, raster+filter
-constexpr uint32_t kFlagRecOverflow = 1u;
+constexpr int kNumStages = 4;                   // pose, setup+bin, raster+filter, status
+constexpr uint32_t kFlagBigOverflow = 1u;
 constexpr uint32_t kFlagBinOverflow = 2u;
 
 // One window-space triangle after setup: 48 bytes = 3 x 16 B (bulk-copy granularity).
@@ -50,20 +58,17 @@ struct __align__(16) TriRec {
 };
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 
-// Per-frame counter block (uint32 words) inside the workspace.
-//   [0] kept records  [1] big-list entries  [2] total bin references  [3] flags
-//   [4 .. 4+nt)        tile reference counts
-//   [4+nt .. 4+2nt)    tile fill cursors
-//   [4+2nt .. 4+3nt)   tile offsets (exclusive scan)
-constexpr int kCtrRec = 0, kCtrBig = 1, kCtrBinTotal = 2, kCtrFlags = 3, kCtrTiles = 4;
+// Per-frame counter block (uint32 words): [0] big-list entries  [1] tile references  [2] flags
+// [3] kept (binned) triangles
+constexpr int kCtrBig = 0, kCtrRef = 1, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
 
 struct Dims {
   int W, H;
   int tiles_x, tiles_y, ntiles;
   int n_parts;           // model matrices per frame (the MVP table has n_parts + 1 rows)
   long long n_tris;
-  uint32_t cap_rec, cap_bin;
-  uint32_t ctr_stride;   // uint32 words per frame counter block
+  uint32_t cap_big, cap_bin;   // per-frame capacities: big list, tile references
+  int n_setup_ctas;            // setup CTAs per frame = table entries per tile
   float halfw, halfh, guard_x, guard_y;
 };
 
@@ -83,10 +88,10 @@ struct FrameBuffers {
 
 struct Workspace {
   float *mvp;            // [frame][n_parts + 1][16]
-  uint32_t *ctr;         // [frame][ctr_stride]
-  TriRec *recs;          // [frame][cap_rec]
-  TriRec *big;           // [frame][kBigCapacity]
-  TriRec *bins;          // [frame][cap_bin]
+  uint32_t *ctr;         // [frame][kCtrWords]
+  TriRec *big;           // [frame][cap_big]
+  TriRec *bins;          // [frame][cap_bin] tile-sorted segments, one per (setup CTA, tile)
+  uint2 *table;          // [frame][tile][n_setup_ctas] (start, count) into bins
   uint32_t *status;      // sticky OR of all frame flags
 };
 
@@ -104,6 +109,6 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
                           const double *d_proj, const double *d_view, const double *d_part_model,
                           const double *d_lookat, float bg_z, int enc, const ShaderParams &sp,
                           const FrameBuffers &fb, cudaStream_t s, int *n_launches,
-                          cudaEvent_t *stage_events /* null or 6 events: before K0, after K0..K4 */);
+                          cudaEvent_t *stage_events /* null or kNumStages+1 events */);
 
 }  // namespace ruf

@@ -13,6 +13,8 @@
 // nvcc neither contracts nor reorders; divisions are IEEE (-prec-div=true is the default).
 #include "ruf_device.cuh"
 
+#include <type_traits>
+
 namespace ruf {
 
 // ------------------------------------------------------------------------------------------
@@ -181,24 +183,11 @@ __device__ __forceinline__ bool to_window(const V4 &c, float halfw, float halfh,
   return true;
 }
 
-// warp-aggregated counter increment (all currently converged lanes share one atomic)
-__device__ __forceinline__ uint32_t agg_inc(uint32_t *ctr)
-{
-  const unsigned m = __activemask();
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(m));
-  base = __shfl_sync(m, base, leader);
-  return base + __popc(m & ((1u << lane) - 1u));
-}
-
-// S5/S8 + culling + hand-over to the binning stage
-__device__ __forceinline__ void emit_window_tri(WV a, WV b, WV c, const Dims &d, TriRec *recs, TriRec *big,
-                                                uint32_t *ctr)
+// S5/S8: orientation, pixel bbox, depth plane.  Returns false when the triangle cannot touch a pixel.
+__device__ __forceinline__ bool setup_window_tri(WV a, WV b, WV c, const Dims &d, TriRec &r)
 {
   long long area2 = (long long)(b.X - a.X) * (c.Y - a.Y) - (long long)(c.X - a.X) * (b.Y - a.Y);
-  if (area2 == 0) return;
+  if (area2 == 0) return false;
   if (area2 < 0) { WV t = b; b = c; c = t; area2 = -area2; }
 
   int xmin = min(a.X, min(b.X, c.X)), xmax = max(a.X, max(b.X, c.X));
@@ -209,7 +198,7 @@ __device__ __forceinline__ void emit_window_tri(WV a, WV b, WV c, const Dims &d,
   int j1 = (ymax - kSubpixHalf) >> kSubpixBits;
   i0 = max(i0, 0); i1 = min(i1, d.W - 1);
   j0 = max(j0, 0); j1 = min(j1, d.H - 1);
-  if (i0 > i1 || j0 > j1) return;
+  if (i0 > i1 || j0 > j1) return false;
 
   // S8: depth plane anchored at vertex 0
   float dx1 = (float)(b.X - a.X), dy1 = (float)(b.Y - a.Y);
@@ -221,29 +210,23 @@ __device__ __forceinline__ void emit_window_tri(WV a, WV b, WV c, const Dims &d,
   float t2 = dz1 * dx2;
   float gyz = fmaf(dz2, dx1, -t2) / fa;
 
-  TriRec r;
   r.x0 = a.X; r.y0 = a.Y; r.x1 = b.X; r.y1 = b.Y; r.x2 = c.X; r.y2 = c.Y;
   r.z0 = a.z; r.gx = gxz; r.gy = gyz;
   r.bx = (uint32_t)i0 | ((uint32_t)i1 << 16);
   r.by = (uint32_t)j0 | ((uint32_t)j1 << 16);
   r.pad = 0;
-
-  const int tx0 = i0 / kTileW, tx1 = i1 / kTileW, ty0 = j0 / kTileH, ty1 = j1 / kTileH;
-  const int nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-  if (nt > kBigTiles) {
-    uint32_t pos = atomicAdd(&ctr[kCtrBig], 1u);
-    if (pos < (uint32_t)kBigCapacity) { big[pos] = r; return; }
-    // list full: fall through and bin it like any other triangle
-  }
-  uint32_t idx = agg_inc(&ctr[kCtrRec]);
-  if (idx >= d.cap_rec) { atomicOr(&ctr[kCtrFlags], kFlagRecOverflow); return; }
-  recs[idx] = r;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&ctr[kCtrTiles + ty * d.tiles_x + tx], 1u);
+  return true;
 }
 
-__device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, TriRec *recs, TriRec *big,
-                                           uint32_t *ctr)
+// per-frame list read by every tile: triangles spanning many tiles and everything the clipper made
+__device__ __forceinline__ void push_big(const TriRec &r, const Dims &d, TriRec *big, uint32_t *ctr)
+{
+  const uint32_t pos = atomicAdd(&ctr[kCtrBig], 1u);
+  if (pos < d.cap_big) big[pos] = r;
+  else atomicOr(&ctr[kCtrFlags], kFlagBigOverflow);
+}
+
+__device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, TriRec *big, uint32_t *ctr)
 {
   V4 poly[kMaxPoly], tmp[kMaxPoly];
   poly[0] = p0; poly[1] = p1; poly[2] = p2;
@@ -266,17 +249,19 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
   WV wv[kMaxPoly];
   for (int i = 0; i < n; ++i)
     if (!to_window(poly[i], d.halfw, d.halfh, wv[i])) return;
-  for (int i = 2; i < n; ++i) emit_window_tri(wv[0], wv[i - 1], wv[i], d, recs, big, ctr);
+  for (int i = 2; i < n; ++i) {
+    TriRec r;
+    if (setup_window_tri(wv[0], wv[i - 1], wv[i], d, r)) push_big(r, d, big, ctr);
+  }
 }
 
-__global__ void __launch_bounds__(256)
-ruf_setup_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float bg_z, TriRec *recs_all,
-                 TriRec *big_all, uint32_t *ctr_all)
+// Vertex stage + setup of triangle t of `frame`.  Returns true when `r` holds a record that has to
+// be binned by the caller; clipped / many-tile triangles are pushed to the frame's big list here.
+__device__ __forceinline__ bool process_triangle(long long t, int frame, const Model &m,
+                                                 const float *__restrict__ mvp_all, const Dims &d, float bg_z,
+                                                 TriRec *big, uint32_t *ctr, TriRec &r, uint32_t &tiles)
 {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int frame = blockIdx.y;
-  if (t >= d.n_tris + 2) return;
-
+  if (t >= d.n_tris + 2) return false;
   float3 a, b, c;
   uint32_t part;
   if (t < d.n_tris) {
@@ -292,14 +277,14 @@ ruf_setup_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float bg_z,
     else               { b = make_float3(100.f, 100.f, bg_z);  c = make_float3(-100.f, 100.f, bg_z); }
     part = (uint32_t)d.n_parts;
   }
-  if (part > (uint32_t)d.n_parts) return;
+  if (part > (uint32_t)d.n_parts) return false;
 
   const float4 *M = reinterpret_cast<const float4 *>(mvp_all + 16 * ((long long)frame * (d.n_parts + 1) + part));
   const float4 c0 = __ldg(M), c1 = __ldg(M + 1), c2 = __ldg(M + 2), c3 = __ldg(M + 3);
   V4 p0 = xform(c0, c1, c2, c3, a.x, a.y, a.z);
   V4 p1 = xform(c0, c1, c2, c3, b.x, b.y, b.z);
   V4 p2 = xform(c0, c1, c2, c3, c.x, c.y, c.z);
-  if (!finite4(p0) || !finite4(p1) || !finite4(p2)) return;
+  if (!finite4(p0) || !finite4(p1) || !finite4(p2)) return false;
 
   // Early outs that cannot change the result (DESIGN.md "Setup-stage rejects"):
   //  * all three vertices in front of the near plane: the clipper would return nothing;
@@ -307,18 +292,14 @@ ruf_setup_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float bg_z,
   //    clipper keeps lies at least 0.3 px outside the viewport.
   {
     const float n0 = p0.z + p0.w, n1 = p1.z + p1.w, n2 = p2.z + p2.w;
-    if (n0 < 0.0f && n1 < 0.0f && n2 < 0.0f) return;
+    if (n0 < 0.0f && n1 < 0.0f && n2 < 0.0f) return false;
     const float k = 1.001f;
     const float w0 = k * p0.w, w1 = k * p1.w, w2 = k * p2.w;
-    if (p0.x > w0 && p1.x > w1 && p2.x > w2) return;
-    if (-p0.x > w0 && -p1.x > w1 && -p2.x > w2) return;
-    if (p0.y > w0 && p1.y > w1 && p2.y > w2) return;
-    if (-p0.y > w0 && -p1.y > w1 && -p2.y > w2) return;
+    if (p0.x > w0 && p1.x > w1 && p2.x > w2) return false;
+    if (-p0.x > w0 && -p1.x > w1 && -p2.x > w2) return false;
+    if (p0.y > w0 && p1.y > w1 && p2.y > w2) return false;
+    if (-p0.y > w0 && -p1.y > w1 && -p2.y > w2) return false;
   }
-
-  TriRec *recs = recs_all + (size_t)frame * d.cap_rec;
-  TriRec *big = big_all + (size_t)frame * kBigCapacity;
-  uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
 
   bool need = false;
 #pragma unroll
@@ -327,84 +308,126 @@ ruf_setup_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float bg_z,
     if (!(plane_dist(p1, k, d.guard_x, d.guard_y) >= 0.0f)) need = true;
     if (!(plane_dist(p2, k, d.guard_x, d.guard_y) >= 0.0f)) need = true;
   }
-  if (need) { clip_and_emit(p0, p1, p2, d, recs, big, ctr); return; }
-  if (!(p0.w > 0.0f) || !(p1.w > 0.0f) || !(p2.w > 0.0f)) return;   // S4b
+  if (need) { clip_and_emit(p0, p1, p2, d, big, ctr); return false; }
+  if (!(p0.w > 0.0f) || !(p1.w > 0.0f) || !(p2.w > 0.0f)) return false;   // S4b
   WV w0, w1, w2;
   if (!to_window(p0, d.halfw, d.halfh, w0) || !to_window(p1, d.halfw, d.halfh, w1) ||
       !to_window(p2, d.halfw, d.halfh, w2))
-    return;
-  emit_window_tri(w0, w1, w2, d, recs, big, ctr);
+    return false;
+  if (!setup_window_tri(w0, w1, w2, d, r)) return false;
+  const int tx0 = (int)(r.bx & 0xffffu) / kTileW, tx1 = (int)(r.bx >> 16) / kTileW;
+  const int ty0 = (int)(r.by & 0xffffu) / kTileH, ty1 = (int)(r.by >> 16) / kTileH;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) { push_big(r, d, big, ctr); return false; }
+  tiles = (uint32_t)tx0 | ((uint32_t)tx1 << 8) | ((uint32_t)ty0 << 16) | ((uint32_t)ty1 << 24);
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: per-frame exclusive scan of tile counts -> offsets; overflow detection
+// K1: vertex stage + setup + CTA-local binning.
+//
+// One CTA handles kSetupTris consecutive triangles of one frame (kTrisPerThread per thread, the
+// records stay in registers).  Tile reference counts are accumulated in shared memory, scanned,
+// and ONE global atomic per CTA reserves a contiguous range of the frame's reference buffer; the
+// records are then written tile-sorted into that range and the (start, count) of every tile is
+// published in table[frame][tile][cta].  The raster kernel gathers its tile's segments from
+// there, so no global per-triangle atomics, no scan kernel and no scatter kernel are needed.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ruf_scan_kernel(Dims d, uint32_t *ctr_all, uint32_t *status)
+template <int TPT>
+__global__ void __launch_bounds__(kSetupThreads)
+ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float bg_z, TriRec *big_all,
+                     TriRec *bins_all, uint2 *table_all, uint32_t *ctr_all)
 {
-  __shared__ uint32_t warp_sum[8];
-  __shared__ uint32_t carry_s;
-  uint32_t *ctr = ctr_all + (size_t)blockIdx.x * d.ctr_stride;
-  uint32_t *cnt = ctr + kCtrTiles;
-  uint32_t *off = ctr + kCtrTiles + 2 * d.ntiles;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  extern __shared__ uint32_t s_dyn[];            // [ntiles] counts, [ntiles] start -> cursor
+  __shared__ uint32_t s_warp[kSetupThreads / 32];
+  __shared__ uint32_t s_base;
+  uint32_t *s_cnt = s_dyn, *s_cur = s_dyn + d.ntiles;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.y, cta = blockIdx.x;
+  TriRec *big = big_all + (size_t)frame * d.cap_big;
+  uint32_t *ctr = ctr_all + (size_t)frame * kCtrWords;
+
+  for (int i = tid; i < d.ntiles; i += kSetupThreads) s_cnt[i] = 0;
   __syncthreads();
-  for (int base = 0; base < d.ntiles; base += 256) {
-    const int i = base + threadIdx.x;
-    uint32_t v = (i < d.ntiles) ? cnt[i] : 0u;
-    uint32_t x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    uint32_t wpre = 0;
-    for (int w = 0; w < warp; ++w) wpre += warp_sum[w];
-    const uint32_t carry = carry_s;
-    if (i < d.ntiles) off[i] = carry + wpre + x - v;
-    __syncthreads();
-    if (threadIdx.x == 255) carry_s = carry + wpre + x;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    uint32_t total = carry_s;
-    ctr[kCtrBinTotal] = total;
-    uint32_t flags = ctr[kCtrFlags];
-    if (total > d.cap_bin) flags |= kFlagBinOverflow;
-    ctr[kCtrFlags] = flags;
-    if (flags) atomicOr(status, flags);
-  }
-}
 
-// ------------------------------------------------------------------------------------------
-// K3: scatter the kept records into their tiles' bins (grid-stride over the frame's records)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ruf_bin_kernel(Dims d, const TriRec *__restrict__ recs_all, TriRec *bins_all, uint32_t *ctr_all)
-{
-  const int frame = blockIdx.y;
-  uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
-  const uint32_t n = min(ctr[kCtrRec], d.cap_rec);
-  const TriRec *recs = recs_all + (size_t)frame * d.cap_rec;
-  TriRec *bins = bins_all + (size_t)frame * d.cap_bin;
-  uint32_t *cur = ctr + kCtrTiles + d.ntiles;
-  const uint32_t *off = ctr + kCtrTiles + 2 * d.ntiles;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(recs + i);
-    const uint4 q0 = src[0], q1 = src[1], q2 = src[2];
-    const uint32_t bx = q2.y, by = q2.z;
-    const int tx0 = (int)(bx & 0xffffu) / kTileW, tx1 = (int)(bx >> 16) / kTileW;
-    const int ty0 = (int)(by & 0xffffu) / kTileH, ty1 = (int)(by >> 16) / kTileH;
+  TriRec rec[TPT];
+  uint32_t tiles[TPT];
+  bool valid[TPT];
+#pragma unroll
+  for (int k = 0; k < TPT; ++k) {
+    const long long t = ((long long)cta * TPT + k) * kSetupThreads + tid;
+    valid[k] = process_triangle(t, frame, m, mvp_all, d, bg_z, big, ctr, rec[k], tiles[k]);
+    if (valid[k]) {
+      const int tx0 = tiles[k] & 255, tx1 = (tiles[k] >> 8) & 255, ty0 = (tiles[k] >> 16) & 255, ty1 = tiles[k] >> 24;
+      for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * d.tiles_x + tx], 1u);
+    }
+  }
+  __syncthreads();
+
+  // exclusive scan of the tile counts (each thread owns a contiguous run of `ipt` tiles)
+  const int ipt = (d.ntiles + kSetupThreads - 1) / kSetupThreads;
+  const int first = tid * ipt;
+  uint32_t run = 0;
+  for (int i = first; i < min(first + ipt, d.ntiles); ++i) run += s_cnt[i];
+  uint32_t x = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  uint32_t wpre = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kSetupThreads / 32; ++w) {
+    const uint32_t v = s_warp[w];
+    if (w < warp) wpre += v;
+    total += v;
+  }
+  {
+    uint32_t kept = 0;
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) kept += valid[k] ? 1u : 0u;
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if (lane == 0 && kept) atomicAdd(&ctr[kCtrKept], kept);     // statistics only
+  }
+  if (tid == 0) {
+    uint32_t base = 0xffffffffu;
+    if (total > 0) {
+      base = atomicAdd(&ctr[kCtrRef], total);
+      if (base + total > d.cap_bin) { atomicOr(&ctr[kCtrFlags], kFlagBinOverflow); base = 0xffffffffu; }
+    }
+    s_base = base;
+  }
+  uint32_t acc = wpre + x - run;
+  for (int i = first; i < min(first + ipt, d.ntiles); ++i) {
+    s_cur[i] = acc;
+    acc += s_cnt[i];
+  }
+  __syncthreads();
+  const uint32_t base = s_base;
+  uint2 *table = table_all + (size_t)frame * d.ntiles * d.n_setup_ctas;
+  for (int i = tid; i < d.ntiles; i += kSetupThreads) {
+    const uint32_t c = (base == 0xffffffffu) ? 0u : s_cnt[i];
+    table[(size_t)i * d.n_setup_ctas + cta] = make_uint2(base + s_cur[i], c);
+  }
+  if (base == 0xffffffffu) return;
+  __syncthreads();          // the table read s_cur; from here on it is the fill cursor
+
+  TriRec *bins = bins_all + (size_t)frame * d.cap_bin + base;
+#pragma unroll
+  for (int k = 0; k < TPT; ++k) {
+    if (!valid[k]) continue;
+    const uint4 q0 = make_uint4((uint32_t)rec[k].x0, (uint32_t)rec[k].y0, (uint32_t)rec[k].x1, (uint32_t)rec[k].y1);
+    const uint4 q1 = make_uint4((uint32_t)rec[k].x2, (uint32_t)rec[k].y2, __float_as_uint(rec[k].z0),
+                                __float_as_uint(rec[k].gx));
+    const uint4 q2 = make_uint4(__float_as_uint(rec[k].gy), rec[k].bx, rec[k].by, 0u);
+    const int tx0 = tiles[k] & 255, tx1 = (tiles[k] >> 8) & 255, ty0 = (tiles[k] >> 16) & 255, ty1 = tiles[k] >> 24;
     for (int ty = ty0; ty <= ty1; ++ty)
       for (int tx = tx0; tx <= tx1; ++tx) {
-        const int tile = ty * d.tiles_x + tx;
-        const uint32_t pos = off[tile] + atomicAdd(&cur[tile], 1u);
-        if (pos < d.cap_bin) {
-          uint4 *dst = reinterpret_cast<uint4 *>(bins + pos);
-          dst[0] = q0; dst[1] = q1; dst[2] = q2;
-        }
+        const uint32_t pos = atomicAdd(&s_cur[ty * d.tiles_x + tx], 1u);
+        uint4 *dst = reinterpret_cast<uint4 *>(bins + pos);
+        dst[0] = q0; dst[1] = q1; dst[2] = q2;
       }
   }
 }
@@ -450,60 +473,72 @@ __device__ __forceinline__ TriRec load_rec_global(const TriRec *p)
   return r;
 }
 
-// one lane walks the (tile-clipped) bbox of a small triangle; 32-bit edge functions are exact
-// because every factor is below 2^14 (extent < 64 px).
-__device__ __forceinline__ void raster_small(const TriRec &r, int i0, int i1, int j0, int j1, int tile_x0,
-                                             int tile_y0, uint32_t *sz)
+// shared-memory min on the z tile (explicit .shared so that no generic-address atomic is generated)
+__device__ __forceinline__ void smem_min(uint32_t saddr, uint32_t v)
 {
-  const Edges e = make_edges(r);
-  const int px0 = i0 * kSubpix + kSubpixHalf;
-  int py = j0 * kSubpix + kSubpixHalf;
-  int r0 = e.A0 * (px0 - r.x0) + e.B0 * (py - r.y0) + e.bias0;
-  int r1 = e.A1 * (px0 - r.x1) + e.B1 * (py - r.y1) + e.bias1;
-  int r2 = e.A2 * (px0 - r.x2) + e.B2 * (py - r.y2) + e.bias2;
-  const int sA0 = e.A0 * kSubpix, sA1 = e.A1 * kSubpix, sA2 = e.A2 * kSubpix;
-  const int sB0 = e.B0 * kSubpix, sB1 = e.B1 * kSubpix, sB2 = e.B2 * kSubpix;
-  for (int j = j0; j <= j1; ++j, py += kSubpix) {
-    const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
-    int e0 = r0, e1 = r1, e2 = r2;
-    uint32_t *row = sz + (j - tile_y0) * kTileW - tile_x0;
-    int px = px0;
-    for (int i = i0; i <= i1; ++i, px += kSubpix) {
-      if ((e0 | e1 | e2) >= 0) {
-        float z = clamp_z(fmaf(r.gx, (float)(px - r.x0), rowz));
-        if (z < 1.0f) atomicMin(row + i, __float_as_uint(z));
-      }
-      e0 += sA0; e1 += sA1; e2 += sA2;
-    }
-    r0 += sB0; r1 += sB1; r2 += sB2;
-  }
+  asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_ld(uint32_t saddr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
 }
 
-// a whole warp covers the tile-clipped bbox in 8x4 footprints; 64-bit edge functions
+// a whole warp covers the tile-clipped bbox in 8x4 footprints.  WIDE = false: every factor of the
+// edge functions is below 2^14, so 32-bit arithmetic is exact; WIDE = true: 64-bit.
+template <bool WIDE>
 __device__ __forceinline__ void raster_warp(const TriRec &r, int i0, int i1, int j0, int j1, int tile_x0,
-                                            int tile_y0, uint32_t *sz, int lane)
+                                            int tile_y0, uint32_t sz_addr, int lane)
 {
+  typedef typename std::conditional<WIDE, long long, int>::type acc_t;
   const Edges e = make_edges(r);
   const int lx = lane & 7, ly = lane >> 3;
   for (int jb = j0; jb <= j1; jb += 4) {
     const int j = jb + ly;
     const int py = j * kSubpix + kSubpixHalf;
     const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
-    const long long c0 = (long long)e.B0 * (py - r.y0) + e.bias0;
-    const long long c1 = (long long)e.B1 * (py - r.y1) + e.bias1;
-    const long long c2 = (long long)e.B2 * (py - r.y2) + e.bias2;
+    const acc_t c0 = (acc_t)e.B0 * (py - r.y0) + e.bias0;
+    const acc_t c1 = (acc_t)e.B1 * (py - r.y1) + e.bias1;
+    const acc_t c2 = (acc_t)e.B2 * (py - r.y2) + e.bias2;
     for (int ib = i0; ib <= i1; ib += 8) {
       const int i = ib + lx;
       const int px = i * kSubpix + kSubpixHalf;
-      const long long e0 = (long long)e.A0 * (px - r.x0) + c0;
-      const long long e1 = (long long)e.A1 * (px - r.x1) + c1;
-      const long long e2 = (long long)e.A2 * (px - r.x2) + c2;
+      const acc_t e0 = (acc_t)e.A0 * (px - r.x0) + c0;
+      const acc_t e1 = (acc_t)e.A1 * (px - r.x1) + c1;
+      const acc_t e2 = (acc_t)e.A2 * (px - r.x2) + c2;
       if (i <= i1 && j <= j1 && (e0 | e1 | e2) >= 0) {
-        float z = clamp_z(fmaf(r.gx, (float)(px - r.x0), rowz));
-        if (z < 1.0f) atomicMin(sz + (j - tile_y0) * kTileW + (i - tile_x0), __float_as_uint(z));
+        const uint32_t z = __float_as_uint(clamp_z(fmaf(r.gx, (float)(px - r.x0), rowz)));
+        const uint32_t addr = sz_addr + 4u * (uint32_t)((j - tile_y0) * kTileW + (i - tile_x0));
+        if (z < 0x3f800000u && z < smem_ld(addr)) smem_min(addr, z);
       }
     }
   }
+}
+
+__device__ __forceinline__ TriRec shfl_rec(const TriRec &r, int src)
+{
+  TriRec o;
+  o.x0 = __shfl_sync(0xffffffffu, r.x0, src); o.y0 = __shfl_sync(0xffffffffu, r.y0, src);
+  o.x1 = __shfl_sync(0xffffffffu, r.x1, src); o.y1 = __shfl_sync(0xffffffffu, r.y1, src);
+  o.x2 = __shfl_sync(0xffffffffu, r.x2, src); o.y2 = __shfl_sync(0xffffffffu, r.y2, src);
+  o.z0 = __shfl_sync(0xffffffffu, r.z0, src); o.gx = __shfl_sync(0xffffffffu, r.gx, src);
+  o.gy = __shfl_sync(0xffffffffu, r.gy, src); o.bx = __shfl_sync(0xffffffffu, r.bx, src);
+  o.by = __shfl_sync(0xffffffffu, r.by, src); o.pad = 0;
+  return o;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync()
+{
+  asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory");
 }
 
 // saturate_cast<ushort>(cvRound(x * 1000.f)) -- cv::Mat::convertTo(CV_16U, 1000.0), src/urdf_filter.cpp:311
@@ -529,114 +564,297 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
 }
 
 template <int ENC>
-__global__ void __launch_bounds__(kRasterThreads, 4)
+__global__ void __launch_bounds__(kRasterBlock, 4)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
-                         const uint32_t *__restrict__ ctr_all, ShaderParams sp, FrameBuffers fb)
+                         const uint2 *__restrict__ table_all, const uint32_t *__restrict__ ctr_all,
+                         ShaderParams sp, FrameBuffers fb)
 {
-  __shared__ __align__(128) TriRec sbuf[2][kChunk];
+  // Warp roles: warps 0..7 (kRasterThreads = 256 threads) rasterise and shade; warp 8 is the producer
+  // that streams the tile's triangle records into the shared-memory ring with bulk async copies.
+  __shared__ __align__(128) TriRec sbuf[kStages][kChunk];
   __shared__ __align__(16) uint32_t sz[kTilePix];
-  __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ uint32_t s_defer_n[2];
-  __shared__ uint16_t s_defer[kChunk];
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ uint32_t s_nseg, s_total, s_next;
+  __shared__ uint32_t seg_src[kSegCap], seg_off[kSegCap], seg_cnt[kSegCap];
+  __shared__ uint16_t s_units[kRasterThreads / 32][32 * kMaxUnits];
+  __shared__ uint8_t s_bigcls[kRasterThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == kRasterThreads / 32;
   const int tile = blockIdx.x, frame = blockIdx.y;
   const int tile_x0 = (tile % d.tiles_x) * kTileW, tile_y0 = (tile / d.tiles_x) * kTileH;
-  const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
-
-  const uint32_t off = ctr[kCtrTiles + 2 * d.ntiles + tile];
-  uint32_t cnt = ctr[kCtrTiles + tile];
-  if (off >= d.cap_bin) cnt = 0; else cnt = min(cnt, d.cap_bin - off);
-  const TriRec *bin = bins_all + (size_t)frame * d.cap_bin + off;
-  const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
+  const uint32_t *ctr = ctr_all + (size_t)frame * kCtrWords;
+  const TriRec *bins = bins_all + (size_t)frame * d.cap_bin;
+  const uint2 *table = table_all + ((size_t)frame * d.ntiles + tile) * d.n_setup_ctas;
+  const uint32_t sz_addr = smem_u32(sz);
 
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);                        // the producer's arrive.expect_tx
+      mbar_init(&empty_bar[s], kRasterThreads / 32);     // one arrive per consumer warp
+    }
     mbar_fence_init();
-    s_defer_n[0] = 0;
-    s_defer_n[1] = 0;
+    s_nseg = 0;
+    s_total = 0;
+    s_next = 0;
   }
   __syncthreads();
-  if (tid == 0 && nchunks > 0) {
-    const uint32_t nrec = min(cnt, (uint32_t)kChunk);
-    mbar_arrive_expect_tx(&mbar[0], nrec * (uint32_t)sizeof(TriRec));
-    bulk_g2s(&sbuf[0][0], bin, nrec * (uint32_t)sizeof(TriRec), &mbar[0]);
-  }
 
-  // ---- big list: pixel-parallel, every thread owns 8 consecutive pixels of one tile row ----
-  const int prow = tid >> 3, pcol = (tid & 7) * 8;
-  float zr[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) zr[i] = 1.0f;       // glClear depth
-  {
-    const uint32_t nbig = min(ctr[kCtrBig], (uint32_t)kBigCapacity);
-    const TriRec *big = big_all + (size_t)frame * kBigCapacity;
-    const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
-    const int py = (tile_y0 + prow) * kSubpix + kSubpixHalf;
-    for (uint32_t b = 0; b < nbig; ++b) {
-      const TriRec r = load_rec_global(big + b);
-      const int bi0 = (int)(r.bx & 0xffffu), bi1 = (int)(r.bx >> 16);
-      const int bj0 = (int)(r.by & 0xffffu), bj1 = (int)(r.by >> 16);
-      if (bi1 < tile_x0 || bi0 >= tile_x0 + kTileW || bj1 < tile_y0 || bj0 >= tile_y0 + kTileH) continue;
-      const Edges e = make_edges(r);
-      long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
-      long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
-      long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
-      const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix,
-                      s2 = (long long)e.A2 * kSubpix;
-      const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if ((e0 | e1 | e2) >= 0) {
-          float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-          if (z < 1.0f) zr[i] = fminf(zr[i], z);
+  const int prow = (tid & (kRasterThreads - 1)) >> 3, pcol = (tid & 7) * 8;
+  const int n_entries = d.n_setup_ctas;
+  uint32_t cc = 0;                           // chunks streamed so far (ring position, all rounds)
+
+  for (int round = 0; round * kSegCap < n_entries || round == 0; ++round) {
+    // ---- segment list of this tile: one (start, count) per setup CTA, empty ones dropped ----
+    if (round > 0) {
+      __syncthreads();                       // everybody is done with the previous list
+      if (tid == 0) { s_nseg = 0; s_total = 0; s_next = 0; }
+      __syncthreads();
+    }
+    {
+      const int hi = min(n_entries, (round + 1) * kSegCap);
+      for (int e = round * kSegCap + tid; e < hi; e += kRasterBlock) {
+        const uint2 en = __ldg(table + e);
+        if (en.y) {
+          const uint32_t k = atomicAdd(&s_nseg, 1u);
+          seg_src[k] = en.x; seg_cnt[k] = en.y;
+          seg_off[k] = atomicAdd(&s_total, en.y);
         }
-        e0 += s0; e1 += s1; e2 += s2;
       }
     }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sz[prow * kTileW + pcol + i] = __float_as_uint(zr[i]);
-  __syncthreads();
+    __syncthreads();
+    const uint32_t nseg = s_nseg, cnt = s_total;
+    const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
 
-  // ---- binned triangles: chunks of 256 records double-buffered through the TMA engine ----
-  for (int c = 0; c < nchunks; ++c) {
-    const int buf = c & 1;
-    if (tid == 0 && c + 1 < nchunks) {
-      const uint32_t nrec = min(cnt - (uint32_t)(c + 1) * kChunk, (uint32_t)kChunk);
-      mbar_arrive_expect_tx(&mbar[buf ^ 1], nrec * (uint32_t)sizeof(TriRec));
-      bulk_g2s(&sbuf[buf ^ 1][0], bin + (size_t)(c + 1) * kChunk, nrec * (uint32_t)sizeof(TriRec),
-               &mbar[buf ^ 1]);
-    }
-    mbar_wait(&mbar[buf], (uint32_t)((c >> 1) & 1));
-    const uint32_t nrec = min(cnt - (uint32_t)c * kChunk, (uint32_t)kChunk);
-    if ((uint32_t)tid < nrec) {
-      const TriRec r = load_rec_smem(&sbuf[buf][tid]);
-      const int i0 = max((int)(r.bx & 0xffffu), tile_x0), i1 = min((int)(r.bx >> 16), tile_x0 + kTileW - 1);
-      const int j0 = max((int)(r.by & 0xffffu), tile_y0), j1 = min((int)(r.by >> 16), tile_y0 + kTileH - 1);
-      const int ex = max(r.x0, max(r.x1, r.x2)) - min(r.x0, min(r.x1, r.x2));
-      const int ey = max(r.y0, max(r.y1, r.y2)) - min(r.y0, min(r.y1, r.y2));
-      const int area = (i1 - i0 + 1) * (j1 - j0 + 1);
-      if (area <= kSmallArea && ex < 16384 && ey < 16384) {
-        raster_small(r, i0, i1, j0, j1, tile_x0, tile_y0, sz);
-      } else {
-        s_defer[atomicAdd(&s_defer_n[buf], 1u)] = (uint16_t)tid;
+    if (is_producer) {
+      // ===== producer warp: every segment piece that falls into the chunk is one bulk copy =====
+      for (int c = 0; c < nchunks; ++c, ++cc) {
+        const int stage = (int)(cc % kStages);
+        const uint32_t use = cc / kStages;
+        if (use > 0) mbar_wait(&empty_bar[stage], (use - 1) & 1);   // consumers drained the previous content
+        const uint32_t lo = (uint32_t)c * kChunk, hi = min(lo + (uint32_t)kChunk, cnt);
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (hi - lo) * (uint32_t)sizeof(TriRec));
+        for (uint32_t sg = lane; sg < nseg; sg += 32) {
+          const uint32_t so = seg_off[sg], se = so + seg_cnt[sg];
+          const uint32_t a = max(so, lo), b = min(se, hi);
+          if (a < b)
+            bulk_g2s(&sbuf[stage][a - lo], bins + seg_src[sg] + (a - so), (b - a) * (uint32_t)sizeof(TriRec),
+                     &full_bar[stage]);
+        }
       }
+    } else {
+      // ===== consumer warps =====
+      if (round == 0) {
+        // big list: pixel-parallel, every thread owns 8 consecutive pixels of one tile row
+        float zr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zr[i] = 1.0f;       // glClear depth
+        const uint32_t nbig = min(ctr[kCtrBig], d.cap_big);
+        const TriRec *big = big_all + (size_t)frame * d.cap_big;
+        const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
+        const int py = (tile_y0 + prow) * kSubpix + kSubpixHalf;
+        const int tpx = tile_x0 * kSubpix + kSubpixHalf, tpy = tile_y0 * kSubpix + kSubpixHalf;
+        for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
+          // classify 256 records in parallel (one per thread): 0 = no sample of this tile can be
+          // covered, 1 = every sample is covered, 2 = mixed.  Edge values are linear over the tile's
+          // sample grid, so their min / max sit on its corners.
+          uint32_t cls = 0;
+          if (b0 + tid < nbig) {
+            const TriRec r = load_rec_global(big + b0 + tid);
+            const int bi0 = (int)(r.bx & 0xffffu), bi1 = (int)(r.bx >> 16);
+            const int bj0 = (int)(r.by & 0xffffu), bj1 = (int)(r.by >> 16);
+            if (!(bi1 < tile_x0 || bi0 >= tile_x0 + kTileW || bj1 < tile_y0 || bj0 >= tile_y0 + kTileH)) {
+              const Edges e = make_edges(r);
+              const long long spanx = (long long)(kTileW - 1) * kSubpix, spany = (long long)(kTileH - 1) * kSubpix;
+              const long long t0 = (long long)e.A0 * (tpx - r.x0) + (long long)e.B0 * (tpy - r.y0) + e.bias0;
+              const long long t1 = (long long)e.A1 * (tpx - r.x1) + (long long)e.B1 * (tpy - r.y1) + e.bias1;
+              const long long t2 = (long long)e.A2 * (tpx - r.x2) + (long long)e.B2 * (tpy - r.y2) + e.bias2;
+              const long long a0 = e.A0 * spanx, c0 = e.B0 * spany, a1 = e.A1 * spanx, c1 = e.B1 * spany,
+                              a2 = e.A2 * spanx, c2 = e.B2 * spany;
+              const long long mx0 = t0 + max(a0, 0LL) + max(c0, 0LL), mn0 = t0 + min(a0, 0LL) + min(c0, 0LL);
+              const long long mx1 = t1 + max(a1, 0LL) + max(c1, 0LL), mn1 = t1 + min(a1, 0LL) + min(c1, 0LL);
+              const long long mx2 = t2 + max(a2, 0LL) + max(c2, 0LL), mn2 = t2 + min(a2, 0LL) + min(c2, 0LL);
+              if ((mx0 | mx1 | mx2) >= 0) cls = ((mn0 | mn1 | mn2) >= 0) ? 1u : 2u;
+            }
+          }
+          s_bigcls[tid] = (uint8_t)cls;
+          consumer_bar_sync();
+          const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
+          for (uint32_t b = 0; b < nb; ++b) {
+            const uint32_t c = s_bigcls[b];
+            if (c == 0) continue;
+            const TriRec r = load_rec_global(big + b0 + b);
+            const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
+            if (c == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+                if (z < 1.0f) zr[i] = fminf(zr[i], z);
+              }
+              continue;
+            }
+            const Edges e = make_edges(r);
+            long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
+            long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
+            long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
+            const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix,
+                            s2 = (long long)e.A2 * kSubpix;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if ((e0 | e1 | e2) >= 0) {
+                float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+                if (z < 1.0f) zr[i] = fminf(zr[i], z);
+              }
+              e0 += s0; e1 += s1; e2 += s2;
+            }
+          }
+          if (b0 + kRasterThreads < nbig) consumer_bar_sync();   // s_bigcls is rewritten next round
+        }
+        uint4 *zp = reinterpret_cast<uint4 *>(&sz[prow * kTileW + pcol]);
+        zp[0] = make_uint4(__float_as_uint(zr[0]), __float_as_uint(zr[1]), __float_as_uint(zr[2]), __float_as_uint(zr[3]));
+        zp[1] = make_uint4(__float_as_uint(zr[4]), __float_as_uint(zr[5]), __float_as_uint(zr[6]), __float_as_uint(zr[7]));
+        consumer_bar_sync();                  // the z tile is initialised for all consumer warps
+      }
+
+      // binned triangles: the chunk's 256 records are 8 batches of 32; warps claim batches from a
+      // shared counter (a warp that drew light triangles simply takes the next batch), and a stage goes
+      // back to the producer once its 8 batches sit in registers.
+      const uint32_t nbatches = (cnt + 31u) / 32u;
+      for (;;) {
+        uint32_t bt = 0;
+        if (lane == 0) bt = atomicAdd(&s_next, 1u);
+        bt = __shfl_sync(0xffffffffu, bt, 0);
+        if (bt >= nbatches) break;
+        const int c = (int)(bt / (kChunk / 32));
+        const uint32_t gc = cc + (uint32_t)c;                 // ring position of the chunk
+        const int stage = (int)(gc % kStages);
+        mbar_wait(&full_bar[stage], (gc / kStages) & 1);
+        const uint32_t nrec = min(cnt - (uint32_t)c * kChunk, (uint32_t)kChunk);
+        const uint32_t idx = (bt % (kChunk / 32)) * 32u + (uint32_t)lane;
+        // ---- phase 1: one lane per record: clip to the tile, derive the incremental edge setup ----
+        TriRec r;
+        int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+        int kind = 0;       // 0 nothing, 1 dealt out as row-block units, 2 warp-wide 32-bit, 3 warp-wide 64-bit
+        int sA0 = 0, sA1 = 0, sA2 = 0, sB0 = 0, sB1 = 0, sB2 = 0, r0 = 0, r1 = 0, r2 = 0;
+        int ncb = 0, nunits = 0;
+        if (idx < nrec) {
+          r = load_rec_smem(&sbuf[stage][idx]);
+          i0 = max((int)(r.bx & 0xffffu), tile_x0); i1 = min((int)(r.bx >> 16), tile_x0 + kTileW - 1);
+          j0 = max((int)(r.by & 0xffffu), tile_y0); j1 = min((int)(r.by >> 16), tile_y0 + kTileH - 1);
+          const int ex = max(r.x0, max(r.x1, r.x2)) - min(r.x0, min(r.x1, r.x2));
+          const int ey = max(r.y0, max(r.y1, r.y2)) - min(r.y0, min(r.y1, r.y2));
+          const bool narrow = ex < 16384 && ey < 16384;     // every edge-function factor < 2^14: int32 is exact
+          ncb = (i1 - i0 + 8) >> 3;                          // 8-sample blocks per row
+          nunits = ncb * (j1 - j0 + 1);
+          kind = narrow ? ((nunits <= kMaxUnits) ? 1 : 2) : 3;
+          if (kind == 1) {
+            const Edges e = make_edges(r);
+            const int px0 = i0 * kSubpix + kSubpixHalf, py0 = j0 * kSubpix + kSubpixHalf;
+            r0 = e.A0 * (px0 - r.x0) + e.B0 * (py0 - r.y0) + e.bias0;
+            r1 = e.A1 * (px0 - r.x1) + e.B1 * (py0 - r.y1) + e.bias1;
+            r2 = e.A2 * (px0 - r.x2) + e.B2 * (py0 - r.y2) + e.bias2;
+            sA0 = e.A0 * kSubpix; sA1 = e.A1 * kSubpix; sA2 = e.A2 * kSubpix;
+            sB0 = e.B0 * kSubpix; sB1 = e.B1 * kSubpix; sB2 = e.B2 * kSubpix;
+          } else {
+            nunits = 0;
+          }
+        } else {
+          r.x0 = r.y0 = r.x1 = r.y1 = r.x2 = r.y2 = 0; r.z0 = r.gx = r.gy = 0.f; r.bx = r.by = r.pad = 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          // this batch sits in registers.  A short last chunk has fewer than 8 batches: whoever drew its
+          // first batch also arrives for the missing ones so that the barrier phase always completes.
+          const uint32_t in_chunk = (nrec + 31u) / 32u;
+          const uint32_t extra = ((bt % (kChunk / 32)) == 0) ? (kChunk / 32 - in_chunk) : 0u;
+          mbar_arrive_n(&empty_bar[stage], 1u + extra);
+        }
+
+        // ---- phase 2: the row-block units (one row x 8 samples) of the 32 records are dealt out to
+        // the lanes round by round, so every lane does the same amount of branch-free work.  Unit
+        // table in shared memory: owner lane | row << 5 | block << 10.
+        int incl = nunits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        const int excl = incl - nunits;
+        const int items = __shfl_sync(0xffffffffu, incl, 31);
+        uint16_t *utab = s_units[warp];
+        {
+          int row = 0, cb = 0;
+          for (int q = 0; q < nunits; ++q) {
+            utab[excl + q] = (uint16_t)(lane | (row << 5) | (cb << 10));
+            if (++cb == ncb) { cb = 0; ++row; }
+          }
+        }
+        __syncwarp();
+        for (int base = 0; base < items; base += 32) {
+          const int x = base + lane;
+          const bool act = x < items;
+          const uint32_t ent = act ? (uint32_t)utab[x] : 0u;
+          const int o = (int)(ent & 31u), row = (int)((ent >> 5) & 31u), cb = (int)(ent >> 10);
+          // fetch the owner's setup (all lanes shuffle; inactive lanes read lane 0 and discard)
+          const int qA0 = __shfl_sync(0xffffffffu, sA0, o), qA1 = __shfl_sync(0xffffffffu, sA1, o),
+                    qA2 = __shfl_sync(0xffffffffu, sA2, o);
+          const int qB0 = __shfl_sync(0xffffffffu, sB0, o), qB1 = __shfl_sync(0xffffffffu, sB1, o),
+                    qB2 = __shfl_sync(0xffffffffu, sB2, o);
+          int e0 = __shfl_sync(0xffffffffu, r0, o), e1 = __shfl_sync(0xffffffffu, r1, o),
+              e2 = __shfl_sync(0xffffffffu, r2, o);
+          const int qi0 = __shfl_sync(0xffffffffu, i0, o), qi1 = __shfl_sync(0xffffffffu, i1, o);
+          const int qj0 = __shfl_sync(0xffffffffu, j0, o);
+          const int qx0 = __shfl_sync(0xffffffffu, r.x0, o), qy0 = __shfl_sync(0xffffffffu, r.y0, o);
+          const float qz0 = __shfl_sync(0xffffffffu, r.z0, o), qgx = __shfl_sync(0xffffffffu, r.gx, o),
+                      qgy = __shfl_sync(0xffffffffu, r.gy, o);
+          if (act) {
+            const int col = qi0 + cb * 8, j = qj0 + row;
+            e0 += row * qB0 + cb * 8 * qA0;
+            e1 += row * qB1 + cb * 8 * qA1;
+            e2 += row * qB2 + cb * 8 * qA2;
+            uint32_t m = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              m = __funnelshift_l((uint32_t)(e0 | e1 | e2), m, 1);   // shifts in 1 for "outside"
+              e0 += qA0; e1 += qA1; e2 += qA2;
+            }
+            // bit (7 - k) of ~m <=> sample col + k is covered; samples beyond i1 belong to another tile
+            const int valid = min(8, qi1 - col + 1);
+            m = (~m) & 0xffu & (0xff00u >> valid);
+            if (m) {
+              const int py = j * kSubpix + kSubpixHalf;
+              const float rowz = fmaf(qgy, (float)(py - qy0), qz0);
+              const float f0 = (float)(col * kSubpix + kSubpixHalf - qx0);   // exact: |value| < 2^24
+              const uint32_t addr = sz_addr + 4u * (uint32_t)((j - tile_y0) * kTileW + (col - tile_x0));
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                // float(px - x0) for sample k = f0 + 256 k (integers below 2^24: the sum is exact)
+                const uint32_t z = __float_as_uint(clamp_z(fmaf(qgx, f0 + (float)(k * kSubpix), rowz)));
+                if ((m & (0x80u >> k)) && z < 0x3f800000u) smem_min(addr + 4u * k, z);
+              }
+            }
+          }
+        }
+        __syncwarp();                          // the unit table is rewritten by the next batch
+        // big or wide records: the whole warp covers one triangle at a time
+        unsigned wide = __ballot_sync(0xffffffffu, kind >= 2);
+        while (wide) {
+          const int src = __ffs(wide) - 1;
+          wide &= wide - 1;
+          const TriRec q = shfl_rec(r, src);
+          const int qi0 = __shfl_sync(0xffffffffu, i0, src), qi1 = __shfl_sync(0xffffffffu, i1, src);
+          const int qj0 = __shfl_sync(0xffffffffu, j0, src), qj1 = __shfl_sync(0xffffffffu, j1, src);
+          if (__shfl_sync(0xffffffffu, kind, src) == 2) raster_warp<false>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz_addr, lane);
+          else raster_warp<true>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz_addr, lane);
+        }
+      }
+      cc += (uint32_t)nchunks;
     }
-    __syncthreads();
-    // s_defer_n[buf ^ 1] was last read before the barrier that ended the previous iteration and
-    // is next incremented after the barrier that ends this one: safe to clear here.
-    if (tid == 0) s_defer_n[buf ^ 1] = 0;
-    const uint32_t ndefer = s_defer_n[buf];
-    for (uint32_t q = warp; q < ndefer; q += kRasterThreads / 32) {
-      const TriRec r = load_rec_smem(&sbuf[buf][s_defer[q]]);
-      const int i0 = max((int)(r.bx & 0xffffu), tile_x0), i1 = min((int)(r.bx >> 16), tile_x0 + kTileW - 1);
-      const int j0 = max((int)(r.by & 0xffffu), tile_y0), j1 = min((int)(r.by >> 16), tile_y0 + kTileH - 1);
-      raster_warp(r, i0, i1, j0, j1, tile_x0, tile_y0, sz, lane);
-    }
-    __syncthreads();
+    if (!((round + 1) * kSegCap < n_entries)) break;
   }
+  __syncthreads();
+  if (is_producer) return;
 
   // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
   const int gy = tile_y0 + prow, gx = tile_x0 + pcol;
@@ -650,39 +868,52 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
                        __uint_as_float(zq1.z), __uint_as_float(zq1.w)};
   const bool full = fb.vec_ok && (gx + 8 <= d.W);
   if (full) {
-    float sensor[8];
+    // to_linear_depth (frag:14-17,22) once per distinct z of this thread's run: background pixels
+    // share one window z, so most threads divide once instead of eight times
+    float virt[8];
+    {
+      float zprev = 1.0f, vprev = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (zw[i] != zprev) { vprev = sp.k1 / (zw[i] - sp.k2); zprev = zw[i]; }
+        virt[i] = vprev;                       // unused where zw == 1 (never drawn)
+      }
+    }
+    uint32_t om[8];
     if (ENC == 1) {
       const uint4 q = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + base));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      const uint32_t repl = f32_to_u16(sp.replace_value);       // convertTo(CV_16U, 1000) of the replaced pixels, :311
+      uint32_t u[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sensor[2 * i] = (float)(w[i] & 0xffffu) * 0.001f;      // convertTo(CV_32F, 0.001), :288
-        sensor[2 * i + 1] = (float)(w[i] >> 16) * 0.001f;
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t raw = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+        const float sensor = (float)raw * 0.001f;               // convertTo(CV_32F, 0.001), :288
+        const bool drawn = zw[i] != 1.0f;                       // else clear colour: depth 0, mask 0 (:566)
+        const bool sflt = drawn && (sensor > (virt[i] - sp.max_diff));   // frag:23
+        // an unfiltered pixel is sat_u16(rint((u * 0.001f) * 1000.f)), which is u itself for every
+        // 16-bit u (exhaustively checked: tests/test_oracle_encodings.py::test_u16_roundtrip_identity_all_65536)
+        u[i] = drawn ? (sflt ? repl : raw) : 0u;
+        om[i] = sflt ? 255u : 0u;
       }
+      uint4 o;
+      o.x = u[0] | (u[1] << 16); o.y = u[2] | (u[3] << 16); o.z = u[4] | (u[5] << 16); o.w = u[6] | (u[7] << 16);
+      *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
     } else {
       const float4 *p = reinterpret_cast<const float4 *>(static_cast<const float *>(fb.depth_in) + base);
       const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
-      sensor[0] = q0.x; sensor[1] = q0.y; sensor[2] = q0.z; sensor[3] = q0.w;
-      sensor[4] = q1.x; sensor[5] = q1.y; sensor[6] = q1.z; sensor[7] = q1.w;
-    }
-    float od[8];
-    uint32_t om[8];
+      const float sensor[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      float od[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const FragOut o = fragment(sensor[i], zw[i], sp);
-      od[i] = o.depth; om[i] = o.mask;
-    }
-    if (ENC == 1) {
-      uint32_t u[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) u[i] = f32_to_u16(od[i]);   // convertTo(CV_16U, 1000), :311
-      uint4 q;
-      q.x = u[0] | (u[1] << 16); q.y = u[2] | (u[3] << 16); q.z = u[4] | (u[5] << 16); q.w = u[6] | (u[7] << 16);
-      *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = q;
-    } else {
-      float4 *p = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
-      p[0] = make_float4(od[0], od[1], od[2], od[3]);
-      p[1] = make_float4(od[4], od[5], od[6], od[7]);
+      for (int i = 0; i < 8; ++i) {
+        const bool drawn = zw[i] != 1.0f;
+        const bool sflt = drawn && (sensor[i] > (virt[i] - sp.max_diff));
+        od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
+        om[i] = sflt ? 255u : 0u;
+      }
+      float4 *po = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
+      po[0] = make_float4(od[0], od[1], od[2], od[3]);
+      po[1] = make_float4(od[4], od[5], od[6], od[7]);
     }
     if (fb.mask_out) {
       uint2 mq;
@@ -714,6 +945,15 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
 // ------------------------------------------------------------------------------------------
 // host-side launcher for one batch
 // ------------------------------------------------------------------------------------------
+// folds the per-frame flag words into the context's sticky status word
+__global__ void ruf_status_kernel(const uint32_t *__restrict__ ctr_all, int n_frames, uint32_t *status)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const uint32_t flags = ctr_all[(size_t)f * kCtrWords + kCtrFlags];
+  if (flags) atomicOr(status, flags);
+}
+
 cudaError_t check_kernel_image()
 {
   cudaFuncAttributes fa;
@@ -727,7 +967,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
 {
   cudaError_t err;
   int launches = 0;
-  err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_frames * d.ctr_stride * sizeof(uint32_t), s);
+  err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_frames * kCtrWords * sizeof(uint32_t), s);
   if (err != cudaSuccess) return err;
   if (ev) cudaEventRecord(ev[0], s);
   {
@@ -738,31 +978,26 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (ev) cudaEventRecord(ev[1], s);
   }
   {
-    dim3 grid((unsigned)((d.n_tris + 2 + 255) / 256), (unsigned)n_frames);
-    ruf_setup_kernel<<<grid, 256, 0, s>>>(m, ws.mvp, d, bg_z, ws.recs, ws.big, ws.ctr);
+    dim3 grid((unsigned)d.n_setup_ctas, (unsigned)n_frames);
+    const size_t smem = (size_t)d.ntiles * 2 * sizeof(uint32_t);
+    ruf_setup_bin_kernel<kTrisPerThread><<<grid, kSetupThreads, smem, s>>>(m, ws.mvp, d, bg_z, ws.big, ws.bins,
+                                                                         ws.table, ws.ctr);
     ++launches;
     if (ev) cudaEventRecord(ev[2], s);
-  }
-  ruf_scan_kernel<<<(unsigned)n_frames, 256, 0, s>>>(d, ws.ctr, ws.status);
-  ++launches;
-  if (ev) cudaEventRecord(ev[3], s);
-  {
-    unsigned per_frame = (unsigned)((d.cap_rec + 255) / 256);
-    if (per_frame > 48) per_frame = 48;
-    if (per_frame < 1) per_frame = 1;
-    dim3 grid(per_frame, (unsigned)n_frames);
-    ruf_bin_kernel<<<grid, 256, 0, s>>>(d, ws.recs, ws.bins, ws.ctr);
-    ++launches;
-    if (ev) cudaEventRecord(ev[4], s);
   }
   {
     dim3 grid((unsigned)d.ntiles, (unsigned)n_frames);
     if (enc == 1)
-      ruf_raster_filter_kernel<1><<<grid, kRasterThreads, 0, s>>>(d, ws.big, ws.bins, ws.ctr, sp, fb);
+      ruf_raster_filter_kernel<1><<<grid, kRasterBlock, 0, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, sp, fb);
     else
-      ruf_raster_filter_kernel<0><<<grid, kRasterThreads, 0, s>>>(d, ws.big, ws.bins, ws.ctr, sp, fb);
+      ruf_raster_filter_kernel<0><<<grid, kRasterBlock, 0, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, sp, fb);
     ++launches;
-    if (ev) cudaEventRecord(ev[5], s);
+    if (ev) cudaEventRecord(ev[3], s);
+  }
+  {
+    ruf_status_kernel<<<(unsigned)((n_frames + 255) / 256), 256, 0, s>>>(ws.ctr, n_frames, ws.status);
+    ++launches;
+    if (ev) cudaEventRecord(ev[4], s);
   }
   if (n_launches) *n_launches = launches;
   return cudaGetLastError();
