@@ -15,7 +15,8 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 HOST = os.path.join(PKG_DIR, "host")
-LIB_PATH = os.path.join(PKG_DIR, "libruf_b200.so")
+# RUF_LIB_PATH / RUF_EXTRA_NVCC: build or load an experimental variant next to the default library
+LIB_PATH = os.environ.get("RUF_LIB_PATH") or os.path.join(PKG_DIR, "libruf_b200.so")
 
 CUDA_SOURCES = ["ruf_kernels.cu", "ruf_api.cu"]
 HOST_SOURCES = ["ruf_host.cpp"]
@@ -61,7 +62,8 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(PKG_DIR, "..", "include"), "-o", LIB_PATH, *sources()]
+    extra = os.environ.get("RUF_EXTRA_NVCC", "").split()
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(PKG_DIR, "..", "include"), "-o", LIB_PATH, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

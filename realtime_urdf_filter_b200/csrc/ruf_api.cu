@@ -26,6 +26,8 @@ struct ruf_context {
   long long n_tris = 0;
   int n_parts = 0;
   float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;
+  float *part_aabb = nullptr;   // [n_parts][6]
+  uint2 *cta_parts = nullptr;   // [n_setup_ctas]
 
   // workspace
   int max_batch = 0;            // frames the workspace is sized for
@@ -162,7 +164,7 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
   const uintptr_t al = (uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_zbuf;
   fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (((uintptr_t)d_mask & 7) == 0);
   const ShaderParams sp = shader_params(c, max_diff, replace_value);
-  Model m{c->v0, c->v1, c->v2};
+  Model m{c->v0, c->v1, c->v2, c->part_aabb, c->cta_parts};
   const float bg_z = (float)(c->z_far * 0.99);   // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
   int launches = 0;
   cudaEvent_t *ev = nullptr;
@@ -254,7 +256,7 @@ int ruf_destroy(ruf_context *c)
   cudaDeviceSynchronize();
   free_workspace(c);
   free_staging(c);
-  cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2);
+  cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2); cudaFree(c->part_aabb); cudaFree(c->cta_parts);
   cudaFree(c->ws.status); cudaFree(c->d_lookat);
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < 2; ++i) {
@@ -302,6 +304,46 @@ int ruf_sync(ruf_context *c)
   return check_status(c, c->stream);
 }
 
+// per-part object-space boxes and the part range of every setup CTA (set-up time, on the host)
+static int upload_part_bounds(ruf_context *c, const float *h_xyz, const uint32_t *h_part, int64_t n_tris, int n_parts)
+{
+  std::vector<float> box((size_t)(n_parts > 0 ? n_parts : 1) * 6);
+  for (int p = 0; p < n_parts; ++p)
+    for (int k = 0; k < 3; ++k) { box[6 * p + k] = 3.0e38f; box[6 * p + 3 + k] = -3.0e38f; }
+  const int64_t n_ctas = (n_tris + 2 + kSetupTris - 1) / kSetupTris;
+  std::vector<uint2> range((size_t)n_ctas, make_uint2(0xffffffffu, 0u));
+  for (int64_t t = 0; t < n_tris; ++t) {
+    const uint32_t p = h_part[t];
+    if (p >= (uint32_t)n_parts) continue;
+    for (int v = 0; v < 3; ++v)
+      for (int k = 0; k < 3; ++k) {
+        const float x = h_xyz[9 * t + 3 * v + k];
+        // NaN / inf vertices never tighten the box (such triangles are dropped by the vertex stage anyway)
+        if (x < box[6 * p + k]) box[6 * p + k] = x;
+        if (x > box[6 * p + 3 + k]) box[6 * p + 3 + k] = x;
+        if (!(x == x) || x > 3.0e38f || x < -3.0e38f) { box[6 * p + k] = -3.0e38f; box[6 * p + 3 + k] = 3.0e38f; }
+      }
+    uint2 &r = range[(size_t)(t / kSetupTris)];
+    if (p < r.x) r.x = p;
+    if (p > r.y) r.y = p;
+  }
+  // the two background-quad triangles (indices n_tris, n_tris + 1) use matrix row n_parts: never culled
+  for (int64_t t = n_tris; t < n_tris + 2; ++t) {
+    uint2 &r = range[(size_t)(t / kSetupTris)];
+    if ((uint32_t)n_parts < r.x) r.x = (uint32_t)n_parts;
+    if ((uint32_t)n_parts > r.y) r.y = (uint32_t)n_parts;
+  }
+  for (uint2 &r : range)
+    if (r.x > r.y) r = make_uint2(0u, 0u);
+  cudaFree(c->part_aabb); cudaFree(c->cta_parts);
+  c->part_aabb = nullptr; c->cta_parts = nullptr;
+  RUF_CUDA(c, cudaMalloc(&c->part_aabb, box.size() * sizeof(float)));
+  RUF_CUDA(c, cudaMalloc(&c->cta_parts, range.size() * sizeof(uint2)));
+  RUF_CUDA(c, cudaMemcpy(c->part_aabb, box.data(), box.size() * sizeof(float), cudaMemcpyHostToDevice));
+  RUF_CUDA(c, cudaMemcpy(c->cta_parts, range.data(), range.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  return RUF_OK;
+}
+
 static int set_model_common(ruf_context *c, const float *d_xyz, const uint32_t *d_part, int64_t n_tris, int n_parts)
 {
   cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2);
@@ -338,6 +380,7 @@ int ruf_set_model(ruf_context *c, const float *tri_xyz, const uint32_t *tri_part
   }
   int rc = set_model_common(c, d_xyz, d_part, n_tris, n_parts);
   cudaFree(d_xyz); cudaFree(d_part);
+  if (rc == RUF_OK) rc = upload_part_bounds(c, tri_xyz, tri_part, n_tris, n_parts);
   return rc;
 }
 
@@ -347,7 +390,16 @@ int ruf_set_model_device(ruf_context *c, const void *d_tri_xyz, const void *d_tr
   if (n_tris < 0 || n_parts < 0 || (n_tris > 0 && (!d_tri_xyz || !d_tri_part)) || n_tris > (1LL << 30))
     return fail(c, RUF_ERR_INVALID, "bad model arguments");
   RUF_CUDA(c, cudaSetDevice(c->device));
-  return set_model_common(c, (const float *)d_tri_xyz, (const uint32_t *)d_tri_part, n_tris, n_parts);
+  int rc = set_model_common(c, (const float *)d_tri_xyz, (const uint32_t *)d_tri_part, n_tris, n_parts);
+  if (rc != RUF_OK) return rc;
+  // set-up time only: bring the soup to the host once to derive the per-part boxes
+  std::vector<float> h_xyz((size_t)n_tris * 9);
+  std::vector<uint32_t> h_part((size_t)n_tris);
+  if (n_tris > 0) {
+    RUF_CUDA(c, cudaMemcpy(h_xyz.data(), d_tri_xyz, h_xyz.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    RUF_CUDA(c, cudaMemcpy(h_part.data(), d_tri_part, h_part.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  return upload_part_bounds(c, h_xyz.data(), h_part.data(), n_tris, n_parts);
 }
 
 int ruf_reserve(ruf_context *c, int max_batch, int64_t rec_capacity, int64_t bin_capacity)

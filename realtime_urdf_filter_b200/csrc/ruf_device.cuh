@@ -34,8 +34,21 @@ constexpr int kStages = 2;                      // ring depth (a stage is releas
 constexpr int kBigTiles = 12;                   // bbox touching more tiles -> per-frame "big" list
 constexpr int kMaxUnits = 16;                   // row-block units (1 row x 8 samples) per record dealt to lanes;
                                                 // larger records are rasterised by the whole warp
-constexpr int kSetupThreads = 256;
-constexpr int kTrisPerThread = 2;
+// tuning knobs (overridable with -D for experiments; the defaults are the measured best)
+#ifndef RUF_SETUP_THREADS
+#define RUF_SETUP_THREADS 256
+#endif
+#ifndef RUF_TRIS_PER_THREAD
+#define RUF_TRIS_PER_THREAD 4
+#endif
+#ifndef RUF_SETUP_MIN_BLOCKS
+#define RUF_SETUP_MIN_BLOCKS 4
+#endif
+#ifndef RUF_RASTER_MIN_BLOCKS
+#define RUF_RASTER_MIN_BLOCKS 4
+#endif
+constexpr int kSetupThreads = RUF_SETUP_THREADS;
+constexpr int kTrisPerThread = RUF_TRIS_PER_THREAD;
 constexpr int kSetupTris = kSetupThreads * kTrisPerThread;   // triangles per setup CTA
 constexpr int kSegCap = 512;                    // table entries gathered per round by a raster CTA
 constexpr int kMaxTiles = 4096;
@@ -99,7 +112,10 @@ struct Model {
   const float4 *v0;      // xyz + part index bits in w
   const float4 *v1;
   const float4 *v2;
+  const float *part_aabb;   // [n_parts][6] object-space min xyz, max xyz
+  const uint2 *cta_parts;   // [n_setup_ctas] (lowest, highest) part index among the CTA's triangles
 };
+constexpr int kCullParts = 8;   // a setup CTA culls per part when its triangles span at most this many parts
 
 // cudaSuccess iff the loaded module has an image the current device can run (sm_100a only)
 cudaError_t check_kernel_image();

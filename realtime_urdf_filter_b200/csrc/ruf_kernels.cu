@@ -259,7 +259,8 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
 // be binned by the caller; clipped / many-tile triangles are pushed to the frame's big list here.
 __device__ __forceinline__ bool process_triangle(long long t, int frame, const Model &m,
                                                  const float *__restrict__ mvp_all, const Dims &d, float bg_z,
-                                                 TriRec *big, uint32_t *ctr, TriRec &r, uint32_t &tiles)
+                                                 TriRec *big, uint32_t *ctr, const uint8_t *pvis, uint32_t pmin,
+                                                 TriRec &r, uint32_t &tiles)
 {
   if (t >= d.n_tris + 2) return false;
   float3 a, b, c;
@@ -278,6 +279,7 @@ __device__ __forceinline__ bool process_triangle(long long t, int frame, const M
     part = (uint32_t)d.n_parts;
   }
   if (part > (uint32_t)d.n_parts) return false;
+  if (pvis && !pvis[part - pmin]) return false;     // the whole part is outside the view volume this frame
 
   const float4 *M = reinterpret_cast<const float4 *>(mvp_all + 16 * ((long long)frame * (d.n_parts + 1) + part));
   const float4 c0 = __ldg(M), c1 = __ldg(M + 1), c2 = __ldg(M + 2), c3 = __ldg(M + 3);
@@ -333,7 +335,7 @@ __device__ __forceinline__ bool process_triangle(long long t, int frame, const M
 // there, so no global per-triangle atomics, no scan kernel and no scatter kernel are needed.
 // ------------------------------------------------------------------------------------------
 template <int TPT>
-__global__ void __launch_bounds__(kSetupThreads)
+__global__ void __launch_bounds__(kSetupThreads, RUF_SETUP_MIN_BLOCKS)
 ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float bg_z, TriRec *big_all,
                      TriRec *bins_all, uint2 *table_all, uint32_t *ctr_all)
 {
@@ -346,8 +348,60 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float b
   TriRec *big = big_all + (size_t)frame * d.cap_big;
   uint32_t *ctr = ctr_all + (size_t)frame * kCtrWords;
 
+  // ---- per-part view-volume culling (result-neutral, DESIGN.md "Setup-stage rejects"): the 8 corners of
+  // a part's object-space box go through the part's MVP; if all 8 lie beyond one clip plane by a margin,
+  // every triangle of the part would be rejected one by one below, so the CTA skips them wholesale.
+  __shared__ uint8_t s_pvis[kCullParts];
+  __shared__ uint32_t s_anyvis;
+  const uint2 prange = __ldg(m.cta_parts + cta);
+  const bool cull = (prange.y - prange.x) < (uint32_t)kCullParts;
+  if (tid == 0) s_anyvis = 0;
   for (int i = tid; i < d.ntiles; i += kSetupThreads) s_cnt[i] = 0;
   __syncthreads();
+  if (cull && warp == 0) {
+    const int corner = lane & 7;
+#pragma unroll
+    for (int pass = 0; pass < kCullParts / 4; ++pass) {
+      const uint32_t part = prange.x + (uint32_t)(pass * 4 + (lane >> 3));
+      uint32_t out = 0;        // bit k: this corner is beyond plane k (near, +x, -x, +y, -y)
+      const bool have = part <= prange.y;
+      if (have && part < (uint32_t)d.n_parts) {
+        const float *bb = m.part_aabb + 6 * (size_t)part;
+        const float px = __ldg(bb + ((corner & 1) ? 3 : 0)), py = __ldg(bb + ((corner & 2) ? 4 : 1)),
+                    pz = __ldg(bb + ((corner & 4) ? 5 : 2));
+        const float4 *M = reinterpret_cast<const float4 *>(mvp_all + 16 * ((long long)frame * (d.n_parts + 1) + part));
+        const V4 c = xform(__ldg(M), __ldg(M + 1), __ldg(M + 2), __ldg(M + 3), px, py, pz);
+        if (finite4(c)) {
+          // margins: 1 % on the side planes, 1e-3 relative on the near plane -- far larger than the
+          // float rounding of the per-triangle tests they stand in for
+          const float wm = 1.01f * c.w, tol = 1e-3f * (fabsf(c.z) + fabsf(c.w));
+          out = (c.z + c.w < -tol ? 1u : 0u) | (c.x > wm ? 2u : 0u) | (-c.x > wm ? 4u : 0u) |
+                (c.y > wm ? 8u : 0u) | (-c.y > wm ? 16u : 0u);
+        }
+      }
+      uint32_t all = 0xffffffffu;      // planes that reject all 8 corners of my part
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const uint32_t b = (__ballot_sync(0xffffffffu, (out >> k) & 1u) >> (lane & 24)) & 0xffu;
+        if (b != 0xffu) all &= ~(1u << k);
+      }
+      if (have && corner == 0) {
+        const bool vis = (all & 31u) == 0u;
+        s_pvis[pass * 4 + (lane >> 3)] = vis ? 1 : 0;
+        if (vis) s_anyvis = 1;
+      }
+    }
+  }
+  if (cull) {
+    __syncthreads();
+    if (!s_anyvis) {
+      // nothing of this CTA can be visible: publish empty segments and leave
+      uint2 *table = table_all + (size_t)frame * d.ntiles * d.n_setup_ctas;
+      for (int i = tid; i < d.ntiles; i += kSetupThreads) table[(size_t)i * d.n_setup_ctas + cta] = make_uint2(0u, 0u);
+      return;
+    }
+  }
+  const uint8_t *pvis = cull ? s_pvis : nullptr;
 
   TriRec rec[TPT];
   uint32_t tiles[TPT];
@@ -355,7 +409,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float b
 #pragma unroll
   for (int k = 0; k < TPT; ++k) {
     const long long t = ((long long)cta * TPT + k) * kSetupThreads + tid;
-    valid[k] = process_triangle(t, frame, m, mvp_all, d, bg_z, big, ctr, rec[k], tiles[k]);
+    valid[k] = process_triangle(t, frame, m, mvp_all, d, bg_z, big, ctr, pvis, prange.x, rec[k], tiles[k]);
     if (valid[k]) {
       const int tx0 = tiles[k] & 255, tx1 = (tiles[k] >> 8) & 255, ty0 = (tiles[k] >> 16) & 255, ty1 = tiles[k] >> 24;
       for (int ty = ty0; ty <= ty1; ++ty)
@@ -564,7 +618,7 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
 }
 
 template <int ENC>
-__global__ void __launch_bounds__(kRasterBlock, 4)
+__global__ void __launch_bounds__(kRasterBlock, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
                          const uint2 *__restrict__ table_all, const uint32_t *__restrict__ ctr_all,
                          ShaderParams sp, FrameBuffers fb)
