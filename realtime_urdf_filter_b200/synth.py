@@ -235,16 +235,17 @@ def blob_mesh(rng, radii, slices, stacks, bump=0.04):
     Y = radii[1] * r * np.sin(TH) * np.sin(PH)
     Z = radii[2] * r * np.cos(TH)
     V = np.stack([X, Y, Z], -1)                      # (stacks+1, slices, 3)
-    out = []
-    for i in range(stacks):
-        for j in range(slices):
-            j1 = (j + 1) % slices
-            p00, p01, p10, p11 = V[i, j], V[i, j1], V[i + 1, j], V[i + 1, j1]
-            if i > 0:
-                out.append(np.concatenate([p00, p10, p01]))
-            if i < stacks - 1:
-                out.append(np.concatenate([p01, p10, p11]))
-    return np.asarray(out, np.float32)
+    j1 = (np.arange(slices) + 1) % slices
+    p00, p01 = V[:-1], V[:-1][:, j1]                 # (stacks, slices, 3)
+    p10, p11 = V[1:], V[1:][:, j1]
+    upper = np.concatenate([p00, p10, p01], -1)[1:]  # rows i > 0        -> (p00, p10, p01)
+    lower = np.concatenate([p01, p10, p11], -1)[:-1] # rows i < stacks-1 -> (p01, p10, p11)
+    # same triangle order as the original per-(i, j) loop: for each (i, j): upper (if i>0) then lower
+    out = np.zeros((stacks, slices, 2, 9))
+    has = np.zeros((stacks, slices, 2), bool)
+    out[1:, :, 0] = upper; has[1:, :, 0] = True
+    out[:-1, :, 1] = lower; has[:-1, :, 1] = True
+    return out[has].astype(np.float32)
 
 
 def blob_for_budget(rng, radii, budget, bump=0.04):
@@ -379,12 +380,13 @@ def pr2_like_scene(width=640, height=480, n_tris=90000, seed=7, name="pr2_like",
     parts, tris, pidx = [], [], []
     wall_tris = 0
     if walls:
-        # C3: two static wall meshes as in urdf/example.urdf.xml (boxes incl. the F4 doubles)
-        w1 = len(links); links.append(Link("wall1", -1, (2.2, 0.0, 1.0), (0, 0, math.pi / 2 + 0.785398163)))
-        w2 = len(links); links.append(Link("wall2", -1, (2.2, 0.0, 1.0), (0, 0, math.pi / 2 - 0.785398163)))
-        add_box(parts, tris, pidx, w1, (4, 0.5, 2))
-        add_box(parts, tris, pidx, w2, (4, 0.5, 2))
-        wall_tris = 48
+        # C3: two static wall meshes (Automatica-style cell walls): box-shaped RenderableMesh parts, 2.6 m ahead
+        w1 = len(links); links.append(Link("wall1", -1, (2.6, 0.9, 1.0), (0, 0, math.pi / 2 + 0.5)))
+        w2 = len(links); links.append(Link("wall2", -1, (2.6, -0.9, 1.0), (0, 0, math.pi / 2 - 0.5)))
+        slab = _lib.box_triangles(3.0, 0.2, 2.5)
+        add_mesh(parts, tris, pidx, w1, slab)
+        add_mesh(parts, tris, pidx, w2, slab)
+        wall_tris = 24
     wsum = sum(s[2] for s in specs)
     for (link, radii, weight, off_t, scale) in specs:
         budget = max(16, n_tris * weight / wsum)
@@ -412,7 +414,11 @@ def multi_robot_scene(width=1920, height=1080, n_tris=500000):
     """C5: four articulated PR2-like URDFs (~125k triangles each) with animated joint sweep; the
     camera rides on robot 0's head but is pulled back so that the neighbours are in view."""
     sc = pr2_like_scene(width, height, n_tris, seed=11, name="pr2_like_x4", copies=4)
-    sc.cam_xyz = (-1.6, 0.0, 0.9)
+    # external camera 3.2 m behind the row of robots, 1.3 m up, pitched 0.15 rad down, looking along +x
+    c, s_ = math.cos(0.15), math.sin(0.15)
+    sc.cam_link = -1
+    sc.cam_xyz = (-3.2, 0.0, 1.3)
+    sc.cam_R = np.array([[0.0, -s_, c], [-1.0, 0.0, 0.0], [0.0, -c, -s_]])   # columns: right, down, forward
     return sc
 
 

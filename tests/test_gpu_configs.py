@@ -1,0 +1,223 @@
+"""GPU parity on the other BASELINE.json configurations and on the edge cases of the path:
+odd image sizes, no mask, empty model, clipping-heavy views, capacity overflow + retry, models whose
+setup CTAs span many parts, more than 512 setup CTAs (multi-round gather), determinism."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle_py as orc
+import realtime_urdf_filter_b200 as ruf
+from realtime_urdf_filter_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_and_compare(sc, k=0, enc="u16", want_mask=True, ctx=None, max_diff=None, replace_value=None):
+    proj, _, _ = sc.proj()
+    fr = helpers.make_frame(sc, k, enc, nthreads=8)
+    md = sc.max_diff if max_diff is None else max_diff
+    rv = sc.replace_value if replace_value is None else replace_value
+    want_d, want_m, _ = helpers.oracle_filter(sc, fr, want_mask=want_mask, nthreads=8, max_diff=md, replace_value=rv)
+    own = ctx is None
+    if own:
+        ctx = ruf.Context(sc.width, sc.height)
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+    try:
+        got_d, got_m = ctx.filter(fr["depth"], proj, fr["view"], fr["pm"], md, rv, want_mask=want_mask)
+        st = ctx.stats()
+    finally:
+        if own:
+            ctx.close()
+    assert np.array_equal(got_d.view(np.uint8), want_d.view(np.uint8)), \
+        f"depth differs at {np.count_nonzero(got_d != want_d)} px"
+    if want_mask:
+        assert np.array_equal(got_m, want_m), f"mask differs at {np.count_nonzero(got_m != want_m)} px"
+    else:
+        assert got_m is None
+    return st, want_m
+
+
+def test_c3_walls_1280x960():
+    st, m = run_and_compare(helpers.scene("walls"), k=3)
+    assert 0.05 < (m == 255).mean() < 0.95
+
+
+def test_c5_four_robots_1920x1080_500k_triangles():
+    sc = helpers.scene("multi")
+    assert sc.n_tris > 490000 and sc.n_parts > 300
+    for k in (0, 9):
+        st, m = run_and_compare(sc, k=k)
+        assert st["visible_tris"] > 10000
+
+
+@pytest.mark.parametrize("size", [(100, 75), (648, 488), (64, 32), (1, 1), (37, 300), (72, 40)])
+def test_odd_image_sizes(size):
+    W, H = size
+    sc = synth.pr2_like_scene(W, H, n_tris=4000, name=f"odd{W}x{H}")
+    run_and_compare(sc, k=2, enc="u16")
+    run_and_compare(sc, k=2, enc="f32")
+
+
+def test_no_mask_and_default_replace_value():
+    sc = helpers.scene("pr2_small")
+    run_and_compare(sc, k=1, want_mask=False, replace_value=0.0)
+    run_and_compare(sc, k=1, enc="f32", want_mask=False, max_diff=0.2, replace_value=-1.0)
+
+
+def test_empty_model_only_background():
+    sc = helpers.scene("example")
+    empty = synth.Scene("empty", 640, 480, sc.P, [], [], np.zeros((0, 9), np.float32), np.zeros(0, np.uint32),
+                        -1, (0, 0, 0), sc.cam_R)
+    depth = np.random.default_rng(0).integers(0, 9000, (480, 640)).astype(np.uint16)
+    proj, _, _ = empty.proj()
+    view, pm = empty.frame(0)
+    mvp = orc.compose_mvp(proj, view, pm, 0)
+    want_d, want_m, _ = orc.filter_frame(depth, empty.tri, empty.tri_part, mvp, np.float32(0.1), np.float32(8.0),
+                                         np.float32(0.05), np.float32(5.0))
+    with ruf.Context(640, 480) as ctx:
+        ctx.set_model(empty.tri, empty.tri_part, 0)
+        got_d, got_m = ctx.filter(depth, proj, view, pm, 0.05, 5.0)
+    assert np.array_equal(got_d, want_d) and np.array_equal(got_m, want_m)
+    # float(7870) * 0.001f = 7.87 > to_linear(z_bg) - 0.05 = 7.86996..: 7870 mm itself is already filtered
+    assert (got_m == 255).sum() == (depth >= 7870).sum()
+
+
+def test_filter_before_set_model_is_an_error():
+    with ruf.Context(64, 48) as ctx:
+        with pytest.raises(ruf.RufError) as e:
+            ctx.filter(np.zeros((48, 64), np.uint16), np.zeros(16), np.zeros(16), np.zeros(0), 0.05, 5.0)
+        assert e.value.code == ruf.RUF_ERR_NO_MODEL
+
+
+def _camera_in_the_arm_scene():
+    """The camera sits inside the left upper arm: ~700 triangles cross the near plane (clipper output ->
+    big list), many are huge on screen."""
+    sc = synth.pr2_like_scene(640, 480, n_tris=60000, name="pr2_clip")
+    sc.cam_link = [l.name for l in sc.links].index("r0/l_upper_arm")
+    sc.cam_xyz = (0.15, 0.0, 0.0)
+    return sc
+
+
+def test_clipping_heavy_view_and_big_list_growth():
+    sc = _camera_in_the_arm_scene()
+    st, m = run_and_compare(sc, k=4)
+    assert st["big_tris"] > 20      # bg quad (2) + what the clipper emitted inside the viewport
+    # force the big list and the reference buffer to overflow: the host call grows them and retries
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        ctx.reserve(1, big_capacity=2, bin_capacity=64)
+        run_and_compare(sc, k=4, ctx=ctx)
+        run_and_compare(sc, k=5, ctx=ctx, enc="f32")
+
+
+def test_device_call_reports_overflow_then_succeeds_after_growth():
+    import torch
+    sc = helpers.scene("pr2_small")
+    proj, _, _ = sc.proj()
+    fr = helpers.make_frame(sc, 0, "u16")
+    want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_in, d_proj, d_view, d_pm = t(fr["depth"].view(np.int16)), t(proj), t(fr["view"]), t(fr["pm"])
+    d_out = torch.empty_like(d_in)
+    d_mask = torch.empty(d_in.shape, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        ctx.reserve(1, big_capacity=1024, bin_capacity=32)
+        args = (1, d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
+        ctx.filter_batch_device(*args)
+        with pytest.raises(ruf.RufError) as e:
+            ctx.sync()
+        assert e.value.code == ruf.RUF_ERR_OVERFLOW
+        for _ in range(12):                      # capacity doubles per failed attempt
+            ctx.filter_batch_device(*args)
+            try:
+                ctx.sync()
+                break
+            except ruf.RufError as err:
+                assert err.code == ruf.RUF_ERR_OVERFLOW
+        else:
+            pytest.fail("never recovered from overflow")
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint16), want_d)
+        assert np.array_equal(d_mask.cpu().numpy(), want_m)
+
+
+def test_one_triangle_per_part_disables_part_culling_but_stays_exact():
+    rng = np.random.default_rng(8)
+    n = 3000
+    sc0 = helpers.scene("example")
+    c = rng.uniform([-1.5, -1.0, 0.5], [1.5, 1.0, 4.0], (n, 1, 3))
+    tri = (c + rng.normal(0, 0.05, (n, 3, 3))).reshape(n, 9).astype(np.float32)
+    links = [synth.Link("l", -1)]
+    parts = [synth.Part(0, (0, 0, 0, 1), tuple(rng.normal(0, 0.01, 3))) for _ in range(n)]
+    sc = synth.Scene("soup", 640, 480, sc0.P, links, parts, tri, np.arange(n, dtype=np.uint32), -1, (0, 0, 0),
+                     np.eye(3))
+    run_and_compare(sc, k=0)
+
+
+def test_more_than_512_setup_ctas_multi_round_gather():
+    """> 512 * 1024 triangles: the raster kernel gathers its segment list in several rounds."""
+    rng = np.random.default_rng(9)
+    n = 600000
+    sc0 = synth.example_scene(320, 240)
+    c = rng.uniform([-1.2, -0.9, 0.6], [1.2, 0.9, 3.0], (n, 1, 3))
+    tri = (c + rng.normal(0, 0.01, (n, 3, 3))).reshape(n, 9).astype(np.float32)
+    nparts = 6
+    part = np.sort(rng.integers(0, nparts, n)).astype(np.uint32)
+    links = [synth.Link("l", -1)]
+    parts = [synth.Part(0, (0, 0, 0, 1), (0.01 * i, 0, 0)) for i in range(nparts)]
+    sc = synth.Scene("soup600k", 320, 240, sc0.P, links, parts, tri, part, -1, (0, 0, 0), np.eye(3))
+    st, _ = run_and_compare(sc, k=0)
+    assert st["binned_refs"] > 100000
+
+
+def test_batched_results_are_deterministic_and_frame_independent():
+    import torch
+    sc = helpers.scene("pr2_small")
+    proj, _, _ = sc.proj()
+    ks = list(range(6))
+    frames = [helpers.make_frame(sc, k, "f32") for k in ks]
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_in = t(np.stack([f["depth"] for f in frames]))
+    d_view, d_pm, d_proj = t(np.stack([f["view"] for f in frames])), t(np.stack([f["pm"] for f in frames])), t(proj)
+    outs = []
+    torch.cuda.synchronize()
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        for rep in range(3):
+            d_out = torch.full_like(d_in, -7.0)
+            d_mask = torch.full(d_in.shape, 3, dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            ctx.filter_batch_device(len(ks), d_in.data_ptr(), ruf.ENC_F32_M, d_proj.data_ptr(), d_view.data_ptr(),
+                                    d_pm.data_ptr(), sc.max_diff, sc.replace_value, d_out.data_ptr(),
+                                    d_mask.data_ptr(), 0)
+            ctx.sync()
+            outs.append((d_out.cpu().numpy(), d_mask.cpu().numpy()))
+    for o, m in outs[1:]:
+        assert np.array_equal(o.view(np.uint32), outs[0][0].view(np.uint32)) and np.array_equal(m, outs[0][1])
+    for i, fr in enumerate(frames):           # each frame of the batch equals its single-frame oracle result
+        want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+        assert np.array_equal(outs[0][0][i].view(np.uint32), want_d.view(np.uint32))
+        assert np.array_equal(outs[0][1][i], want_m)
+
+
+def test_all_u16_values_pass_through_unfiltered_pixels():
+    """The fused 16UC1 path writes the input bits for unfiltered pixels (round-trip identity)."""
+    sc = helpers.scene("example")
+    empty_tri, empty_part = np.zeros((0, 9), np.float32), np.zeros(0, np.uint32)
+    depth = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    P = synth.kinect_P(256, 256)
+    proj, tx, ty = ruf.projection_matrix(P, 256, 256)
+    view = ruf.view_matrix((0, 0, 0, 1), (0, 0, 0), (0, 0, 0, 1), (0, 0, 0), tx, ty)
+    mvp = orc.compose_mvp(proj, view, np.zeros(16), 0)
+    want_d, want_m, _ = orc.filter_frame(depth, empty_tri, empty_part, mvp, np.float32(0.1), np.float32(8.0),
+                                         np.float32(0.05), np.float32(5.0))
+    with ruf.Context(256, 256) as ctx:
+        ctx.set_model(empty_tri, empty_part, 0)
+        got_d, got_m = ctx.filter(depth, proj, view, np.zeros(0), 0.05, 5.0)
+    assert np.array_equal(got_d, want_d) and np.array_equal(got_m, want_m)
+    keep = want_m == 0
+    assert np.array_equal(got_d[keep], depth[keep]) and keep.sum() > 7000
