@@ -153,10 +153,10 @@ RUF_API int ruf_get_stats(ruf_context *ctx, ruf_stats *out);
 /* Per-kernel device timing (the analogue of the reference's gettimeofday bookkeeping around
  * filter(), src/urdf_filter.cpp:239-266, but per stage and on the device).  When enabled every
  * launch sequence is bracketed by CUDA events on the launching stream.  ruf_get_stage_times
- * synchronises, then returns the accumulated milliseconds of the four kernels in launch order
- * {pose, setup+bin, raster+filter, status} and the number of launch sequences they cover. */
+ * synchronises, then returns the accumulated milliseconds of the three kernels in launch order
+ * {pose, setup+bin, raster+filter} and the number of launch sequences they cover. */
 RUF_API int ruf_set_profiling(ruf_context *ctx, int enable);
-RUF_API int ruf_get_stage_times(ruf_context *ctx, double *ms4, int64_t *calls, int reset);
+RUF_API int ruf_get_stage_times(ruf_context *ctx, double *ms3, int64_t *calls, int reset);
 
 /* ------------------------------------------------------------------------------------ */
 /* Host-side matrices (double precision, same operation order as the reference + tf/GLU)  */

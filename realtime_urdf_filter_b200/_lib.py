@@ -289,7 +289,7 @@ class Context:
             C.c_void_p(d_part_model or 0), max_diff, replace_value, C.c_void_p(d_depth_out),
             C.c_void_p(d_mask_out or 0), C.c_void_p(d_zbuf_out or 0)))
 
-    STAGES = ("pose", "setup_bin", "raster_filter", "status")
+    STAGES = ("pose", "setup_bin", "raster_filter")
 
     def set_profiling(self, enable: bool):
         self._check(self._lib.ruf_set_profiling(self._h, int(enable)))

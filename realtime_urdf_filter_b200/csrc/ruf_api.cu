@@ -54,7 +54,7 @@ struct ruf_context {
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;     // kNumStages + 1 events per recorded launch sequence
   size_t ev_used = 0;                   // events in use since the last ruf_get_stage_times
-  double stage_ms[kNumStages] = {0, 0, 0, 0};
+  double stage_ms[kNumStages] = {0, 0, 0};
   int64_t stage_calls = 0;
 };
 

@@ -8,7 +8,6 @@
 //   K2 ruf_raster_filter_kernel   one CTA / (frame, 64x32 tile): gathers its segments with bulk
 //                           async copies (TMA) into smem -> smem z-tile (min) -> fused fragment
 //                           shader + encode + store
-//   K3 ruf_status_kernel    folds per-frame overflow flags into the sticky status word
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,7 +31,10 @@ constexpr int kRasterBlock = kRasterThreads + 32;   // + one producer warp (bulk
 constexpr int kChunk = 256;                     // records per ring stage (one per consumer thread)
 constexpr int kStages = 2;                      // ring depth (a stage is released as soon as its records sit in registers)
 constexpr int kBigTiles = 12;                   // bbox touching more tiles -> per-frame "big" list
-constexpr int kMaxUnits = 16;                   // row-block units (1 row x 8 samples) per record dealt to lanes;
+#ifndef RUF_MAX_UNITS
+#define RUF_MAX_UNITS 32
+#endif
+constexpr int kMaxUnits = RUF_MAX_UNITS;                   // row-block units (1 row x 8 samples) per record dealt to lanes;
                                                 // larger records are rasterised by the whole warp
 // tuning knobs (overridable with -D for experiments; the defaults are the measured best)
 #ifndef RUF_SETUP_THREADS
@@ -50,10 +52,13 @@ constexpr int kMaxUnits = 16;                   // row-block units (1 row x 8 sa
 constexpr int kSetupThreads = RUF_SETUP_THREADS;
 constexpr int kTrisPerThread = RUF_TRIS_PER_THREAD;
 constexpr int kSetupTris = kSetupThreads * kTrisPerThread;   // triangles per setup CTA
-constexpr int kSegCap = 512;                    // table entries gathered per round by a raster CTA
+#ifndef RUF_SEG_CAP
+#define RUF_SEG_CAP 512
+#endif
+constexpr int kSegCap = RUF_SEG_CAP;                    // table entries gathered per round by a raster CTA
 constexpr int kMaxTiles = 4096;
 
-constexpr int kNumStages = 4;                   // pose, setup+bin, raster+filter, status
+constexpr int kNumStages = 3;                   // pose, setup+bin, raster+filter
 constexpr uint32_t kFlagBigOverflow = 1u;
 constexpr uint32_t kFlagBinOverflow = 2u;
 
@@ -70,6 +75,8 @@ struct __align__(16) TriRec {
   uint32_t pad;
 };
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+// dynamic shared memory of the raster kernel: record ring + per-warp unit tables
+constexpr size_t kRasterDynSmem = sizeof(TriRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
 
 // Per-frame counter block (uint32 words): [0] big-list entries  [1] tile references  [2] flags
 // [3] kept (binned) triangles

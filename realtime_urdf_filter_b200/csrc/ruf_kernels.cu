@@ -532,6 +532,12 @@ __device__ __forceinline__ void smem_min(uint32_t saddr, uint32_t v)
 {
   asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t smem_add(uint32_t saddr, uint32_t v)
+{
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ uint32_t smem_ld(uint32_t saddr)
 {
   uint32_t v;
@@ -621,26 +627,34 @@ template <int ENC>
 __global__ void __launch_bounds__(kRasterBlock, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
                          const uint2 *__restrict__ table_all, const uint32_t *__restrict__ ctr_all,
-                         ShaderParams sp, FrameBuffers fb)
+                         uint32_t *status, ShaderParams sp, FrameBuffers fb)
 {
   // Warp roles: warps 0..7 (kRasterThreads = 256 threads) rasterise and shade; warp 8 is the producer
   // that streams the tile's triangle records into the shared-memory ring with bulk async copies.
-  __shared__ __align__(128) TriRec sbuf[kStages][kChunk];
+  // dynamic shared memory (more than the 48 KB static limit): record ring, then the unit tables
+  extern __shared__ __align__(128) unsigned char s_raster_dyn[];
+  TriRec (*sbuf)[kChunk] = reinterpret_cast<TriRec (*)[kChunk]>(s_raster_dyn);
+  uint16_t (*s_units)[32 * kMaxUnits] =
+      reinterpret_cast<uint16_t (*)[32 * kMaxUnits]>(s_raster_dyn + sizeof(TriRec) * kStages * kChunk);
   __shared__ __align__(16) uint32_t sz[kTilePix];
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ uint32_t s_nseg, s_total, s_next;
   __shared__ uint32_t seg_src[kSegCap], seg_off[kSegCap], seg_cnt[kSegCap];
-  __shared__ uint16_t s_units[kRasterThreads / 32][32 * kMaxUnits];
   __shared__ uint8_t s_bigcls[kRasterThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_producer = warp == kRasterThreads / 32;
-  const int tile = blockIdx.x, frame = blockIdx.y;
-  const int tile_x0 = (tile % d.tiles_x) * kTileW, tile_y0 = (tile / d.tiles_x) * kTileH;
+  const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
+  const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
   const uint32_t *ctr = ctr_all + (size_t)frame * kCtrWords;
   const TriRec *bins = bins_all + (size_t)frame * d.cap_bin;
   const uint2 *table = table_all + ((size_t)frame * d.ntiles + tile) * d.n_setup_ctas;
   const uint32_t sz_addr = smem_u32(sz);
+  // fold this frame's overflow flags into the context's sticky status word (one thread per frame)
+  if (tile == 0 && threadIdx.x == 0) {
+    const uint32_t flags = ctr[kCtrFlags];
+    if (flags) atomicOr(status, flags);
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -777,7 +791,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       const uint32_t nbatches = (cnt + 31u) / 32u;
       for (;;) {
         uint32_t bt = 0;
-        if (lane == 0) bt = atomicAdd(&s_next, 1u);
+        if (lane == 0) bt = smem_add(smem_u32(&s_next), 1u);
         bt = __shfl_sync(0xffffffffu, bt, 0);
         if (bt >= nbatches) break;
         const int c = (int)(bt / (kChunk / 32));
@@ -999,19 +1013,17 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
 // ------------------------------------------------------------------------------------------
 // host-side launcher for one batch
 // ------------------------------------------------------------------------------------------
-// folds the per-frame flag words into the context's sticky status word
-__global__ void ruf_status_kernel(const uint32_t *__restrict__ ctr_all, int n_frames, uint32_t *status)
-{
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_frames) return;
-  const uint32_t flags = ctr_all[(size_t)f * kCtrWords + kCtrFlags];
-  if (flags) atomicOr(status, flags);
-}
-
 cudaError_t check_kernel_image()
 {
   cudaFuncAttributes fa;
-  return cudaFuncGetAttributes(&fa, (const void *)ruf_raster_filter_kernel<1>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)ruf_raster_filter_kernel<1>);
+  if (e != cudaSuccess) return e;
+  // opt in to > 48 KB of dynamic shared memory (per device: call once per context)
+  e = cudaFuncSetAttribute((const void *)ruf_raster_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kRasterDynSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void *)ruf_raster_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)kRasterDynSmem);
 }
 
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
@@ -1040,18 +1052,13 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (ev) cudaEventRecord(ev[2], s);
   }
   {
-    dim3 grid((unsigned)d.ntiles, (unsigned)n_frames);
+    dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (enc == 1)
-      ruf_raster_filter_kernel<1><<<grid, kRasterBlock, 0, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, sp, fb);
+      ruf_raster_filter_kernel<1><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, ws.status, sp, fb);
     else
-      ruf_raster_filter_kernel<0><<<grid, kRasterBlock, 0, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, sp, fb);
+      ruf_raster_filter_kernel<0><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, ws.status, sp, fb);
     ++launches;
     if (ev) cudaEventRecord(ev[3], s);
-  }
-  {
-    ruf_status_kernel<<<(unsigned)((n_frames + 255) / 256), 256, 0, s>>>(ws.ctr, n_frames, ws.status);
-    ++launches;
-    if (ev) cudaEventRecord(ev[4], s);
   }
   if (n_launches) *n_launches = launches;
   return cudaGetLastError();
