@@ -349,7 +349,8 @@ def run_b200(args, rank, world, local_rank):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(dom)
+            per_frame = json.load(f)["bytes_per_frame"].get(dom)
+            traffic = None if per_frame is None else per_frame * B      # per launch, like `achieved`
     except Exception:
         pass
 
