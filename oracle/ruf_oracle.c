@@ -529,30 +529,43 @@ static void raster_tri(wvert v0, wvert v1, wvert v2, float *zbuf, int W, int H, 
   }
 }
 
-static void render_tri(const float *m, const float *tri, float gx, float gy, float halfw, float halfh,
-                       float *zbuf, int W, int H, int row0, int row1)
+/* Vertex stage + clipping + viewport for one triangle: appends up to MAX_POLY-2 window-space triangles
+ * (a fan around vertex 0 of the clipped polygon) to out[] and returns how many. */
+typedef struct { wvert v[3]; } wtri;
+
+static int window_tris(const float *m, const float *tri, float gx, float gy, float halfw, float halfh, wtri *out)
 {
   vec4 poly[MAX_POLY];
   poly[0] = xform(m, tri);
   poly[1] = xform(m, tri + 3);
   poly[2] = xform(m, tri + 6);
-  if (!finite4(poly[0]) || !finite4(poly[1]) || !finite4(poly[2])) return;
+  if (!finite4(poly[0]) || !finite4(poly[1]) || !finite4(poly[2])) return 0;
   int n = 3, need = 0;
   for (int i = 0; i < 3; ++i)
     for (int k = 0; k < 5; ++k)
       if (!(plane_dist(poly[i], k, gx, gy) >= 0.0f)) need = 1;
   if (need) n = clip_poly(poly, 3, gx, gy);
-  if (n < 3) return;
+  if (n < 3) return 0;
   /* S4b: after clipping every vertex satisfies |x| <= gx*w, |y| <= gy*w, z >= -w, hence
    * w >= 0; a vertex with w == 0 (or a NaN produced by clipping) has no window position,
    * so the whole primitive is dropped instead of feeding inf/NaN to the snap. */
   for (int i = 0; i < n; ++i)
-    if (!(poly[i].w > 0.0f)) return;
+    if (!(poly[i].w > 0.0f)) return 0;
   wvert wv[MAX_POLY];
   for (int i = 0; i < n; ++i)
-    if (!to_window(poly[i], halfw, halfh, &wv[i])) return;
-  for (int i = 2; i < n; ++i)
-    raster_tri(wv[0], wv[i - 1], wv[i], zbuf, W, H, row0, row1);
+    if (!to_window(poly[i], halfw, halfh, &wv[i])) return 0;
+  for (int i = 2; i < n; ++i) {
+    out[i - 2].v[0] = wv[0]; out[i - 2].v[1] = wv[i - 1]; out[i - 2].v[2] = wv[i];
+  }
+  return n - 2;
+}
+
+static void render_tri(const float *m, const float *tri, float gx, float gy, float halfw, float halfh,
+                       float *zbuf, int W, int H, int row0, int row1)
+{
+  wtri w[MAX_POLY];
+  int n = window_tris(m, tri, gx, gy, halfw, halfh, w);
+  for (int i = 0; i < n; ++i) raster_tri(w[i].v[0], w[i].v[1], w[i].v[2], zbuf, W, H, row0, row1);
 }
 
 /* the background quad of src/urdf_filter.cpp:591-596 as two triangles */
@@ -579,24 +592,94 @@ ORC_API int orc_render(const float *tri, const uint32_t *tri_link, int64_t T,
   if (W <= 0 || H <= 0 || W > 4096 || H > 4096) return -1;
   const float halfw = 0.5f * (float)W, halfh = 0.5f * (float)H;
   const float gx = GUARD_PX / halfw, gy = GUARD_PX / halfh;
-  for (size_t i = 0; i < (size_t)W * H; ++i) zbuf[i] = 1.0f;   /* glClear, depth 1.0 */
+#pragma omp parallel for schedule(static) num_threads(nthreads > 1 ? nthreads : 1) if (nthreads > 1)
+  for (int64_t i = 0; i < (int64_t)W * H; ++i) zbuf[i] = 1.0f;   /* glClear, depth 1.0 */
   for (int64_t t = 0; t < T; ++t)
     if (tri_link[t] >= (uint32_t)L) return -2;
   if (nthreads < 1) nthreads = 1;
-  int nb = nthreads > 1 ? nthreads * 4 : 1;
-  if (nb > H) nb = H;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) if (nthreads > 1)
-  for (int b = 0; b < nb; ++b) {
-    int row0 = (int)((int64_t)H * b / nb), row1 = (int)((int64_t)H * (b + 1) / nb);
+  if (nthreads == 1) {
     if (bg_z > 0.0f) {
       float q[18];
       bg_quad(bg_z, q);
-      render_tri(mvp + 16 * (size_t)L, q, gx, gy, halfw, halfh, zbuf, W, H, row0, row1);
-      render_tri(mvp + 16 * (size_t)L, q + 9, gx, gy, halfw, halfh, zbuf, W, H, row0, row1);
+      render_tri(mvp + 16 * (size_t)L, q, gx, gy, halfw, halfh, zbuf, W, H, 0, H);
+      render_tri(mvp + 16 * (size_t)L, q + 9, gx, gy, halfw, halfh, zbuf, W, H, 0, H);
     }
     for (int64_t t = 0; t < T; ++t)
-      render_tri(mvp + 16 * (size_t)tri_link[t], tri + 9 * t, gx, gy, halfw, halfh, zbuf, W, H, row0, row1);
+      render_tri(mvp + 16 * (size_t)tri_link[t], tri + 9 * t, gx, gy, halfw, halfh, zbuf, W, H, 0, H);
+    return 0;
   }
+  /* Multi-threaded form (same result: the per-pixel min does not depend on the order):
+   *   phase 1  vertex stage + clipping once per triangle, threads own contiguous triangle ranges and
+   *            keep the window-space triangles that can touch a pixel row of the image;
+   *   phase 2  row bands, every band walks all kept triangles and rasterises its rows. */
+  typedef struct { wtri *p; size_t n, cap; } wlist;
+  wlist *lists = (wlist *)calloc((size_t)nthreads, sizeof(wlist));
+  if (!lists) return -3;
+  int failed = 0;
+#pragma omp parallel num_threads(nthreads)
+  {
+#ifdef _OPENMP
+    const int me = omp_get_thread_num(), nth = omp_get_num_threads();
+#else
+    const int me = 0, nth = 1;
+#endif
+    wlist *l = &lists[me];
+    const int64_t total = T + (bg_z > 0.0f ? 2 : 0);
+    const int64_t lo = total * me / nth, hi = total * (me + 1) / nth;
+    float q[18];
+    bg_quad(bg_z > 0.0f ? bg_z : 1.0f, q);
+    for (int64_t t = lo; t < hi; ++t) {
+      wtri w[MAX_POLY];
+      int n;
+      if (t < T) n = window_tris(mvp + 16 * (size_t)tri_link[t], tri + 9 * t, gx, gy, halfw, halfh, w);
+      else n = window_tris(mvp + 16 * (size_t)L, q + 9 * (t - T), gx, gy, halfw, halfh, w);
+      for (int i = 0; i < n; ++i) {
+        /* cheap reject of triangles that cannot touch any pixel centre row / column of the image */
+        int32_t ymin = w[i].v[0].Y, ymax = ymin, xmin = w[i].v[0].X, xmax = xmin;
+        for (int k = 1; k < 3; ++k) {
+          if (w[i].v[k].Y < ymin) ymin = w[i].v[k].Y;
+          if (w[i].v[k].Y > ymax) ymax = w[i].v[k].Y;
+          if (w[i].v[k].X < xmin) xmin = w[i].v[k].X;
+          if (w[i].v[k].X > xmax) xmax = w[i].v[k].X;
+        }
+        if (floor_shift((int64_t)ymin - SUBPIX_HALF + (SUBPIX - 1)) > floor_shift((int64_t)ymax - SUBPIX_HALF)) continue;
+        if (floor_shift((int64_t)xmin - SUBPIX_HALF + (SUBPIX - 1)) > floor_shift((int64_t)xmax - SUBPIX_HALF)) continue;
+        if (ymax < 0 || xmax < 0 || ymin > (int64_t)H * SUBPIX || xmin > (int64_t)W * SUBPIX) continue;
+        if (l->n == l->cap) {
+          size_t cap = l->cap ? 2 * l->cap : 4096;
+          wtri *np_ = (wtri *)realloc(l->p, cap * sizeof(wtri));
+          if (!np_) { failed = 1; break; }
+          l->p = np_; l->cap = cap;
+        }
+        l->p[l->n++] = w[i];
+      }
+    }
+  }
+  if (!failed) {
+    int nb = nthreads * 4;
+    if (nb > H) nb = H;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int b = 0; b < nb; ++b) {
+      const int row0 = (int)((int64_t)H * b / nb), row1 = (int)((int64_t)H * (b + 1) / nb);
+      const int64_t y_lo = (int64_t)row0 * SUBPIX, y_hi = (int64_t)row1 * SUBPIX;
+      for (int th = 0; th < nthreads; ++th) {
+        const wlist *l = &lists[th];
+        for (size_t i = 0; i < l->n; ++i) {
+          const wtri *w = &l->p[i];
+          int32_t ymin = w->v[0].Y, ymax = ymin;
+          if (w->v[1].Y < ymin) ymin = w->v[1].Y;
+          if (w->v[1].Y > ymax) ymax = w->v[1].Y;
+          if (w->v[2].Y < ymin) ymin = w->v[2].Y;
+          if (w->v[2].Y > ymax) ymax = w->v[2].Y;
+          if (ymax < y_lo || ymin > y_hi) continue;
+          raster_tri(w->v[0], w->v[1], w->v[2], zbuf, W, H, row0, row1);
+        }
+      }
+    }
+  }
+  for (int th = 0; th < nthreads; ++th) free(lists[th].p);
+  free(lists);
+  if (failed) return -3;
   return 0;
 }
 
@@ -642,12 +725,11 @@ ORC_API float orc_to_linear_depth(float d, float z_near, float z_far)
  *   virt_out  : optional linearised virtual depth (metres; 0 where no fragment)
  * Pixels no fragment covered keep the clear colour 0 (src/urdf_filter.cpp:566).
  */
-ORC_API void orc_filter(const void *depth_in, int enc, const float *zbuf, int W, int H,
-                        float z_near, float z_far, float max_diff, float replace_value,
-                        void *depth_out, uint8_t *mask_out, float *virt_out)
+static void filter_range(const void *depth_in, int enc, const float *zbuf, size_t i0, size_t i1,
+                         float z_near, float z_far, float max_diff, float replace_value,
+                         void *depth_out, uint8_t *mask_out, float *virt_out)
 {
-  const size_t n = (size_t)W * H;
-  for (size_t i = 0; i < n; ++i) {
+  for (size_t i = i0; i < i1; ++i) {
     float sensor = (enc == ENC_U16_MM) ? (float)((const uint16_t *)depth_in)[i] * 0.001f
                                        : ((const float *)depth_in)[i];
     float out, s, virt = 0.0f;
@@ -665,6 +747,27 @@ ORC_API void orc_filter(const void *depth_in, int enc, const float *zbuf, int W,
   }
 }
 
+ORC_API void orc_filter_mt(const void *depth_in, int enc, const float *zbuf, int W, int H,
+                           float z_near, float z_far, float max_diff, float replace_value,
+                           void *depth_out, uint8_t *mask_out, float *virt_out, int nthreads)
+{
+  const size_t n = (size_t)W * H;
+  if (nthreads < 1) nthreads = 1;
+  const int chunks = nthreads * 4;
+#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+  for (int c = 0; c < chunks; ++c)
+    filter_range(depth_in, enc, zbuf, n * c / chunks, n * (c + 1) / chunks, z_near, z_far, max_diff,
+                 replace_value, depth_out, mask_out, virt_out);
+}
+
+ORC_API void orc_filter(const void *depth_in, int enc, const float *zbuf, int W, int H,
+                        float z_near, float z_far, float max_diff, float replace_value,
+                        void *depth_out, uint8_t *mask_out, float *virt_out)
+{
+  filter_range(depth_in, enc, zbuf, 0, (size_t)W * H, z_near, z_far, max_diff, replace_value, depth_out,
+               mask_out, virt_out);
+}
+
 /* One whole frame: render + filter.  Returns 0 on success. */
 ORC_API int orc_filter_frame(const void *depth_in, int enc, int W, int H,
                              const float *tri, const uint32_t *tri_link, int64_t T,
@@ -677,7 +780,8 @@ ORC_API int orc_filter_frame(const void *depth_in, int enc, int W, int H,
   float bg_z = (float)((double)z_far * 0.99);       /* glVertex3f(.., far_plane_*0.99) */
   int rc = orc_render(tri, tri_link, T, mvp, L, W, H, bg_z, zbuf, nthreads);
   if (rc == 0)
-    orc_filter(depth_in, enc, zbuf, W, H, z_near, z_far, max_diff, replace_value, depth_out, mask_out, NULL);
+    orc_filter_mt(depth_in, enc, zbuf, W, H, z_near, z_far, max_diff, replace_value, depth_out, mask_out, NULL,
+                  nthreads);
   if (!zbuf_out) free(zbuf);
   return rc;
 }
