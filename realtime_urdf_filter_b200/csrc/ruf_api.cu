@@ -3,6 +3,7 @@
 // path lives here except the three scalar shader constants.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -495,7 +496,12 @@ int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, in
     return fail(c, RUF_ERR_INVALID, "bad arguments");
   if (!c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
   RUF_CUDA(c, cudaSetDevice(c->device));
-  int chunk = n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1);
+  // frames per pipeline chunk: large enough for efficient copies/launches, small enough to overlap (measured)
+  int chunk = n_frames >= 128 ? 32 : (n_frames >= 64 ? 16 : (n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1)));
+  if (const char *e = getenv("RUF_HOST_CHUNK")) {      // tuning aid
+    const int v = atoi(e);
+    if (v >= 1 && v <= 4096) chunk = v < n_frames ? v : n_frames;
+  }
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_workspace(c, chunk);
     if (rc != RUF_OK) return rc;
