@@ -136,6 +136,39 @@ RUF_API int ruf_filter_batch_host(ruf_context *ctx, int n_frames, const void *de
                                   float max_diff, float replace_value,
                                   void *depth_out, uint8_t *mask_out);
 
+/* ------------------------------------------------------------------------------------ */
+/* Forward kinematics on the device ("next" row of the hot path: the caller side)          */
+/* ------------------------------------------------------------------------------------ */
+
+/* Kinematic tree of the loaded model.  Replaces, per frame, the L tf lookups of
+ * URDFRenderer::update_link_transforms (src/urdf_renderer.cpp:173-190) and the camera lookup of
+ * render (src/urdf_filter.cpp:522): link poses are computed from joint positions on the device
+ * (what robot_state_publisher + tf do on the host).
+ *   parent[l]      index of the parent link (< l) or -1 for the fixed frame
+ *   joint_type[l]  0 fixed, 1 revolute/continuous, 2 prismatic
+ *   origin[l]      16 doubles, column-major: joint origin (parent_T_joint)
+ *   axis[l]        3 doubles, unit joint axis
+ *   part_link[p]   link that part p rides on; part_local[p] = link_offset [* suffix] (16 doubles)
+ *   cam_link       link the camera rides on (-1: fixed frame); cam_mount = optical frame in that link
+ *   view_pre       LookAt * inverse(camera_offset) (ruf_view_matrix with an identity camera transform)
+ * All host pointers; n_parts must equal the loaded model's. */
+RUF_API int ruf_set_kinematics(ruf_context *ctx, int n_links, const int32_t *parent, const int32_t *joint_type,
+                               const double *origin, const double *axis, const int32_t *part_link,
+                               const double *part_local, int cam_link, const double *cam_mount,
+                               const double *view_pre);
+
+/* Joint positions -> part models + view matrices, device buffers, asynchronous.
+ * d_joint_q [n_frames][n_links]; d_part_model_out [n_frames][n_parts][16]; d_view_out [n_frames][16].
+ * camera_tx / camera_ty as returned by ruf_projection_matrix. */
+RUF_API int ruf_fk_batch_device(ruf_context *ctx, int n_frames, const double *d_joint_q, double camera_tx,
+                                double camera_ty, double *d_part_model_out, double *d_view_out);
+
+/* ruf_filter_batch_device with the poses computed on the device from joint positions. */
+RUF_API int ruf_filter_batch_device_fk(ruf_context *ctx, int n_frames, const void *d_depth_in, int enc,
+                                       const double *d_proj, const double *d_joint_q, double camera_tx,
+                                       double camera_ty, float max_diff, float replace_value,
+                                       void *d_depth_out, uint8_t *d_mask_out, float *d_zbuf_out);
+
 RUF_API int ruf_host_alloc(void **ptr, size_t bytes);   /* cudaHostAlloc (pinned) */
 RUF_API int ruf_host_free(void *ptr);
 

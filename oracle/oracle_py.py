@@ -67,6 +67,9 @@ def load(native: bool = False) -> C.CDLL:
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.orc_filter_frame.restype = C.c_int
     lib.orc_max_threads.restype = C.c_int
+    lib.orc_sincos.argtypes = [C.c_double, _dp, _dp]
+    lib.orc_fk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp]
+    lib.orc_fk_outputs.argtypes = [_dp, C.c_int, C.c_void_p, _dp, C.c_int, _dp, _dp, C.c_double, C.c_double, _dp, _dp]
     _libs[key] = lib
     return lib
 
@@ -195,3 +198,29 @@ def f32_to_u16(a):
 
 def max_threads() -> int:
     return int(load().orc_max_threads())
+
+
+def sincos(x):
+    s, c = C.c_double(), C.c_double()
+    load().orc_sincos(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def fk(kin: dict, q):
+    """Oracle forward kinematics -> (links[n,16], part_models[P,16], view[16]) for joint positions q."""
+    n = len(kin["parent"])
+    parent = np.ascontiguousarray(kin["parent"], np.int32)
+    jt = np.ascontiguousarray(kin["joint_type"], np.int32)
+    origin = _f64(kin["origin"], 16 * n) if n else np.zeros(1)
+    axis = _f64(kin["axis"], 3 * n) if n else np.zeros(1)
+    qq = _f64(q, n) if n else np.zeros(1)
+    links = np.zeros((max(n, 1), 16))
+    load().orc_fk(n, parent.ctypes.data, jt.ctypes.data, _d(origin), _d(axis), _d(qq), _d(links))
+    P = len(kin["part_link"])
+    pl = np.ascontiguousarray(kin["part_link"], np.int32)
+    plocal = _f64(kin["part_local"], 16 * P) if P else np.zeros(1)
+    pm = np.zeros((max(P, 1), 16))
+    view = np.zeros(16)
+    load().orc_fk_outputs(_d(links), P, pl.ctypes.data, _d(plocal), int(kin["cam_link"]), _d(_f64(kin["cam_mount"], 16)),
+                          _d(_f64(kin["view_pre"], 16)), float(kin.get("tx", 0.0)), float(kin.get("ty", 0.0)), _d(pm), _d(view))
+    return links[:n], pm[:P], view

@@ -21,6 +21,8 @@
  *   include/shaders/urdf_filter.frag:14-35  linearise / compare / mix -> orc_filter
  *   src/urdf_filter.cpp:287-288,311      16UC1 <-> 32FC1 convertTo -> orc_u16_to_f32 / orc_f32_to_u16
  *   src/urdf_filter.cpp:729-735          readback of attachment 1 (.r) and 3 (.r as 0/255)
+ *   src/urdf_renderer.cpp:173-190 (per-frame tf lookups) -> orc_fk / orc_fk_outputs: forward kinematics
+ *                                        from joint positions (robot_state_publisher + tf, restated)
  *
  * PARITY STATUS: **parity unpinned** for everything except the 16UC1<->32FC1
  * encodings.  The reference has no tests, golden images or fixtures
@@ -257,6 +259,121 @@ ORC_API void orc_compose_mvp(const double *proj, const double *view,
   orc_lookat(LA);
   mat4_mul(proj, LA, M);
   for (int i = 0; i < 16; ++i) mvp[16 * (size_t)L + i] = (float)M[i];
+}
+
+/* ========================================================================= */
+/* 1b. Forward kinematics (the "next" row f1 of SURVEY.md section 8: replaces the   */
+/*     per-frame tf lookups of src/urdf_renderer.cpp:173-190 and urdf_filter.cpp:522) */
+/* ========================================================================= */
+
+/* sin and cos with a FIXED operation order (no libm, no fma) so that the CUDA kernel and this oracle
+ * give the same bits: Cody-Waite reduction by pi/2 (3 constants), then Taylor polynomials of degree
+ * 17 / 16 on [-pi/4, pi/4] in Horner form.  |error| < 3e-16 for |x| < 1e5. */
+ORC_API void orc_sincos(double x, double *sn, double *cs)
+{
+  const double two_over_pi = 0.63661977236758134308;
+  const double p1 = 1.57079632673412561417e+00;   /* pi/2 split in three parts (fdlibm) */
+  const double p2 = 6.07710050650619224932e-11;
+  const double p3 = 2.02226624879595063154e-21;
+  double kf = x * two_over_pi;
+  kf = (kf >= 0.0) ? floor(kf + 0.5) : -floor(-kf + 0.5);
+  double r = x - kf * p1;
+  r = r - kf * p2;
+  r = r - kf * p3;
+  const double z = r * r;
+  /* sin(r) = r + r*z*(S1 + z*(S2 + ... )) */
+  double ps = 2.81145725434552076320e-15;            /* 1/17! */
+  ps = ps * z + -7.64716373181981647590e-13;         /* -1/15! */
+  ps = ps * z + 1.60590438368216145994e-10;          /* 1/13! */
+  ps = ps * z + -2.50521083854417187751e-08;         /* -1/11! */
+  ps = ps * z + 2.75573192239858906526e-06;          /* 1/9! */
+  ps = ps * z + -1.98412698412698412698e-04;         /* -1/7! */
+  ps = ps * z + 8.33333333333333333333e-03;          /* 1/5! */
+  ps = ps * z + -1.66666666666666666667e-01;         /* -1/3! */
+  const double sr = r + (r * z) * ps;
+  double pc = 4.77947733238738529744e-14;            /* 1/16! */
+  pc = pc * z + -1.14707455977297247139e-11;         /* -1/14! */
+  pc = pc * z + 2.08767569878680989792e-09;          /* 1/12! */
+  pc = pc * z + -2.75573192239858906526e-07;         /* -1/10! */
+  pc = pc * z + 2.48015873015873015873e-05;          /* 1/8! */
+  pc = pc * z + -1.38888888888888888889e-03;         /* -1/6! */
+  pc = pc * z + 4.16666666666666666667e-02;          /* 1/4! */
+  pc = pc * z + -0.5;                                /* -1/2! */
+  const double cr = 1.0 + z * pc;
+  const long long k = (long long)kf;
+  switch ((int)(k & 3)) {
+    case 0: *sn = sr; *cs = cr; break;
+    case 1: *sn = cr; *cs = -sr; break;
+    case 2: *sn = -sr; *cs = -cr; break;
+    default: *sn = -cr; *cs = sr; break;
+  }
+}
+
+/* joint motion as a column-major 4x4: revolute = rotation by q about the unit axis (quaternion
+ * (axis*sin(q/2), cos(q/2)) -> tf::Matrix3x3::setRotation), prismatic = translation by axis*q */
+static void joint_motion(int type, const double *axis, double q, double *M)
+{
+  mat4_identity(M);
+  if (type == 1) {
+    double sn, cs;
+    orc_sincos(q * 0.5, &sn, &cs);
+    const double x = axis[0] * sn, y = axis[1] * sn, z = axis[2] * sn, w = cs;
+    const double d = x * x + y * y + z * z + w * w;
+    const double s = 2.0 / d;
+    const double xs = x * s, ys = y * s, zs = z * s;
+    const double wx = w * xs, wy = w * ys, wz = w * zs;
+    const double xx = x * xs, xy = x * ys, xz = x * zs;
+    const double yy = y * ys, yz = y * zs, zz = z * zs;
+    M[0] = 1.0 - (yy + zz); M[4] = xy - wz;         M[8] = xz + wy;
+    M[1] = xy + wz;         M[5] = 1.0 - (xx + zz); M[9] = yz - wx;
+    M[2] = xz - wy;         M[6] = yz + wx;         M[10] = 1.0 - (xx + yy);
+  } else if (type == 2) {
+    M[12] = axis[0] * q; M[13] = axis[1] * q; M[14] = axis[2] * q;
+  }
+}
+
+/* link_to_fixed of every link: T_link = (T_parent * origin) * motion(q), parents first.
+ *   parent[l] < l or -1; type 0 fixed / 1 revolute / 2 prismatic; origin n*16; axis n*3 (unit); q n
+ *   out: n*16 column-major */
+ORC_API void orc_fk(int n_links, const int32_t *parent, const int32_t *type, const double *origin,
+                    const double *axis, const double *q, double *out)
+{
+  for (int l = 0; l < n_links; ++l) {
+    double T[16], M[16];
+    if (parent[l] < 0) memcpy(T, origin + 16 * (size_t)l, sizeof(T));
+    else mat4_mul(out + 16 * (size_t)parent[l], origin + 16 * (size_t)l, T);
+    if (type[l] != 0) {
+      joint_motion(type[l], axis + 3 * (size_t)l, q[l], M);
+      mat4_mul(T, M, T);
+    }
+    memcpy(out + 16 * (size_t)l, T, sizeof(T));
+  }
+}
+
+/* part models and the view matrix of one frame from the link poses:
+ *   part_model[p] = T_link[part_link[p]] * part_local[p]
+ *   view = view_pre * inverse_rigid(T_link[cam_link] * cam_mount) with the origin shifted by
+ *          tx along the camera's x axis and ty along its y axis (src/urdf_filter.cpp:607-610);
+ *          view_pre = LookAt * inverse(camera_offset) (host); cam_link = -1: the fixed frame */
+ORC_API void orc_fk_outputs(const double *links, int n_parts, const int32_t *part_link, const double *part_local,
+                            int cam_link, const double *cam_mount, const double *view_pre, double tx, double ty,
+                            double *part_model, double *view)
+{
+  for (int p = 0; p < n_parts; ++p)
+    mat4_mul(links + 16 * (size_t)part_link[p], part_local + 16 * (size_t)p, part_model + 16 * (size_t)p);
+  double C[16];
+  if (cam_link < 0) memcpy(C, cam_mount, sizeof(C));
+  else mat4_mul(links + 16 * (size_t)cam_link, cam_mount, C);
+  /* tf::Transform::inverse: R^T, R^T * (-t); then the tx/ty shift along the inverse's basis columns */
+  double I[16];
+  mat4_identity(I);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) I[c * 4 + r] = C[r * 4 + c];
+  for (int r = 0; r < 3; ++r)
+    I[12 + r] = I[0 * 4 + r] * -C[12] + I[1 * 4 + r] * -C[13] + I[2 * 4 + r] * -C[14];
+  for (int r = 0; r < 3; ++r) I[12 + r] = I[12 + r] + I[0 * 4 + r] * tx;
+  for (int r = 0; r < 3; ++r) I[12 + r] = I[12 + r] + I[1 * 4 + r] * ty;
+  mat4_mul(view_pre, I, view);
 }
 
 /* ========================================================================= */

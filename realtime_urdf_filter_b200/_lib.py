@@ -56,6 +56,12 @@ SIGNATURES = {
                                           C.c_void_p]),
     "ruf_filter_batch_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "ruf_set_kinematics": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ruf_fk_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "ruf_filter_batch_device_fk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_double, C.c_double, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
     "ruf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ruf_host_free": (C.c_int, [C.c_void_p]),
     "ruf_get_stats": (C.c_int, [C.c_void_p, C.POINTER(RufStats)]),
@@ -288,6 +294,30 @@ class Context:
             self._h, n_frames, C.c_void_p(d_depth_in), enc, C.c_void_p(d_proj), C.c_void_p(d_view),
             C.c_void_p(d_part_model or 0), max_diff, replace_value, C.c_void_p(d_depth_out),
             C.c_void_p(d_mask_out or 0), C.c_void_p(d_zbuf_out or 0)))
+
+    def set_kinematics(self, parent, joint_type, origin, axis, part_link, part_local, cam_link, cam_mount, view_pre):
+        """Kinematic tree for the device-side forward kinematics (ruf_set_kinematics)."""
+        parent = np.ascontiguousarray(parent, np.int32)
+        jt = np.ascontiguousarray(joint_type, np.int32)
+        n = parent.size
+        origin = _as_f64(origin, 16 * n)
+        axis = _as_f64(axis, 3 * n)
+        pl = np.ascontiguousarray(part_link, np.int32)
+        plocal = _as_f64(part_local, 16 * self.n_parts)
+        self._check(self._lib.ruf_set_kinematics(self._h, n, parent.ctypes.data, jt.ctypes.data, origin.ctypes.data,
+                                                 axis.ctypes.data, pl.ctypes.data, plocal.ctypes.data, int(cam_link),
+                                                 _as_f64(cam_mount, 16).ctypes.data, _as_f64(view_pre, 16).ctypes.data))
+        self.n_links = n
+
+    def fk_batch_device(self, n_frames, d_joint_q, tx, ty, d_part_model_out, d_view_out):
+        self._check(self._lib.ruf_fk_batch_device(self._h, n_frames, C.c_void_p(d_joint_q), tx, ty,
+                                                  C.c_void_p(d_part_model_out), C.c_void_p(d_view_out)))
+
+    def filter_batch_device_fk(self, n_frames, d_depth_in, enc, d_proj, d_joint_q, tx, ty, max_diff, replace_value,
+                               d_depth_out, d_mask_out=0, d_zbuf_out=0):
+        self._check(self._lib.ruf_filter_batch_device_fk(
+            self._h, n_frames, C.c_void_p(d_depth_in), enc, C.c_void_p(d_proj), C.c_void_p(d_joint_q), tx, ty,
+            max_diff, replace_value, C.c_void_p(d_depth_out), C.c_void_p(d_mask_out or 0), C.c_void_p(d_zbuf_out or 0)))
 
     STAGES = ("pose", "setup_bin", "raster_filter")
 

@@ -48,6 +48,12 @@ struct ruf_context {
   cudaEvent_t ev_in[2]{}, ev_k[2]{}, ev_out[2]{};
   uint32_t *h_status = nullptr;  // pinned
 
+  // forward kinematics (ruf_set_kinematics)
+  Kinematics kin{};
+  void *kin_blob = nullptr;          // one device allocation holding all kinematics arrays
+  double *fk_links = nullptr, *fk_pm = nullptr, *fk_view = nullptr;
+  int fk_frames = 0;
+
   ruf_stats stats{};
   int last_frames = 0;
 
@@ -258,6 +264,7 @@ int ruf_destroy(ruf_context *c)
   free_workspace(c);
   free_staging(c);
   cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2); cudaFree(c->part_aabb); cudaFree(c->cta_parts);
+  cudaFree(c->kin_blob); cudaFree(c->fk_links); cudaFree(c->fk_pm); cudaFree(c->fk_view);
   cudaFree(c->ws.status); cudaFree(c->d_lookat);
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < 2; ++i) {
@@ -361,6 +368,8 @@ static int set_model_common(ruf_context *c, const float *d_xyz, const uint32_t *
   free_workspace(c);
   free_staging(c);
   c->want_big = c->want_bin = 0;
+  cudaFree(c->kin_blob);       // kinematics belong to the previous model
+  c->kin_blob = nullptr;
   return RUF_OK;
 }
 
@@ -522,6 +531,110 @@ int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj
 {
   return ruf_filter_batch_host(c, 1, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
                                mask_out);
+}
+
+int ruf_set_kinematics(ruf_context *c, int n_links, const int32_t *parent, const int32_t *joint_type,
+                       const double *origin, const double *axis, const int32_t *part_link, const double *part_local,
+                       int cam_link, const double *cam_mount, const double *view_pre)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (!c->v0) return fail(c, RUF_ERR_NO_MODEL, "load the model first (ruf_set_model)");
+  if (n_links < 0 || n_links > (1 << 20) || cam_link >= n_links || !cam_mount || !view_pre ||
+      (n_links > 0 && (!parent || !joint_type || !origin || !axis)) || (c->n_parts > 0 && (!part_link || !part_local)))
+    return fail(c, RUF_ERR_INVALID, "bad kinematics arguments");
+  std::vector<int32_t> off(n_links + 1, 0), idx;
+  for (int l = 0; l < n_links; ++l) {
+    if (parent[l] >= l || parent[l] < -1) return fail(c, RUF_ERR_INVALID, "links must be ordered parents first (link %d)", l);
+    if (joint_type[l] < 0 || joint_type[l] > 2) return fail(c, RUF_ERR_INVALID, "joint_type[%d] invalid", l);
+    std::vector<int32_t> chain;
+    for (int a = l; a >= 0; a = parent[a]) chain.push_back(a);
+    for (auto it = chain.rbegin(); it != chain.rend(); ++it) idx.push_back(*it);
+    off[l + 1] = (int32_t)idx.size();
+  }
+  for (int p = 0; p < c->n_parts; ++p)
+    if (part_link[p] < 0 || part_link[p] >= n_links) return fail(c, RUF_ERR_INVALID, "part_link[%d] out of range", p);
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  RUF_CUDA(c, cudaStreamSynchronize(c->stream));
+  // pack everything into one blob (8-byte aligned sections)
+  auto pad8 = [](size_t n) { return (n + 7) & ~(size_t)7; };
+  const size_t nl = (size_t)n_links, np = (size_t)c->n_parts;
+  const size_t o_type = 0, o_origin = pad8(o_type + nl * 4), o_axis = o_origin + nl * 128, o_off = o_axis + nl * 24,
+               o_idx = pad8(o_off + (nl + 1) * 4), o_plink = pad8(o_idx + idx.size() * 4), o_plocal = pad8(o_plink + np * 4),
+               o_mount = o_plocal + np * 128, o_pre = o_mount + 128, total = o_pre + 128;
+  std::vector<unsigned char> h(total, 0);
+  if (nl) {
+    std::memcpy(h.data() + o_type, joint_type, nl * 4);
+    std::memcpy(h.data() + o_origin, origin, nl * 128);
+    std::memcpy(h.data() + o_axis, axis, nl * 24);
+  }
+  std::memcpy(h.data() + o_off, off.data(), (nl + 1) * 4);
+  if (!idx.empty()) std::memcpy(h.data() + o_idx, idx.data(), idx.size() * 4);
+  if (np) {
+    std::memcpy(h.data() + o_plink, part_link, np * 4);
+    std::memcpy(h.data() + o_plocal, part_local, np * 128);
+  }
+  std::memcpy(h.data() + o_mount, cam_mount, 128);
+  std::memcpy(h.data() + o_pre, view_pre, 128);
+  cudaFree(c->kin_blob);
+  c->kin_blob = nullptr;
+  RUF_CUDA(c, cudaMalloc(&c->kin_blob, total));
+  RUF_CUDA(c, cudaMemcpy(c->kin_blob, h.data(), total, cudaMemcpyHostToDevice));
+  unsigned char *b = (unsigned char *)c->kin_blob;
+  Kinematics &k = c->kin;
+  k.n_links = n_links; k.n_parts = c->n_parts; k.cam_link = cam_link;
+  k.type = (const int32_t *)(b + o_type); k.origin = (const double *)(b + o_origin); k.axis = (const double *)(b + o_axis);
+  k.chain_off = (const int32_t *)(b + o_off); k.chain_idx = (const int32_t *)(b + o_idx);
+  k.part_link = (const int32_t *)(b + o_plink); k.part_local = (const double *)(b + o_plocal);
+  k.cam_mount = (const double *)(b + o_mount); k.view_pre = (const double *)(b + o_pre);
+  return RUF_OK;
+}
+
+static int ensure_fk_buffers(ruf_context *c, int frames)
+{
+  if (!c->kin_blob) return fail(c, RUF_ERR_INVALID, "no kinematics loaded (ruf_set_kinematics)");
+  if (c->kin.n_parts != c->n_parts) return fail(c, RUF_ERR_INVALID, "kinematics were set for another model");
+  if (c->fk_frames >= frames) return RUF_OK;
+  RUF_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->fk_links); cudaFree(c->fk_pm); cudaFree(c->fk_view);
+  c->fk_links = c->fk_pm = c->fk_view = nullptr;
+  c->fk_frames = 0;
+  const size_t f = (size_t)frames;
+  RUF_CUDA(c, cudaMalloc(&c->fk_links, f * (c->kin.n_links > 0 ? c->kin.n_links : 1) * 128));
+  RUF_CUDA(c, cudaMalloc(&c->fk_pm, f * (c->n_parts > 0 ? c->n_parts : 1) * 128));
+  RUF_CUDA(c, cudaMalloc(&c->fk_view, f * 128));
+  c->fk_frames = frames;
+  return RUF_OK;
+}
+
+int ruf_fk_batch_device(ruf_context *c, int n_frames, const double *d_joint_q, double camera_tx, double camera_ty,
+                        double *d_part_model_out, double *d_view_out)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (n_frames < 1 || !d_view_out || (c->n_parts > 0 && !d_part_model_out)) return fail(c, RUF_ERR_INVALID, "bad arguments");
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure_fk_buffers(c, n_frames);
+  if (rc != RUF_OK) return rc;
+  if (c->kin.n_links > 0 && !d_joint_q) return fail(c, RUF_ERR_INVALID, "d_joint_q is NULL");
+  cudaError_t e = launch_fk(c->kin, n_frames, d_joint_q, camera_tx, camera_ty, c->fk_links, d_part_model_out, d_view_out,
+                            c->stream);
+  if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "fk launch failed: %s", cudaGetErrorString(e));
+  return RUF_OK;
+}
+
+int ruf_filter_batch_device_fk(ruf_context *c, int n_frames, const void *d_depth_in, int enc, const double *d_proj,
+                               const double *d_joint_q, double camera_tx, double camera_ty, float max_diff,
+                               float replace_value, void *d_depth_out, uint8_t *d_mask_out, float *d_zbuf_out)
+{
+  if (!c) return RUF_ERR_INVALID;
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure_fk_buffers(c, n_frames);
+  if (rc != RUF_OK) return rc;
+  rc = ruf_fk_batch_device(c, n_frames, d_joint_q, camera_tx, camera_ty, c->fk_pm, c->fk_view);
+  if (rc != RUF_OK) return rc;
+  rc = ruf_filter_batch_device(c, n_frames, d_depth_in, enc, d_proj, c->fk_view, c->fk_pm, max_diff, replace_value,
+                               d_depth_out, d_mask_out, d_zbuf_out);
+  if (rc == RUF_OK) c->stats.kernel_launches += 2;
+  return rc;
 }
 
 int ruf_set_profiling(ruf_context *c, int enable)

@@ -128,6 +128,21 @@ constexpr int kCullParts = 8;   // a setup CTA culls per part when its triangles
 cudaError_t check_kernel_image();
 cudaError_t launch_pack_model(const float *d_tri_xyz, const uint32_t *d_tri_part, long long n_tris,
                               float4 *v0, float4 *v1, float4 *v2, cudaStream_t s);
+// forward kinematics: joint positions -> link poses -> part models + view matrix
+struct Kinematics {
+  int n_links, n_parts, cam_link;
+  const int32_t *type;        // [n_links] 0 fixed, 1 revolute, 2 prismatic
+  const double *origin;       // [n_links][16] parent_T_joint
+  const double *axis;         // [n_links][3] unit
+  const int32_t *chain_off;   // [n_links + 1] CSR offsets into chain_idx
+  const int32_t *chain_idx;   // ancestors of every link, root first, the link itself last
+  const int32_t *part_link;   // [n_parts]
+  const double *part_local;   // [n_parts][16] link_offset [* suffix]
+  const double *cam_mount;    // [16] camera optical frame in its link
+  const double *view_pre;     // [16] LookAt * inverse(camera_offset)
+};
+cudaError_t launch_fk(const Kinematics &k, int n_frames, const double *d_joint_q, double tx, double ty,
+                      double *d_links, double *d_part_model, double *d_view, cudaStream_t s);
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
                           const double *d_proj, const double *d_view, const double *d_part_model,
                           const double *d_lookat, float bg_z, int enc, const ShaderParams &sp,

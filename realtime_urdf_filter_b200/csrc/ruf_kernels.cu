@@ -1013,6 +1013,181 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
 // ------------------------------------------------------------------------------------------
 // host-side launcher for one batch
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Forward kinematics on the device (replaces the per-frame tf lookups of the reference's host:
+// src/urdf_renderer.cpp:173-190 for the links, src/urdf_filter.cpp:522,602-614 for the camera).
+// Double precision, no fma, the same operation order as the CPU oracle (orc_fk*): bit-exact.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void d_mat4_mul(const double *A, const double *B, double *C)
+{
+  double T[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += A[k * 4 + r] * B[c * 4 + k];
+      T[c * 4 + r] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) C[i] = T[i];
+}
+
+// sin / cos with a fixed operation order (Cody-Waite by pi/2 + Taylor in Horner form): same bits as the oracle
+__device__ __forceinline__ void d_sincos(double x, double &sn, double &cs)
+{
+  const double two_over_pi = 0.63661977236758134308;
+  const double p1 = 1.57079632673412561417e+00, p2 = 6.07710050650619224932e-11, p3 = 2.02226624879595063154e-21;
+  double kf = x * two_over_pi;
+  kf = (kf >= 0.0) ? floor(kf + 0.5) : -floor(-kf + 0.5);
+  double r = x - kf * p1;
+  r = r - kf * p2;
+  r = r - kf * p3;
+  const double z = r * r;
+  double ps = 2.81145725434552076320e-15;
+  ps = ps * z + -7.64716373181981647590e-13;
+  ps = ps * z + 1.60590438368216145994e-10;
+  ps = ps * z + -2.50521083854417187751e-08;
+  ps = ps * z + 2.75573192239858906526e-06;
+  ps = ps * z + -1.98412698412698412698e-04;
+  ps = ps * z + 8.33333333333333333333e-03;
+  ps = ps * z + -1.66666666666666666667e-01;
+  const double sr = r + (r * z) * ps;
+  double pc = 4.77947733238738529744e-14;
+  pc = pc * z + -1.14707455977297247139e-11;
+  pc = pc * z + 2.08767569878680989792e-09;
+  pc = pc * z + -2.75573192239858906526e-07;
+  pc = pc * z + 2.48015873015873015873e-05;
+  pc = pc * z + -1.38888888888888888889e-03;
+  pc = pc * z + 4.16666666666666666667e-02;
+  pc = pc * z + -0.5;
+  const double cr = 1.0 + z * pc;
+  const long long k = (long long)kf;
+  switch ((int)(k & 3)) {
+    case 0: sn = sr; cs = cr; break;
+    case 1: sn = cr; cs = -sr; break;
+    case 2: sn = -sr; cs = -cr; break;
+    default: sn = -cr; cs = sr; break;
+  }
+}
+
+__device__ __forceinline__ void d_joint_motion(int type, const double *axis, double q, double *M)
+{
+#pragma unroll
+  for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  if (type == 1) {
+    double sn, cs;
+    d_sincos(q * 0.5, sn, cs);
+    const double x = axis[0] * sn, y = axis[1] * sn, z = axis[2] * sn, w = cs;
+    const double d = x * x + y * y + z * z + w * w;
+    const double s = 2.0 / d;
+    const double xs = x * s, ys = y * s, zs = z * s;
+    const double wx = w * xs, wy = w * ys, wz = w * zs;
+    const double xx = x * xs, xy = x * ys, xz = x * zs;
+    const double yy = y * ys, yz = y * zs, zz = z * zs;
+    M[0] = 1.0 - (yy + zz); M[4] = xy - wz;         M[8] = xz + wy;
+    M[1] = xy + wz;         M[5] = 1.0 - (xx + zz); M[9] = yz - wx;
+    M[2] = xz - wy;         M[6] = yz + wx;         M[10] = 1.0 - (xx + yy);
+  } else if (type == 2) {
+    M[12] = axis[0] * q; M[13] = axis[1] * q; M[14] = axis[2] * q;
+  }
+}
+
+// one thread per (frame, link): the product along the link's ancestor chain, root first
+__global__ void __launch_bounds__(128) ruf_fk_links_kernel(Kinematics k, int n_frames, const double *__restrict__ joint_q,
+                                                         double *__restrict__ links)
+{
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n_frames * k.n_links) return;
+  const int l = (int)(gid % k.n_links);
+  const long long f = gid / k.n_links;
+  const double *q = joint_q + f * k.n_links;
+  double T[16], M[16], O[16];
+  const int c0 = k.chain_off[l], c1 = k.chain_off[l + 1];
+  for (int c = c0; c < c1; ++c) {
+    const int a = k.chain_idx[c];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) O[i] = k.origin[16 * (size_t)a + i];
+    if (c == c0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) T[i] = O[i];
+    } else {
+      d_mat4_mul(T, O, T);
+    }
+    const int type = k.type[a];
+    if (type != 0) {
+      d_joint_motion(type, k.axis + 3 * (size_t)a, q[a], M);
+      d_mat4_mul(T, M, T);
+    }
+  }
+  double *out = links + 16 * (size_t)gid;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = T[i];
+}
+
+// one thread per (frame, part) plus one per frame for the view matrix
+__global__ void __launch_bounds__(128) ruf_fk_outputs_kernel(Kinematics k, int n_frames, const double *__restrict__ links,
+                                                           double tx, double ty, double *__restrict__ part_model,
+                                                           double *__restrict__ view)
+{
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = k.n_parts + 1;
+  if (gid >= (long long)n_frames * per) return;
+  const int p = (int)(gid % per);
+  const long long f = gid / per;
+  const double *L = links + 16 * (size_t)f * k.n_links;
+  double A[16], B[16], C[16];
+  if (p < k.n_parts) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { A[i] = L[16 * (size_t)k.part_link[p] + i]; B[i] = k.part_local[16 * (size_t)p + i]; }
+    d_mat4_mul(A, B, C);
+    double *out = part_model + 16 * ((size_t)f * k.n_parts + p);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = C[i];
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) B[i] = k.cam_mount[i];
+  if (k.cam_link < 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) C[i] = B[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] = L[16 * (size_t)k.cam_link + i];
+    d_mat4_mul(A, B, C);
+  }
+  double I[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) I[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) I[c * 4 + r] = C[r * 4 + c];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) I[12 + r] = I[0 * 4 + r] * -C[12] + I[1 * 4 + r] * -C[13] + I[2 * 4 + r] * -C[14];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) I[12 + r] = I[12 + r] + I[0 * 4 + r] * tx;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) I[12 + r] = I[12 + r] + I[1 * 4 + r] * ty;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) A[i] = k.view_pre[i];
+  d_mat4_mul(A, I, C);
+  double *out = view + 16 * (size_t)f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = C[i];
+}
+
+cudaError_t launch_fk(const Kinematics &k, int n_frames, const double *d_joint_q, double tx, double ty,
+                      double *d_links, double *d_part_model, double *d_view, cudaStream_t s)
+{
+  const long long n1 = (long long)n_frames * k.n_links;
+  if (n1 > 0) ruf_fk_links_kernel<<<(unsigned)((n1 + 127) / 128), 128, 0, s>>>(k, n_frames, d_joint_q, d_links);
+  const long long n2 = (long long)n_frames * (k.n_parts + 1);
+  ruf_fk_outputs_kernel<<<(unsigned)((n2 + 127) / 128), 128, 0, s>>>(k, n_frames, d_links, tx, ty, d_part_model, d_view);
+  return cudaGetLastError();
+}
+
 cudaError_t check_kernel_image()
 {
   cudaFuncAttributes fa;

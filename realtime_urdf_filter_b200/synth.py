@@ -170,6 +170,30 @@ class Scene:
             pm[i] = _lib.part_model(q, t, p.off_q, p.off_t, p.suffix)
         return view, pm
 
+    # ---- device-side forward kinematics inputs (ruf_set_kinematics / ruf_fk_batch_device) ----
+    def joint_q(self, k: int) -> np.ndarray:
+        """Joint positions at frame k (the same sweep link_poses() uses)."""
+        t = k / self.fps
+        return np.array([ln.q0 + ln.amp * math.sin(2 * math.pi * ln.freq * t + ln.phase) for ln in self.links])
+
+    def kinematics(self) -> dict:
+        jt = {"fixed": 0, "revolute": 1, "prismatic": 2}
+        n = len(self.links)
+        origin = np.zeros((n, 16))
+        axis = np.zeros((n, 3))
+        for i, ln in enumerate(self.links):
+            origin[i] = make_T(rpy_matrix(*ln.rpy), ln.xyz).T.reshape(-1)      # column-major
+            axis[i] = np.asarray(ln.axis, float) / np.linalg.norm(ln.axis)
+        part_local = np.zeros((self.n_parts, 16))
+        for i, p in enumerate(self.parts):
+            part_local[i] = _lib.part_model((0, 0, 0, 1), (0, 0, 0), p.off_q, p.off_t, p.suffix)
+        return dict(parent=np.array([ln.parent for ln in self.links], np.int32),
+                    joint_type=np.array([jt[ln.jtype] for ln in self.links], np.int32),
+                    origin=origin, axis=axis, part_link=np.array([p.link for p in self.parts], np.int32),
+                    part_local=part_local, cam_link=self.cam_link,
+                    cam_mount=make_T(self.cam_R, self.cam_xyz).T.reshape(-1),
+                    view_pre=_lib.view_matrix(self.offset_q, self.offset_t, (0, 0, 0, 1), (0, 0, 0), 0.0, 0.0))
+
     def frames(self, ks):
         views = np.zeros((len(ks), 16))
         pms = np.zeros((len(ks), self.n_parts, 16))
