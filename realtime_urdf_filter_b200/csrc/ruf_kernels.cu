@@ -259,7 +259,7 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
 // be binned by the caller; clipped / many-tile triangles are pushed to the frame's big list here.
 __device__ __forceinline__ bool process_triangle(long long t, int frame, const Model &m,
                                                  const float *__restrict__ mvp_all, const Dims &d, float bg_z,
-                                                 TriRec *big, uint32_t *ctr, const uint8_t *pvis, uint32_t pmin,
+                                                 TriRec *big, uint32_t *ctr, uint32_t pvis_bits, uint32_t pmin,
                                                  TriRec &r, uint32_t &tiles)
 {
   if (t >= d.n_tris + 2) return false;
@@ -279,7 +279,9 @@ __device__ __forceinline__ bool process_triangle(long long t, int frame, const M
     part = (uint32_t)d.n_parts;
   }
   if (part > (uint32_t)d.n_parts) return false;
-  if (pvis && !pvis[part - pmin]) return false;     // the whole part is outside the view volume this frame
+  // pvis_bits is all ones when the CTA spans too many parts to cull (then part - pmin may exceed 31: the
+  // shift is masked, the bit is set either way)
+  if (!((pvis_bits >> ((part - pmin) & 31u)) & 1u)) return false;   // the whole part is outside the view volume
 
   const float4 *M = reinterpret_cast<const float4 *>(mvp_all + 16 * ((long long)frame * (d.n_parts + 1) + part));
   const float4 c0 = __ldg(M), c1 = __ldg(M + 1), c2 = __ldg(M + 2), c3 = __ldg(M + 3);
@@ -351,14 +353,14 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float b
   // ---- per-part view-volume culling (result-neutral, DESIGN.md "Setup-stage rejects"): the 8 corners of
   // a part's object-space box go through the part's MVP; if all 8 lie beyond one clip plane by a margin,
   // every triangle of the part would be rejected one by one below, so the CTA skips them wholesale.
-  __shared__ uint8_t s_pvis[kCullParts];
-  __shared__ uint32_t s_anyvis;
+  // Every warp evaluates the (at most 8) parts of this CTA itself -- same inputs, same result in all warps,
+  // so no barrier is needed and the decision to leave early is consistent across the CTA.
   const uint2 prange = __ldg(m.cta_parts + cta);
   const bool cull = (prange.y - prange.x) < (uint32_t)kCullParts;
-  if (tid == 0) s_anyvis = 0;
   for (int i = tid; i < d.ntiles; i += kSetupThreads) s_cnt[i] = 0;
-  __syncthreads();
-  if (cull && warp == 0) {
+  uint32_t pvis_bits = 0xffffffffu;        // bit i: part prange.x + i may be visible
+  if (cull) {
+    pvis_bits = 0;
     const int corner = lane & 7;
 #pragma unroll
     for (int pass = 0; pass < kCullParts / 4; ++pass) {
@@ -379,29 +381,24 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float b
                 (c.y > wm ? 8u : 0u) | (-c.y > wm ? 16u : 0u);
         }
       }
-      uint32_t all = 0xffffffffu;      // planes that reject all 8 corners of my part
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const uint32_t b = (__ballot_sync(0xffffffffu, (out >> k) & 1u) >> (lane & 24)) & 0xffu;
-        if (b != 0xffu) all &= ~(1u << k);
-      }
-      if (have && corner == 0) {
-        const bool vis = (all & 31u) == 0u;
-        s_pvis[pass * 4 + (lane >> 3)] = vis ? 1 : 0;
-        if (vis) s_anyvis = 1;
+      for (int g = 0; g < 4; ++g) {          // the four parts of this pass
+        bool rejected = false;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          rejected |= ((__ballot_sync(0xffffffffu, (out >> k) & 1u) >> (8 * g)) & 0xffu) == 0xffu;
+        const uint32_t pg = prange.x + (uint32_t)(pass * 4 + g);
+        if (pg <= prange.y && !rejected) pvis_bits |= 1u << (pass * 4 + g);
       }
     }
-  }
-  if (cull) {
-    __syncthreads();
-    if (!s_anyvis) {
+    if (pvis_bits == 0) {
       // nothing of this CTA can be visible: publish empty segments and leave
       uint2 *table = table_all + (size_t)frame * d.ntiles * d.n_setup_ctas;
       for (int i = tid; i < d.ntiles; i += kSetupThreads) table[(size_t)i * d.n_setup_ctas + cta] = make_uint2(0u, 0u);
       return;
     }
   }
-  const uint8_t *pvis = cull ? s_pvis : nullptr;
+  __syncthreads();               // s_cnt is zeroed
 
   TriRec rec[TPT];
   uint32_t tiles[TPT];
@@ -409,7 +406,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float b
 #pragma unroll
   for (int k = 0; k < TPT; ++k) {
     const long long t = ((long long)cta * TPT + k) * kSetupThreads + tid;
-    valid[k] = process_triangle(t, frame, m, mvp_all, d, bg_z, big, ctr, pvis, prange.x, rec[k], tiles[k]);
+    valid[k] = process_triangle(t, frame, m, mvp_all, d, bg_z, big, ctr, pvis_bits, prange.x, rec[k], tiles[k]);
     if (valid[k]) {
       const int tx0 = tiles[k] & 255, tx1 = (tiles[k] >> 8) & 255, ty0 = (tiles[k] >> 16) & 255, ty1 = tiles[k] >> 24;
       for (int ty = ty0; ty <= ty1; ++ty)
