@@ -221,3 +221,37 @@ def test_all_u16_values_pass_through_unfiltered_pixels():
     assert np.array_equal(got_d, want_d) and np.array_equal(got_m, want_m)
     keep = want_m == 0
     assert np.array_equal(got_d[keep], depth[keep]) and keep.sum() > 7000
+
+
+def test_concurrent_contexts_are_independent():
+    """C4 in miniature: several camera streams, one context (and stream) each, driven from separate host
+    threads at the same time (ctypes releases the GIL): no process-global state, results stay bit-exact."""
+    import threading
+    scs = [helpers.scene("pr2_small"), helpers.scene("example"), synth.pr2_like_scene(320, 240, n_tris=3000, name="t3"),
+           helpers.scene("pr2_small")]
+    jobs = []
+    for i, sc in enumerate(scs):
+        fr = helpers.make_frame(sc, i + 1, "u16" if i % 2 == 0 else "f32")
+        want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+        jobs.append((sc, fr, want_d, want_m))
+    errors = []
+
+    def worker(sc, fr, want_d, want_m):
+        try:
+            proj, _, _ = sc.proj()
+            with ruf.Context(sc.width, sc.height) as ctx:
+                ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+                for _ in range(25):
+                    d, m = ctx.filter(fr["depth"], proj, fr["view"], fr["pm"], sc.max_diff, sc.replace_value)
+                    if not (np.array_equal(d.view(np.uint8), want_d.view(np.uint8)) and np.array_equal(m, want_m)):
+                        errors.append(f"{sc.name}: mismatch")
+                        return
+        except Exception as e:          # noqa: BLE001
+            errors.append(f"{sc.name}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
