@@ -92,9 +92,9 @@ RUF_API int ruf_set_model(ruf_context *ctx, const float *tri_xyz, const uint32_t
 RUF_API int ruf_set_model_device(ruf_context *ctx, const void *d_tri_xyz, const void *d_tri_part,
                                  int64_t n_tris, int n_parts);
 
-/* Capacity control for device-resident batches: max frames per call, and (0 = automatic)
- * per-frame capacities of the internal big-triangle list and tile-reference buffer. */
-RUF_API int ruf_reserve(ruf_context *ctx, int max_batch, int64_t big_capacity, int64_t bin_capacity);
+/* Capacity control for device-resident batches: max frames per call, and (0 = automatic) the
+ * capacities of the internal per-frame big-triangle list and of the record list every 64x32 tile owns. */
+RUF_API int ruf_reserve(ruf_context *ctx, int max_batch, int64_t big_capacity, int64_t tile_capacity);
 
 /* ------------------------------------------------------------------------------------ */
 /* The per-frame path                                                                     */
@@ -221,6 +221,16 @@ RUF_API int ruf_sphere_triangles(float radius, int slices, int stacks, float *ou
 RUF_API int ruf_cylinder_triangles(float radius, float height, int slices, int stacks, float *out); /* :96 */
 RUF_API int ruf_sphere_triangle_count(int slices, int stacks);
 RUF_API int ruf_cylinder_triangle_count(int slices, int stacks);
+
+/* Diagnostics of the model ingest (CPU only, no device needed).  ruf_set_model cuts the soup into
+ * "meshlets" (runs of consecutive triangles whose bit-identical vertices are welded, the device-side
+ * replacement of the reference's VBO/IBO pairs, src/renderable.cpp:339-350); this builds them with the
+ * given limits (the library uses 256 vertices, 512 triangles, 32 parts) and expands them again:
+ * out_xyz (n_tris + 2) * 9 floats, out_part n_tris + 2 -- the input soup bit for bit, followed by the
+ * two triangles of the background quad (part = n_parts).  counts[3] = meshlets, welded vertices, triangles. */
+RUF_API int ruf_meshlet_roundtrip(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts,
+                                  double z_far, int max_verts, int max_tris, int max_parts,
+                                  float *out_xyz, uint32_t *out_part, int64_t *counts);
 
 RUF_API const char *ruf_version(void);
 

@@ -62,6 +62,8 @@ SIGNATURES = {
     "ruf_filter_batch_device_fk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_double, C.c_double, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),
+    "ruf_meshlet_roundtrip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ruf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ruf_host_free": (C.c_int, [C.c_void_p]),
     "ruf_get_stats": (C.c_int, [C.c_void_p, C.POINTER(RufStats)]),
@@ -198,6 +200,22 @@ def cylinder_triangles(radius, height, slices=10, stacks=10):
 # ---------------------------------------------------------------------------------------------
 # context wrapper
 # ---------------------------------------------------------------------------------------------
+def meshlet_roundtrip(tri_xyz, tri_part, n_parts, z_far=8.0, max_verts=256, max_tris=512, max_parts=32):
+    """Model-ingest diagnostics (CPU): soup -> meshlets -> soup.  -> (xyz (T+2, 9), part (T+2,), counts dict)."""
+    lib = load()
+    xyz = np.ascontiguousarray(tri_xyz, dtype=np.float32).reshape(-1, 9)
+    part = np.ascontiguousarray(tri_part, dtype=np.uint32)
+    n = xyz.shape[0]
+    out_xyz = np.empty((n + 2, 9), np.float32)
+    out_part = np.empty(n + 2, np.uint32)
+    counts = np.zeros(3, np.int64)
+    rc = lib.ruf_meshlet_roundtrip(xyz.ctypes.data, part.ctypes.data, n, int(n_parts), float(z_far), max_verts, max_tris,
+                                   max_parts, out_xyz.ctypes.data, out_part.ctypes.data, counts.ctypes.data)
+    if rc != RUF_OK:
+        raise RufError(rc, "ruf_meshlet_roundtrip failed")
+    return out_xyz, out_part, dict(meshlets=int(counts[0]), verts=int(counts[1]), tris=int(counts[2]))
+
+
 class Context:
     """Thin RAII wrapper over ruf_context."""
 
@@ -252,6 +270,7 @@ class Context:
         self.n_parts, self.n_tris = int(n_parts), int(n_tris)
 
     def reserve(self, max_batch: int, big_capacity: int = 0, bin_capacity: int = 0):
+        """bin_capacity: records per (frame, tile) list (0 = automatic)."""
         self._check(self._lib.ruf_reserve(self._h, max_batch, big_capacity, bin_capacity))
 
     def _enc_dtype(self, enc):

@@ -19,7 +19,7 @@ HOST = os.path.join(PKG_DIR, "host")
 LIB_PATH = os.environ.get("RUF_LIB_PATH") or os.path.join(PKG_DIR, "libruf_b200.so")
 
 CUDA_SOURCES = ["ruf_kernels.cu", "ruf_api.cu"]
-HOST_SOURCES = ["ruf_host.cpp"]
+HOST_SOURCES = ["ruf_host.cpp", "ruf_meshlet.cpp"]
 FACADE_SOURCES = ["urdf_model.cpp", "urdf_filter.cpp", "facade_c.cpp"]
 
 NVCC_FLAGS = [

@@ -11,6 +11,7 @@
 
 #include "../../include/ruf_b200.h"
 #include "ruf_device.cuh"
+#include "ruf_meshlet.h"
 
 using namespace ruf;
 
@@ -26,9 +27,12 @@ struct ruf_context {
   // model
   long long n_tris = 0;
   int n_parts = 0;
-  float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;
+  bool have_model = false;
+  int n_meshlets = 0;
+  uint4 *meshlets = nullptr;    // [n_meshlets] headers (ruf_device.cuh Model)
+  float4 *mverts = nullptr;     // welded vertices of all meshlets
+  uint32_t *mtris = nullptr;    // packed local indices
   float *part_aabb = nullptr;   // [n_parts][6]
-  uint2 *cta_parts = nullptr;   // [n_setup_ctas]
 
   // workspace
   int max_batch = 0;            // frames the workspace is sized for
@@ -88,8 +92,8 @@ static int fail(ruf_context *c, int code, const char *fmt, ...)
 
 static void free_workspace(ruf_context *c)
 {
-  cudaFree(c->ws.mvp); cudaFree(c->ws.ctr); cudaFree(c->ws.table); cudaFree(c->ws.big); cudaFree(c->ws.bins);
-  c->ws.mvp = nullptr; c->ws.ctr = nullptr; c->ws.table = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
+  cudaFree(c->ws.mvp); cudaFree(c->ws.ctr); cudaFree(c->ws.big); cudaFree(c->ws.bins);
+  c->ws.mvp = nullptr; c->ws.ctr = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
   c->max_batch = 0;
 }
 
@@ -105,26 +109,33 @@ static void free_staging(ruf_context *c)
 
 static int ensure_workspace(ruf_context *c, int frames)
 {
-  if (c->n_tris < 0 || !c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
   if (frames < c->want_batch) frames = c->want_batch;
-  // per-frame capacities: tile references (typically ~0.3 T; a triangle can reference up to kBigTiles
-  // tiles) and the big list; both grow by doubling after an overflow (check_status)
-  long long cap_bin = c->want_bin > 0 ? c->want_bin : c->n_tris + c->n_tris / 2 + 16LL * c->dims.ntiles + 4096;
+  // capacities: every tile of every frame owns a record list of cap_tile entries (a robot seen from its own
+  // head concentrates its triangles in a third of the tiles: the default is 8x the mean, at least 2048), plus
+  // the per-frame big list; both grow by doubling after an overflow (check_status)
+  long long cap_tile = c->want_bin;
+  if (cap_tile <= 0) {
+    cap_tile = 8 * (c->n_tris + 2) / c->dims.ntiles;
+    if (cap_tile < 2048) cap_tile = 2048;
+    if (cap_tile > c->n_tris + 2) cap_tile = c->n_tris + 2;
+    cap_tile = (cap_tile + 63) & ~63LL;
+  }
   long long cap_big = c->want_big > 0 ? c->want_big : 1024;
-  if (cap_big > 0x7fffffffLL || cap_bin > 0x7fffffffLL) return fail(c, RUF_ERR_INVALID, "capacity too large");
-  if (c->max_batch >= frames && c->dims.cap_big == (uint32_t)cap_big && c->dims.cap_bin == (uint32_t)cap_bin)
+  if (cap_big > 0x7fffffffLL || cap_tile > 0x7fffffffLL) return fail(c, RUF_ERR_INVALID, "capacity too large");
+  if (c->max_batch >= frames && c->dims.cap_big == (uint32_t)cap_big && c->dims.cap_tile == (uint32_t)cap_tile)
     return RUF_OK;
   RUF_CUDA(c, cudaStreamSynchronize(c->stream));
   free_workspace(c);
   c->dims.cap_big = (uint32_t)cap_big;
-  c->dims.cap_bin = (uint32_t)cap_bin;
-  c->dims.n_setup_ctas = (int)((c->n_tris + 2 + kSetupTris - 1) / kSetupTris);
+  c->dims.cap_tile = (uint32_t)cap_tile;
+  c->dims.n_meshlets = c->n_meshlets;
+  c->dims.ctr_stride = kCtrWords + c->dims.ntiles;
   const size_t f = (size_t)frames;
   RUF_CUDA(c, cudaMalloc(&c->ws.mvp, f * (c->n_parts + 1) * 16 * sizeof(float)));
-  RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * kCtrWords * sizeof(uint32_t)));
-  RUF_CUDA(c, cudaMalloc(&c->ws.table, f * c->dims.ntiles * c->dims.n_setup_ctas * sizeof(uint2)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * c->dims.ctr_stride * sizeof(uint32_t)));
   RUF_CUDA(c, cudaMalloc(&c->ws.big, f * cap_big * sizeof(TriRec)));
-  RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * cap_bin * sizeof(TriRec)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * c->dims.ntiles * cap_tile * sizeof(TriRec)));
   c->max_batch = frames;
   return RUF_OK;
 }
@@ -171,8 +182,7 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
   const uintptr_t al = (uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_zbuf;
   fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (((uintptr_t)d_mask & 7) == 0);
   const ShaderParams sp = shader_params(c, max_diff, replace_value);
-  Model m{c->v0, c->v1, c->v2, c->part_aabb, c->cta_parts};
-  const float bg_z = (float)(c->z_far * 0.99);   // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
+  Model m{c->meshlets, c->mverts, c->mtris, c->part_aabb};
   int launches = 0;
   cudaEvent_t *ev = nullptr;
   if (c->profiling) {
@@ -186,7 +196,7 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
     ev = c->ev_pool.data() + c->ev_used;
     c->ev_used += kNumStages + 1;
   }
-  cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, bg_z, enc,
+  cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, enc,
                                 sp, fb, s, &launches, ev);
   if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   c->stats.kernel_launches += launches;
@@ -263,7 +273,7 @@ int ruf_destroy(ruf_context *c)
   cudaDeviceSynchronize();
   free_workspace(c);
   free_staging(c);
-  cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2); cudaFree(c->part_aabb); cudaFree(c->cta_parts);
+  cudaFree(c->meshlets); cudaFree(c->mverts); cudaFree(c->mtris); cudaFree(c->part_aabb);
   cudaFree(c->kin_blob); cudaFree(c->fk_links); cudaFree(c->fk_pm); cudaFree(c->fk_view);
   cudaFree(c->ws.status); cudaFree(c->d_lookat);
   if (c->h_status) cudaFreeHost(c->h_status);
@@ -298,7 +308,7 @@ static int check_status(ruf_context *c, cudaStream_t s)
     RUF_CUDA(c, cudaMemsetAsync(c->ws.status, 0, sizeof(uint32_t), s));
     // grow so that the caller's retry fits
     if (flags & kFlagBigOverflow) c->want_big = 4LL * c->dims.cap_big;
-    if (flags & kFlagBinOverflow) c->want_bin = 2LL * c->dims.cap_bin;
+    if (flags & kFlagBinOverflow) c->want_bin = 2LL * c->dims.cap_tile;
     return fail(c, RUF_ERR_OVERFLOW, "internal %s buffer overflow (capacity raised for the next call)",
                 (flags & kFlagBigOverflow) ? "big-list" : "tile-reference");
   }
@@ -312,59 +322,30 @@ int ruf_sync(ruf_context *c)
   return check_status(c, c->stream);
 }
 
-// per-part object-space boxes and the part range of every setup CTA (set-up time, on the host)
-static int upload_part_bounds(ruf_context *c, const float *h_xyz, const uint32_t *h_part, int64_t n_tris, int n_parts)
+// Model ingest (set-up time): the soup is cut into meshlets on the host (ruf_meshlet.cpp) and uploaded.
+static int build_model(ruf_context *c, const float *h_xyz, const uint32_t *h_part, int64_t n_tris, int n_parts)
 {
-  std::vector<float> box((size_t)(n_parts > 0 ? n_parts : 1) * 6);
-  for (int p = 0; p < n_parts; ++p)
-    for (int k = 0; k < 3; ++k) { box[6 * p + k] = 3.0e38f; box[6 * p + 3 + k] = -3.0e38f; }
-  const int64_t n_ctas = (n_tris + 2 + kSetupTris - 1) / kSetupTris;
-  std::vector<uint2> range((size_t)n_ctas, make_uint2(0xffffffffu, 0u));
-  for (int64_t t = 0; t < n_tris; ++t) {
-    const uint32_t p = h_part[t];
-    if (p >= (uint32_t)n_parts) continue;
-    for (int v = 0; v < 3; ++v)
-      for (int k = 0; k < 3; ++k) {
-        const float x = h_xyz[9 * t + 3 * v + k];
-        // NaN / inf vertices never tighten the box (such triangles are dropped by the vertex stage anyway)
-        if (x < box[6 * p + k]) box[6 * p + k] = x;
-        if (x > box[6 * p + 3 + k]) box[6 * p + 3 + k] = x;
-        if (!(x == x) || x > 3.0e38f || x < -3.0e38f) { box[6 * p + k] = -3.0e38f; box[6 * p + 3 + k] = 3.0e38f; }
-      }
-    uint2 &r = range[(size_t)(t / kSetupTris)];
-    if (p < r.x) r.x = p;
-    if (p > r.y) r.y = p;
-  }
-  // the two background-quad triangles (indices n_tris, n_tris + 1) use matrix row n_parts: never culled
-  for (int64_t t = n_tris; t < n_tris + 2; ++t) {
-    uint2 &r = range[(size_t)(t / kSetupTris)];
-    if ((uint32_t)n_parts < r.x) r.x = (uint32_t)n_parts;
-    if ((uint32_t)n_parts > r.y) r.y = (uint32_t)n_parts;
-  }
-  for (uint2 &r : range)
-    if (r.x > r.y) r = make_uint2(0u, 0u);
-  cudaFree(c->part_aabb); cudaFree(c->cta_parts);
-  c->part_aabb = nullptr; c->cta_parts = nullptr;
-  RUF_CUDA(c, cudaMalloc(&c->part_aabb, box.size() * sizeof(float)));
-  RUF_CUDA(c, cudaMalloc(&c->cta_parts, range.size() * sizeof(uint2)));
-  RUF_CUDA(c, cudaMemcpy(c->part_aabb, box.data(), box.size() * sizeof(float), cudaMemcpyHostToDevice));
-  RUF_CUDA(c, cudaMemcpy(c->cta_parts, range.data(), range.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-  return RUF_OK;
-}
-
-static int set_model_common(ruf_context *c, const float *d_xyz, const uint32_t *d_part, int64_t n_tris, int n_parts)
-{
-  cudaFree(c->v0); cudaFree(c->v1); cudaFree(c->v2);
-  c->v0 = c->v1 = c->v2 = nullptr;
-  const size_t n = (size_t)(n_tris > 0 ? n_tris : 1);
-  RUF_CUDA(c, cudaMalloc(&c->v0, n * sizeof(float4)));
-  RUF_CUDA(c, cudaMalloc(&c->v1, n * sizeof(float4)));
-  RUF_CUDA(c, cudaMalloc(&c->v2, n * sizeof(float4)));
-  cudaError_t e = launch_pack_model(d_xyz, d_part, n_tris, c->v0, c->v1, c->v2, c->stream);
-  if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "pack kernel: %s", cudaGetErrorString(e));
+  MeshletModel mm;
+  // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
+  build_meshlets(h_xyz, h_part, n_tris, n_parts, (float)(c->z_far * 0.99), kMeshVerts, kMeshTris, kMeshParts, mm);
+  if (mm.verts.size() / 4 > 0xffffffffull || mm.tris.size() > 0xffffffffull || mm.n_meshlets() > 0x7fffffffull)
+    return fail(c, RUF_ERR_INVALID, "model too large");
   RUF_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->meshlets); cudaFree(c->mverts); cudaFree(c->mtris); cudaFree(c->part_aabb);
+  c->meshlets = nullptr; c->mverts = nullptr; c->mtris = nullptr; c->part_aabb = nullptr;
+  c->have_model = false;
+  RUF_CUDA(c, cudaMalloc(&c->meshlets, mm.hdr.size() * sizeof(uint32_t)));
+  RUF_CUDA(c, cudaMalloc(&c->mverts, mm.verts.size() * sizeof(float)));
+  RUF_CUDA(c, cudaMalloc(&c->mtris, mm.tris.size() * sizeof(uint32_t)));
+  RUF_CUDA(c, cudaMalloc(&c->part_aabb, mm.part_aabb.size() * sizeof(float)));
+  RUF_CUDA(c, cudaMemcpy(c->meshlets, mm.hdr.data(), mm.hdr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  RUF_CUDA(c, cudaMemcpy(c->mverts, mm.verts.data(), mm.verts.size() * sizeof(float), cudaMemcpyHostToDevice));
+  RUF_CUDA(c, cudaMemcpy(c->mtris, mm.tris.data(), mm.tris.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  RUF_CUDA(c, cudaMemcpy(c->part_aabb, mm.part_aabb.data(), mm.part_aabb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->n_meshlets = (int)mm.n_meshlets();
   c->n_tris = n_tris; c->n_parts = n_parts;
   c->dims.n_tris = n_tris; c->dims.n_parts = n_parts;
+  c->have_model = true;
   free_workspace(c);
   free_staging(c);
   c->want_big = c->want_bin = 0;
@@ -381,35 +362,25 @@ int ruf_set_model(ruf_context *c, const float *tri_xyz, const uint32_t *tri_part
   for (int64_t t = 0; t < n_tris; ++t)
     if (tri_part[t] >= (uint32_t)n_parts) return fail(c, RUF_ERR_INVALID, "tri_part[%lld] = %u >= n_parts", (long long)t, tri_part[t]);
   RUF_CUDA(c, cudaSetDevice(c->device));
-  float *d_xyz = nullptr; uint32_t *d_part = nullptr;
-  if (n_tris > 0) {
-    RUF_CUDA(c, cudaMalloc(&d_xyz, (size_t)n_tris * 9 * sizeof(float)));
-    RUF_CUDA(c, cudaMalloc(&d_part, (size_t)n_tris * sizeof(uint32_t)));
-    RUF_CUDA(c, cudaMemcpy(d_xyz, tri_xyz, (size_t)n_tris * 9 * sizeof(float), cudaMemcpyHostToDevice));
-    RUF_CUDA(c, cudaMemcpy(d_part, tri_part, (size_t)n_tris * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  }
-  int rc = set_model_common(c, d_xyz, d_part, n_tris, n_parts);
-  cudaFree(d_xyz); cudaFree(d_part);
-  if (rc == RUF_OK) rc = upload_part_bounds(c, tri_xyz, tri_part, n_tris, n_parts);
-  return rc;
+  return build_model(c, tri_xyz, tri_part, n_tris, n_parts);
 }
 
 int ruf_set_model_device(ruf_context *c, const void *d_tri_xyz, const void *d_tri_part, int64_t n_tris, int n_parts)
 {
   if (!c) return RUF_ERR_INVALID;
-  if (n_tris < 0 || n_parts < 0 || (n_tris > 0 && (!d_tri_xyz || !d_tri_part)) || n_tris > (1LL << 30))
+  if (n_tris < 0 || n_parts < 0 || n_parts > (1 << 20) || (n_tris > 0 && (!d_tri_xyz || !d_tri_part)) || n_tris > (1LL << 30))
     return fail(c, RUF_ERR_INVALID, "bad model arguments");
   RUF_CUDA(c, cudaSetDevice(c->device));
-  int rc = set_model_common(c, (const float *)d_tri_xyz, (const uint32_t *)d_tri_part, n_tris, n_parts);
-  if (rc != RUF_OK) return rc;
-  // set-up time only: bring the soup to the host once to derive the per-part boxes
+  // set-up time only: the soup comes to the host once, where the meshlets are built
   std::vector<float> h_xyz((size_t)n_tris * 9);
   std::vector<uint32_t> h_part((size_t)n_tris);
   if (n_tris > 0) {
     RUF_CUDA(c, cudaMemcpy(h_xyz.data(), d_tri_xyz, h_xyz.size() * sizeof(float), cudaMemcpyDeviceToHost));
     RUF_CUDA(c, cudaMemcpy(h_part.data(), d_tri_part, h_part.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   }
-  return upload_part_bounds(c, h_xyz.data(), h_part.data(), n_tris, n_parts);
+  for (int64_t t = 0; t < n_tris; ++t)
+    if (h_part[t] >= (uint32_t)n_parts) return fail(c, RUF_ERR_INVALID, "tri_part[%lld] = %u >= n_parts", (long long)t, h_part[t]);
+  return build_model(c, h_xyz.data(), h_part.data(), n_tris, n_parts);
 }
 
 int ruf_reserve(ruf_context *c, int max_batch, int64_t rec_capacity, int64_t bin_capacity)
@@ -430,7 +401,7 @@ int ruf_filter_batch_device(ruf_context *c, int n_frames, const void *d_depth_in
   if (n_frames < 1 || !d_depth_in || !d_depth_out || !d_proj || !d_view || (c->n_parts > 0 && !d_part_model) ||
       (enc != RUF_ENC_F32_M && enc != RUF_ENC_U16_MM))
     return fail(c, RUF_ERR_INVALID, "bad arguments");
-  if (!c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
   RUF_CUDA(c, cudaSetDevice(c->device));
   if (n_frames > 65535) return fail(c, RUF_ERR_INVALID, "n_frames > 65535");
   int rc = ensure_workspace(c, n_frames);
@@ -503,7 +474,7 @@ int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, in
   if (n_frames < 1 || !depth_in || !depth_out || !proj || !view || (c->n_parts > 0 && !part_model) ||
       (enc != RUF_ENC_F32_M && enc != RUF_ENC_U16_MM))
     return fail(c, RUF_ERR_INVALID, "bad arguments");
-  if (!c->v0) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
   RUF_CUDA(c, cudaSetDevice(c->device));
   // frames per pipeline chunk: large enough for efficient copies/launches, small enough to overlap (measured)
   int chunk = n_frames >= 128 ? 32 : (n_frames >= 64 ? 16 : (n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1)));
@@ -538,7 +509,7 @@ int ruf_set_kinematics(ruf_context *c, int n_links, const int32_t *parent, const
                        int cam_link, const double *cam_mount, const double *view_pre)
 {
   if (!c) return RUF_ERR_INVALID;
-  if (!c->v0) return fail(c, RUF_ERR_NO_MODEL, "load the model first (ruf_set_model)");
+  if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "load the model first (ruf_set_model)");
   if (n_links < 0 || n_links > (1 << 20) || cam_link >= n_links || !cam_mount || !view_pre ||
       (n_links > 0 && (!parent || !joint_type || !origin || !axis)) || (c->n_parts > 0 && (!part_link || !part_local)))
     return fail(c, RUF_ERR_INVALID, "bad kinematics arguments");
@@ -688,13 +659,14 @@ int ruf_get_stats(ruf_context *c, ruf_stats *out)
   ruf_stats s = c->stats;
   s.visible_tris = s.binned_refs = s.big_tris = 0;
   if (c->last_frames > 0 && c->ws.ctr) {
-    std::vector<uint32_t> h((size_t)c->last_frames * kCtrWords);
+    const size_t stride = (size_t)c->dims.ctr_stride;
+    std::vector<uint32_t> h((size_t)c->last_frames * stride);
     RUF_CUDA(c, cudaMemcpy(h.data(), c->ws.ctr, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (int f = 0; f < c->last_frames; ++f) {
-      const uint32_t *p = h.data() + (size_t)f * kCtrWords;
+      const uint32_t *p = h.data() + (size_t)f * stride;
       s.visible_tris += p[kCtrKept];
-      s.binned_refs += p[kCtrRef];
       s.big_tris += p[kCtrBig];
+      for (int t = 0; t < c->dims.ntiles; ++t) s.binned_refs += p[kCtrWords + t];
     }
   }
   *out = s;

@@ -28,7 +28,10 @@ constexpr int kTileH = 32;
 constexpr int kTilePix = kTileW * kTileH;       // 2048
 constexpr int kRasterThreads = 256;             // consumer threads: 8 pixels of one tile row each
 constexpr int kRasterBlock = kRasterThreads + 32;   // + one producer warp (bulk async copies)
-constexpr int kChunk = 256;                     // records per ring stage (one per consumer thread)
+#ifndef RUF_CHUNK
+#define RUF_CHUNK 256
+#endif
+constexpr int kChunk = RUF_CHUNK;               // records per ring stage (a multiple of 32)
 constexpr int kStages = 2;                      // ring depth (a stage is released as soon as its records sit in registers)
 constexpr int kBigTiles = 12;                   // bbox touching more tiles -> per-frame "big" list
 #ifndef RUF_MAX_UNITS
@@ -40,8 +43,11 @@ constexpr int kMaxUnits = RUF_MAX_UNITS;                   // row-block units (1
 #ifndef RUF_SETUP_THREADS
 #define RUF_SETUP_THREADS 256
 #endif
-#ifndef RUF_TRIS_PER_THREAD
-#define RUF_TRIS_PER_THREAD 4
+#ifndef RUF_MESH_VERTS
+#define RUF_MESH_VERTS 256
+#endif
+#ifndef RUF_MESH_TRIS
+#define RUF_MESH_TRIS 512
 #endif
 #ifndef RUF_SETUP_MIN_BLOCKS
 #define RUF_SETUP_MIN_BLOCKS 4
@@ -50,12 +56,14 @@ constexpr int kMaxUnits = RUF_MAX_UNITS;                   // row-block units (1
 #define RUF_RASTER_MIN_BLOCKS 4
 #endif
 constexpr int kSetupThreads = RUF_SETUP_THREADS;
-constexpr int kTrisPerThread = RUF_TRIS_PER_THREAD;
-constexpr int kSetupTris = kSetupThreads * kTrisPerThread;   // triangles per setup CTA
-#ifndef RUF_SEG_CAP
-#define RUF_SEG_CAP 512
-#endif
-constexpr int kSegCap = RUF_SEG_CAP;                    // table entries gathered per round by a raster CTA
+// A meshlet is the unit of work of one setup CTA: up to kMeshTris consecutive triangles of the model whose
+// bit-identical vertices were welded (at most kMeshVerts distinct ones, local indices of 10 bits) and whose
+// parts span at most kMeshParts consecutive part indices.
+constexpr int kMeshVerts = RUF_MESH_VERTS;
+constexpr int kMeshTris = RUF_MESH_TRIS;
+constexpr int kMeshParts = 32;
+constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   // surviving triangles per thread
+static_assert(kMeshVerts <= 1024 && kMeshTris <= 1023, "meshlet indices are packed in 10 bits");
 constexpr int kMaxTiles = 4096;
 
 constexpr int kNumStages = 3;                   // pose, setup+bin, raster+filter
@@ -78,17 +86,18 @@ static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 // dynamic shared memory of the raster kernel: record ring + per-warp unit tables
 constexpr size_t kRasterDynSmem = sizeof(TriRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
 
-// Per-frame counter block (uint32 words): [0] big-list entries  [1] tile references  [2] flags
-// [3] kept (binned) triangles
-constexpr int kCtrBig = 0, kCtrRef = 1, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
+// Per-frame counter block (uint32 words): [0] big-list entries  [1] unused  [2] flags
+// [3] kept (binned) triangles  [4 .. 4 + ntiles) records in every tile's list
+constexpr int kCtrBig = 0, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
 
 struct Dims {
   int W, H;
   int tiles_x, tiles_y, ntiles;
   int n_parts;           // model matrices per frame (the MVP table has n_parts + 1 rows)
   long long n_tris;
-  uint32_t cap_big, cap_bin;   // per-frame capacities: big list, tile references
-  int n_setup_ctas;            // setup CTAs per frame = table entries per tile
+  uint32_t cap_big, cap_tile;  // capacities: big list per frame, record list per (frame, tile)
+  int n_meshlets;              // setup CTAs per frame
+  int ctr_stride;              // uint32 words of one frame's counter block = kCtrWords + ntiles
   float halfw, halfh, guard_x, guard_y;
 };
 
@@ -108,26 +117,21 @@ struct FrameBuffers {
 
 struct Workspace {
   float *mvp;            // [frame][n_parts + 1][16]
-  uint32_t *ctr;         // [frame][kCtrWords]
+  uint32_t *ctr;         // [frame][ctr_stride]
   TriRec *big;           // [frame][cap_big]
-  TriRec *bins;          // [frame][cap_bin] tile-sorted segments, one per (setup CTA, tile)
-  uint2 *table;          // [frame][tile][n_setup_ctas] (start, count) into bins
+  TriRec *bins;          // [frame][tile][cap_tile] one record list per tile
   uint32_t *status;      // sticky OR of all frame flags
 };
 
 struct Model {
-  const float4 *v0;      // xyz + part index bits in w
-  const float4 *v1;
-  const float4 *v2;
+  const uint4 *meshlets;    // [n_meshlets] vert_off, tri_off, nverts | ntris << 10 | (nparts - 1) << 20, lowest part
+  const float4 *verts;      // welded vertices of all meshlets: xyz, w = bits(part - meshlet's lowest part)
+  const uint32_t *tris;     // local vertex indices i0 | i1 << 10 | i2 << 20
   const float *part_aabb;   // [n_parts][6] object-space min xyz, max xyz
-  const uint2 *cta_parts;   // [n_setup_ctas] (lowest, highest) part index among the CTA's triangles
 };
-constexpr int kCullParts = 8;   // a setup CTA culls per part when its triangles span at most this many parts
 
 // cudaSuccess iff the loaded module has an image the current device can run (sm_100a only)
 cudaError_t check_kernel_image();
-cudaError_t launch_pack_model(const float *d_tri_xyz, const uint32_t *d_tri_part, long long n_tris,
-                              float4 *v0, float4 *v1, float4 *v2, cudaStream_t s);
 // forward kinematics: joint positions -> link poses -> part models + view matrix
 struct Kinematics {
   int n_links, n_parts, cam_link;
@@ -145,7 +149,7 @@ cudaError_t launch_fk(const Kinematics &k, int n_frames, const double *d_joint_q
                       double *d_links, double *d_part_model, double *d_view, cudaStream_t s);
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
                           const double *d_proj, const double *d_view, const double *d_part_model,
-                          const double *d_lookat, float bg_z, int enc, const ShaderParams &sp,
+                          const double *d_lookat, int enc, const ShaderParams &sp,
                           const FrameBuffers &fb, cudaStream_t s, int *n_launches,
                           cudaEvent_t *stage_events /* null or kNumStages+1 events */);
 

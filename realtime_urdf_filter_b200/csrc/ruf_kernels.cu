@@ -61,29 +61,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // ------------------------------------------------------------------------------------------
-// model packing: T*9 floats + T part ids -> three float4 streams (coalesced 16-byte loads)
-// ------------------------------------------------------------------------------------------
-__global__ void ruf_pack_model_kernel(const float *__restrict__ xyz, const uint32_t *__restrict__ part,
-                                      long long n, float4 *v0, float4 *v1, float4 *v2)
-{
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const float *p = xyz + 9 * t;
-  v0[t] = make_float4(p[0], p[1], p[2], __uint_as_float(part[t]));
-  v1[t] = make_float4(p[3], p[4], p[5], 0.f);
-  v2[t] = make_float4(p[6], p[7], p[8], 0.f);
-}
-
-cudaError_t launch_pack_model(const float *d_tri_xyz, const uint32_t *d_tri_part, long long n_tris,
-                              float4 *v0, float4 *v1, float4 *v2, cudaStream_t s)
-{
-  if (n_tris <= 0) return cudaSuccess;
-  unsigned blocks = (unsigned)((n_tris + 255) / 256);
-  ruf_pack_model_kernel<<<blocks, 256, 0, s>>>(d_tri_xyz, d_tri_part, n_tris, v0, v1, v2);
-  return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
 // K0: MVP table.  gl_ModelViewProjectionMatrix of every drawn part, composed in double in the
 // order the GL matrix stack does (PROJECTION * MODELVIEW, MODELVIEW = view * part_model) and
 // rounded once to float.  Row n_parts is the background quad: P * LookAt
@@ -126,7 +103,7 @@ __global__ void ruf_pose_kernel(const double *__restrict__ proj, const double *_
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: vertex stage + primitive setup
+// vertex stage + primitive setup: building blocks of K1
 // ------------------------------------------------------------------------------------------
 struct V4 { float x, y, z, w; };
 struct WV { int32_t X, Y; float z; };
@@ -255,123 +232,115 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
   }
 }
 
-// Vertex stage + setup of triangle t of `frame`.  Returns true when `r` holds a record that has to
-// be binned by the caller; clipped / many-tile triangles are pushed to the frame's big list here.
-__device__ __forceinline__ bool process_triangle(long long t, int frame, const Model &m,
-                                                 const float *__restrict__ mvp_all, const Dims &d, float bg_z,
-                                                 TriRec *big, uint32_t *ctr, uint32_t pvis_bits, uint32_t pmin,
-                                                 TriRec &r, uint32_t &tiles)
+// ------------------------------------------------------------------------------------------
+// K1: vertex stage + primitive setup + binning, one CTA per (meshlet, frame).
+//
+// The model is stored as meshlets (built once on the host, ruf_api.cu): runs of consecutive
+// triangles whose bit-identical vertices are welded, so that the vertex shader
+// (include/shaders/urdf_filter.vert:5), the clip tests, the perspective divide and the viewport
+// snap run ONCE per distinct vertex instead of once per triangle corner.  The per-vertex result
+// is a pure function of (MVP, position), so sharing it cannot change a bit of the output.
+//
+//   P0  per-part view-volume culling (every warp evaluates the meshlet's <= 32 parts itself)
+//   P1  thread per vertex:    clip = MVP * v, clip-plane flags, window coordinates -> shared memory
+//   P2  thread per triangle:  flag logic (reject / clip / keep), zero-area and empty-bbox tests;
+//                             the rare clipped triangles are emitted to the frame's big list here;
+//                             survivors are compacted into a list in shared memory
+//   P3  thread per SURVIVOR:  full setup (depth plane: two IEEE divisions), records stay in
+//                             registers; tile reference counts in shared memory
+//   P4  one global atomic per touched tile reserves a run of that tile's record list; the
+//       records are written there.  The raster kernel reads ONE contiguous list per tile.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kVfDead = 1u;     // part culled or non-finite clip coordinate: the triangle is dropped
+constexpr uint32_t kVfNear = 2u;     // z + w < 0
+constexpr uint32_t kVfXp = 4u;       //  x > 1.001 w
+constexpr uint32_t kVfXn = 8u;       // -x > 1.001 w
+constexpr uint32_t kVfYp = 16u;      //  y > 1.001 w
+constexpr uint32_t kVfYn = 32u;      // -y > 1.001 w
+constexpr uint32_t kVfClip = 64u;    // outside the near plane or the guard band: the triangle goes through the clipper
+constexpr uint32_t kVfBadW = 128u;   // S4b: !(w > 0) or window coordinates out of range
+constexpr uint32_t kVfAllOut = kVfNear | kVfXp | kVfXn | kVfYp | kVfYn;
+
+// S1 + the per-vertex part of the setup-stage rejects, S3's inside tests and S4 for one vertex.
+// -> (X, Y, bits(z_w), flags)
+__device__ __forceinline__ uint4 vertex_stage(const float4 &c0, const float4 &c1, const float4 &c2, const float4 &c3,
+                                              float x, float y, float z, const Dims &d)
 {
-  if (t >= d.n_tris + 2) return false;
-  float3 a, b, c;
-  uint32_t part;
-  if (t < d.n_tris) {
-    const float4 q0 = __ldg(m.v0 + t), q1 = __ldg(m.v1 + t), q2 = __ldg(m.v2 + t);
-    a = make_float3(q0.x, q0.y, q0.z);
-    b = make_float3(q1.x, q1.y, q1.z);
-    c = make_float3(q2.x, q2.y, q2.z);
-    part = __float_as_uint(q0.w);
-  } else {
-    // background quad (src/urdf_filter.cpp:591-596) as triangles (q0,q1,q2), (q0,q2,q3)
-    a = make_float3(-100.f, -100.f, bg_z);
-    if (t == d.n_tris) { b = make_float3(100.f, -100.f, bg_z); c = make_float3(100.f, 100.f, bg_z); }
-    else               { b = make_float3(100.f, 100.f, bg_z);  c = make_float3(-100.f, 100.f, bg_z); }
-    part = (uint32_t)d.n_parts;
-  }
-  if (part > (uint32_t)d.n_parts) return false;
-  // pvis_bits is all ones when the CTA spans too many parts to cull (then part - pmin may exceed 31: the
-  // shift is masked, the bit is set either way)
-  if (!((pvis_bits >> ((part - pmin) & 31u)) & 1u)) return false;   // the whole part is outside the view volume
-
-  const float4 *M = reinterpret_cast<const float4 *>(mvp_all + 16 * ((long long)frame * (d.n_parts + 1) + part));
-  const float4 c0 = __ldg(M), c1 = __ldg(M + 1), c2 = __ldg(M + 2), c3 = __ldg(M + 3);
-  V4 p0 = xform(c0, c1, c2, c3, a.x, a.y, a.z);
-  V4 p1 = xform(c0, c1, c2, c3, b.x, b.y, b.z);
-  V4 p2 = xform(c0, c1, c2, c3, c.x, c.y, c.z);
-  if (!finite4(p0) || !finite4(p1) || !finite4(p2)) return false;
-
-  // Early outs that cannot change the result (DESIGN.md "Setup-stage rejects"):
-  //  * all three vertices in front of the near plane: the clipper would return nothing;
-  //  * all three beyond one side plane of the view volume by a 0.1 % margin: whatever the
+  const V4 p = xform(c0, c1, c2, c3, x, y, z);
+  if (!finite4(p)) return make_uint4(0u, 0u, 0u, kVfDead);
+  uint32_t fl = 0;
+  // Early outs that cannot change the result (DESIGN.md "Setup-stage rejects"): a triangle is skipped when
+  //  * all three vertices are in front of the near plane: the clipper would return nothing;
+  //  * all three are beyond one side plane of the view volume by a 0.1 % margin: whatever the
   //    clipper keeps lies at least 0.3 px outside the viewport.
-  {
-    const float n0 = p0.z + p0.w, n1 = p1.z + p1.w, n2 = p2.z + p2.w;
-    if (n0 < 0.0f && n1 < 0.0f && n2 < 0.0f) return false;
-    const float k = 1.001f;
-    const float w0 = k * p0.w, w1 = k * p1.w, w2 = k * p2.w;
-    if (p0.x > w0 && p1.x > w1 && p2.x > w2) return false;
-    if (-p0.x > w0 && -p1.x > w1 && -p2.x > w2) return false;
-    if (p0.y > w0 && p1.y > w1 && p2.y > w2) return false;
-    if (-p0.y > w0 && -p1.y > w1 && -p2.y > w2) return false;
-  }
-
+  if (p.z + p.w < 0.0f) fl |= kVfNear;
+  const float kw = 1.001f * p.w;
+  if (p.x > kw) fl |= kVfXp;
+  if (-p.x > kw) fl |= kVfXn;
+  if (p.y > kw) fl |= kVfYp;
+  if (-p.y > kw) fl |= kVfYn;
   bool need = false;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    if (!(plane_dist(p0, k, d.guard_x, d.guard_y) >= 0.0f)) need = true;
-    if (!(plane_dist(p1, k, d.guard_x, d.guard_y) >= 0.0f)) need = true;
-    if (!(plane_dist(p2, k, d.guard_x, d.guard_y) >= 0.0f)) need = true;
-  }
-  if (need) { clip_and_emit(p0, p1, p2, d, big, ctr); return false; }
-  if (!(p0.w > 0.0f) || !(p1.w > 0.0f) || !(p2.w > 0.0f)) return false;   // S4b
-  WV w0, w1, w2;
-  if (!to_window(p0, d.halfw, d.halfh, w0) || !to_window(p1, d.halfw, d.halfh, w1) ||
-      !to_window(p2, d.halfw, d.halfh, w2))
-    return false;
-  if (!setup_window_tri(w0, w1, w2, d, r)) return false;
-  const int tx0 = (int)(r.bx & 0xffffu) / kTileW, tx1 = (int)(r.bx >> 16) / kTileW;
-  const int ty0 = (int)(r.by & 0xffffu) / kTileH, ty1 = (int)(r.by >> 16) / kTileH;
-  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) { push_big(r, d, big, ctr); return false; }
-  tiles = (uint32_t)tx0 | ((uint32_t)tx1 << 8) | ((uint32_t)ty0 << 16) | ((uint32_t)ty1 << 24);
-  return true;
+  for (int k = 0; k < 5; ++k)
+    if (!(plane_dist(p, k, d.guard_x, d.guard_y) >= 0.0f)) need = true;
+  WV w;
+  w.X = 0; w.Y = 0; w.z = 0.0f;
+  if (need) fl |= kVfClip;
+  else if (!(p.w > 0.0f) || !to_window(p, d.halfw, d.halfh, w)) fl |= kVfBadW;
+  return make_uint4((uint32_t)w.X, (uint32_t)w.Y, __float_as_uint(w.z), fl);
 }
 
-// ------------------------------------------------------------------------------------------
-// K1: vertex stage + setup + CTA-local binning.
-//
-// One CTA handles kSetupTris consecutive triangles of one frame (kTrisPerThread per thread, the
-// records stay in registers).  Tile reference counts are accumulated in shared memory, scanned,
-// and ONE global atomic per CTA reserves a contiguous range of the frame's reference buffer; the
-// records are then written tile-sorted into that range and the (start, count) of every tile is
-// published in table[frame][tile][cta].  The raster kernel gathers its tile's segments from
-// there, so no global per-triangle atomics, no scan kernel and no scatter kernel are needed.
-// ------------------------------------------------------------------------------------------
-template <int TPT>
-__global__ void __launch_bounds__(kSetupThreads, RUF_SETUP_MIN_BLOCKS)
-ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float bg_z, TriRec *big_all,
-                     TriRec *bins_all, uint2 *table_all, uint32_t *ctr_all)
+// S5 (zero area) and the pixel bbox of S6: can the triangle touch a sample at all?
+__device__ __forceinline__ bool tri_may_touch(const uint4 &a, const uint4 &b, const uint4 &c, const Dims &d)
 {
-  extern __shared__ uint32_t s_dyn[];            // [ntiles] counts, [ntiles] start -> cursor
-  __shared__ uint32_t s_warp[kSetupThreads / 32];
-  __shared__ uint32_t s_base;
-  uint32_t *s_cnt = s_dyn, *s_cur = s_dyn + d.ntiles;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int frame = blockIdx.y, cta = blockIdx.x;
-  TriRec *big = big_all + (size_t)frame * d.cap_big;
-  uint32_t *ctr = ctr_all + (size_t)frame * kCtrWords;
+  const int ax = (int)a.x, ay = (int)a.y, bx = (int)b.x, by = (int)b.y, cx = (int)c.x, cy = (int)c.y;
+  const long long area2 = (long long)(bx - ax) * (cy - ay) - (long long)(cx - ax) * (by - ay);
+  if (area2 == 0) return false;
+  const int xmin = min(ax, min(bx, cx)), xmax = max(ax, max(bx, cx));
+  const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
+  const int i0 = max((xmin - kSubpixHalf + (kSubpix - 1)) >> kSubpixBits, 0);
+  const int i1 = min((xmax - kSubpixHalf) >> kSubpixBits, d.W - 1);
+  const int j0 = max((ymin - kSubpixHalf + (kSubpix - 1)) >> kSubpixBits, 0);
+  const int j1 = min((ymax - kSubpixHalf) >> kSubpixBits, d.H - 1);
+  return i0 <= i1 && j0 <= j1;
+}
 
-  // ---- per-part view-volume culling (result-neutral, DESIGN.md "Setup-stage rejects"): the 8 corners of
-  // a part's object-space box go through the part's MVP; if all 8 lie beyond one clip plane by a margin,
-  // every triangle of the part would be rejected one by one below, so the CTA skips them wholesale.
-  // Every warp evaluates the (at most 8) parts of this CTA itself -- same inputs, same result in all warps,
-  // so no barrier is needed and the decision to leave early is consistent across the CTA.
-  const uint2 prange = __ldg(m.cta_parts + cta);
-  const bool cull = (prange.y - prange.x) < (uint32_t)kCullParts;
-  for (int i = tid; i < d.ntiles; i += kSetupThreads) s_cnt[i] = 0;
-  uint32_t pvis_bits = 0xffffffffu;        // bit i: part prange.x + i may be visible
-  if (cull) {
-    pvis_bits = 0;
+__global__ void __launch_bounds__(kSetupThreads, RUF_SETUP_MIN_BLOCKS)
+ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, TriRec *big_all, TriRec *bins_all,
+                     uint32_t *ctr_all)
+{
+  extern __shared__ uint32_t s_dyn[];            // [ntiles] counts, [ntiles] fill cursors
+  __shared__ uint4 s_vert[kMeshVerts];           // X, Y, bits(z_w), flags
+  __shared__ uint16_t s_list[kMeshTris];         // surviving triangles (meshlet-local index)
+  __shared__ uint32_t s_nsurv;
+  uint32_t *s_cnt = s_dyn, *s_cur = s_dyn + d.ntiles;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int frame = blockIdx.y;
+  TriRec *big = big_all + (size_t)frame * d.cap_big;
+  uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
+
+  const uint4 hdr = __ldg(m.meshlets + blockIdx.x);
+  const uint32_t vert_off = hdr.x, tri_off = hdr.y, part_lo = hdr.w;
+  const int nverts = (int)(hdr.z & 1023u), ntris = (int)((hdr.z >> 10) & 1023u), npm1 = (int)(hdr.z >> 20);
+  const float *mvp_frame = mvp_all + 16 * ((size_t)frame * (d.n_parts + 1) + part_lo);
+
+  // ---- P0: per-part view-volume culling (result-neutral, DESIGN.md "Setup-stage rejects"): the 8 corners
+  // of a part's object-space box go through the part's MVP; if all 8 lie beyond one clip plane by a margin,
+  // every triangle of the part would be rejected one by one below, so its vertices are not even transformed.
+  // Every warp evaluates the meshlet's parts itself -- same inputs, same result in all warps, so no barrier
+  // is needed and the decision to leave early is consistent across the CTA.
+  uint32_t pvis_bits = 0;                  // bit i: part part_lo + i may be visible
+  {
     const int corner = lane & 7;
-#pragma unroll
-    for (int pass = 0; pass < kCullParts / 4; ++pass) {
-      const uint32_t part = prange.x + (uint32_t)(pass * 4 + (lane >> 3));
+    for (int pass = 0; pass * 4 <= npm1; ++pass) {
+      const int slot = pass * 4 + (lane >> 3);
+      const uint32_t part = part_lo + (uint32_t)slot;
       uint32_t out = 0;        // bit k: this corner is beyond plane k (near, +x, -x, +y, -y)
-      const bool have = part <= prange.y;
-      if (have && part < (uint32_t)d.n_parts) {
+      if (slot <= npm1 && part < (uint32_t)d.n_parts) {
         const float *bb = m.part_aabb + 6 * (size_t)part;
         const float px = __ldg(bb + ((corner & 1) ? 3 : 0)), py = __ldg(bb + ((corner & 2) ? 4 : 1)),
                     pz = __ldg(bb + ((corner & 4) ? 5 : 2));
-        const float4 *M = reinterpret_cast<const float4 *>(mvp_all + 16 * ((long long)frame * (d.n_parts + 1) + part));
+        const float4 *M = reinterpret_cast<const float4 *>(mvp_frame + 16 * slot);
         const V4 c = xform(__ldg(M), __ldg(M + 1), __ldg(M + 2), __ldg(M + 3), px, py, pz);
         if (finite4(c)) {
           // margins: 1 % on the side planes, 1e-3 relative on the near plane -- far larger than the
@@ -387,87 +356,113 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float b
 #pragma unroll
         for (int k = 0; k < 5; ++k)
           rejected |= ((__ballot_sync(0xffffffffu, (out >> k) & 1u) >> (8 * g)) & 0xffu) == 0xffu;
-        const uint32_t pg = prange.x + (uint32_t)(pass * 4 + g);
-        if (pg <= prange.y && !rejected) pvis_bits |= 1u << (pass * 4 + g);
+        if (pass * 4 + g <= npm1 && !rejected) pvis_bits |= 1u << (pass * 4 + g);
       }
     }
-    if (pvis_bits == 0) {
-      // nothing of this CTA can be visible: publish empty segments and leave
-      uint2 *table = table_all + (size_t)frame * d.ntiles * d.n_setup_ctas;
-      for (int i = tid; i < d.ntiles; i += kSetupThreads) table[(size_t)i * d.n_setup_ctas + cta] = make_uint2(0u, 0u);
-      return;
-    }
+    if (pvis_bits == 0) return;            // nothing of this meshlet can be visible
   }
-  __syncthreads();               // s_cnt is zeroed
 
-  TriRec rec[TPT];
-  uint32_t tiles[TPT];
-  bool valid[TPT];
-#pragma unroll
-  for (int k = 0; k < TPT; ++k) {
-    const long long t = ((long long)cta * TPT + k) * kSetupThreads + tid;
-    valid[k] = process_triangle(t, frame, m, mvp_all, d, bg_z, big, ctr, pvis_bits, prange.x, rec[k], tiles[k]);
-    if (valid[k]) {
-      const int tx0 = tiles[k] & 255, tx1 = (tiles[k] >> 8) & 255, ty0 = (tiles[k] >> 16) & 255, ty1 = tiles[k] >> 24;
-      for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * d.tiles_x + tx], 1u);
+  for (int i = tid; i < d.ntiles; i += kSetupThreads) s_cnt[i] = 0;
+  if (tid == 0) s_nsurv = 0;
+
+  // ---- P1: vertex stage, once per welded vertex ----
+  for (int v = tid; v < nverts; v += kSetupThreads) {
+    const float4 q = __ldg(m.verts + vert_off + v);
+    const uint32_t slot = __float_as_uint(q.w);
+    uint4 r = make_uint4(0u, 0u, 0u, kVfDead);
+    if ((pvis_bits >> (slot & 31u)) & 1u) {
+      const float4 *M = reinterpret_cast<const float4 *>(mvp_frame + 16 * slot);
+      r = vertex_stage(__ldg(M), __ldg(M + 1), __ldg(M + 2), __ldg(M + 3), q.x, q.y, q.z, d);
     }
+    s_vert[v] = r;
   }
   __syncthreads();
 
-  // exclusive scan of the tile counts (each thread owns a contiguous run of `ipt` tiles)
-  const int ipt = (d.ntiles + kSetupThreads - 1) / kSetupThreads;
-  const int first = tid * ipt;
-  uint32_t run = 0;
-  for (int i = first; i < min(first + ipt, d.ntiles); ++i) run += s_cnt[i];
-  uint32_t x = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
+  // ---- P2: per triangle: flag logic, cheap rejects, clipper for the rare crossers; survivors compacted ----
+  for (int t0 = 0; t0 < ntris; t0 += kSetupThreads) {
+    const int t = t0 + tid;
+    bool keep = false;
+    if (t < ntris) {
+      const uint32_t ix = __ldg(m.tris + tri_off + t);
+      const uint32_t ia = ix & 1023u, ib = (ix >> 10) & 1023u, ic = ix >> 20;
+      const uint4 a = s_vert[ia], b = s_vert[ib], c = s_vert[ic];
+      const uint32_t f_or = a.w | b.w | c.w, f_and = a.w & b.w & c.w;
+      if (!(f_or & kVfDead) && !(f_and & kVfAllOut)) {
+        if (f_or & kVfClip) {
+          // S3: recompute the three clip-space vertices (same inputs, same bits as P1) and clip
+          const float4 qa = __ldg(m.verts + vert_off + ia), qb = __ldg(m.verts + vert_off + ib),
+                       qc = __ldg(m.verts + vert_off + ic);
+          const float4 *M = reinterpret_cast<const float4 *>(mvp_frame + 16 * __float_as_uint(qa.w));
+          const float4 c0 = __ldg(M), c1 = __ldg(M + 1), c2 = __ldg(M + 2), c3 = __ldg(M + 3);
+          clip_and_emit(xform(c0, c1, c2, c3, qa.x, qa.y, qa.z), xform(c0, c1, c2, c3, qb.x, qb.y, qb.z),
+                        xform(c0, c1, c2, c3, qc.x, qc.y, qc.z), d, big, ctr);
+        } else if (!(f_or & kVfBadW)) {
+          keep = tri_may_touch(a, b, c, d);
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (bal) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&s_nsurv, (uint32_t)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
+    }
   }
-  if (lane == 31) s_warp[warp] = x;
   __syncthreads();
-  uint32_t wpre = 0, total = 0;
+  const int nsurv = (int)s_nsurv;
+
+  // ---- P3: full setup of the survivors, one thread per survivor (dense), records stay in registers ----
+  TriRec rec[kSetupSlots];
+  uint32_t tiles[kSetupSlots];
+  bool valid[kSetupSlots];
 #pragma unroll
-  for (int w = 0; w < kSetupThreads / 32; ++w) {
-    const uint32_t v = s_warp[w];
-    if (w < warp) wpre += v;
-    total += v;
+  for (int k = 0; k < kSetupSlots; ++k) {
+    const int s = k * kSetupThreads + tid;
+    valid[k] = false;
+    if (s < nsurv) {
+      const uint32_t ix = __ldg(m.tris + tri_off + s_list[s]);
+      const uint4 a = s_vert[ix & 1023u], b = s_vert[(ix >> 10) & 1023u], c = s_vert[ix >> 20];
+      WV wa, wb, wc;
+      wa.X = (int)a.x; wa.Y = (int)a.y; wa.z = __uint_as_float(a.z);
+      wb.X = (int)b.x; wb.Y = (int)b.y; wb.z = __uint_as_float(b.z);
+      wc.X = (int)c.x; wc.Y = (int)c.y; wc.z = __uint_as_float(c.z);
+      if (setup_window_tri(wa, wb, wc, d, rec[k])) {
+        const int tx0 = (int)(rec[k].bx & 0xffffu) / kTileW, tx1 = (int)(rec[k].bx >> 16) / kTileW;
+        const int ty0 = (int)(rec[k].by & 0xffffu) / kTileH, ty1 = (int)(rec[k].by >> 16) / kTileH;
+        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) {
+          push_big(rec[k], d, big, ctr);          // read by every tile
+        } else {
+          valid[k] = true;
+          tiles[k] = (uint32_t)tx0 | ((uint32_t)tx1 << 8) | ((uint32_t)ty0 << 16) | ((uint32_t)ty1 << 24);
+          for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * d.tiles_x + tx], 1u);
+        }
+      }
+    }
   }
   {
     uint32_t kept = 0;
 #pragma unroll
-    for (int k = 0; k < TPT; ++k) kept += valid[k] ? 1u : 0u;
+    for (int k = 0; k < kSetupSlots; ++k) kept += valid[k] ? 1u : 0u;
     kept = __reduce_add_sync(0xffffffffu, kept);
     if (lane == 0 && kept) atomicAdd(&ctr[kCtrKept], kept);     // statistics only
   }
-  if (tid == 0) {
-    uint32_t base = 0xffffffffu;
-    if (total > 0) {
-      base = atomicAdd(&ctr[kCtrRef], total);
-      if (base + total > d.cap_bin) { atomicOr(&ctr[kCtrFlags], kFlagBinOverflow); base = 0xffffffffu; }
+  __syncthreads();
+
+  // ---- P4: reserve a run in the record list of every touched tile, then fill ----
+  for (int i = tid; i < d.ntiles; i += kSetupThreads) {
+    const uint32_t c = s_cnt[i];
+    if (c) {
+      const uint32_t base = atomicAdd(&ctr[kCtrWords + i], c);
+      if (base + c > d.cap_tile) atomicOr(&ctr[kCtrFlags], kFlagBinOverflow);   // the host grows cap_tile and retries
+      s_cur[i] = base;
     }
-    s_base = base;
-  }
-  uint32_t acc = wpre + x - run;
-  for (int i = first; i < min(first + ipt, d.ntiles); ++i) {
-    s_cur[i] = acc;
-    acc += s_cnt[i];
   }
   __syncthreads();
-  const uint32_t base = s_base;
-  uint2 *table = table_all + (size_t)frame * d.ntiles * d.n_setup_ctas;
-  for (int i = tid; i < d.ntiles; i += kSetupThreads) {
-    const uint32_t c = (base == 0xffffffffu) ? 0u : s_cnt[i];
-    table[(size_t)i * d.n_setup_ctas + cta] = make_uint2(base + s_cur[i], c);
-  }
-  if (base == 0xffffffffu) return;
-  __syncthreads();          // the table read s_cur; from here on it is the fill cursor
-
-  TriRec *bins = bins_all + (size_t)frame * d.cap_bin + base;
+  TriRec *bins = bins_all + (size_t)frame * d.ntiles * d.cap_tile;
 #pragma unroll
-  for (int k = 0; k < TPT; ++k) {
+  for (int k = 0; k < kSetupSlots; ++k) {
     if (!valid[k]) continue;
     const uint4 q0 = make_uint4((uint32_t)rec[k].x0, (uint32_t)rec[k].y0, (uint32_t)rec[k].x1, (uint32_t)rec[k].y1);
     const uint4 q1 = make_uint4((uint32_t)rec[k].x2, (uint32_t)rec[k].y2, __float_as_uint(rec[k].z0),
@@ -476,9 +471,12 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, float b
     const int tx0 = tiles[k] & 255, tx1 = (tiles[k] >> 8) & 255, ty0 = (tiles[k] >> 16) & 255, ty1 = tiles[k] >> 24;
     for (int ty = ty0; ty <= ty1; ++ty)
       for (int tx = tx0; tx <= tx1; ++tx) {
-        const uint32_t pos = atomicAdd(&s_cur[ty * d.tiles_x + tx], 1u);
-        uint4 *dst = reinterpret_cast<uint4 *>(bins + pos);
-        dst[0] = q0; dst[1] = q1; dst[2] = q2;
+        const int tile = ty * d.tiles_x + tx;
+        const uint32_t pos = atomicAdd(&s_cur[tile], 1u);
+        if (pos < d.cap_tile) {
+          uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)tile * d.cap_tile + pos);
+          dst[0] = q0; dst[1] = q1; dst[2] = q2;
+        }
       }
   }
 }
@@ -623,11 +621,10 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
 template <int ENC>
 __global__ void __launch_bounds__(kRasterBlock, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
-                         const uint2 *__restrict__ table_all, const uint32_t *__restrict__ ctr_all,
-                         uint32_t *status, ShaderParams sp, FrameBuffers fb)
+                         const uint32_t *__restrict__ ctr_all, uint32_t *status, ShaderParams sp, FrameBuffers fb)
 {
   // Warp roles: warps 0..7 (kRasterThreads = 256 threads) rasterise and shade; warp 8 is the producer
-  // that streams the tile's triangle records into the shared-memory ring with bulk async copies.
+  // that streams the tile's record list into the shared-memory ring with bulk async copies.
   // dynamic shared memory (more than the 48 KB static limit): record ring, then the unit tables
   extern __shared__ __align__(128) unsigned char s_raster_dyn[];
   TriRec (*sbuf)[kChunk] = reinterpret_cast<TriRec (*)[kChunk]>(s_raster_dyn);
@@ -635,84 +632,63 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       reinterpret_cast<uint16_t (*)[32 * kMaxUnits]>(s_raster_dyn + sizeof(TriRec) * kStages * kChunk);
   __shared__ __align__(16) uint32_t sz[kTilePix];
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
-  __shared__ uint32_t s_nseg, s_total, s_next;
-  __shared__ uint32_t seg_src[kSegCap], seg_off[kSegCap], seg_cnt[kSegCap];
+  __shared__ uint32_t s_next;
   __shared__ uint8_t s_bigcls[kRasterThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_producer = warp == kRasterThreads / 32;
   const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
   const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
-  const uint32_t *ctr = ctr_all + (size_t)frame * kCtrWords;
-  const TriRec *bins = bins_all + (size_t)frame * d.cap_bin;
-  const uint2 *table = table_all + ((size_t)frame * d.ntiles + tile) * d.n_setup_ctas;
+  const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
   const uint32_t sz_addr = smem_u32(sz);
+  // records binned to this tile (CTA-uniform).  Two thirds of the tiles of a typical frame see only the
+  // background quad: they take the register-only path below (no ring, no z tile, no CTA-wide barrier).
+  const uint32_t cnt = min(__ldg(ctr + kCtrWords + tile), d.cap_tile);
   // fold this frame's overflow flags into the context's sticky status word (one thread per frame)
   if (tile == 0 && threadIdx.x == 0) {
     const uint32_t flags = ctr[kCtrFlags];
     if (flags) atomicOr(status, flags);
   }
-
-  if (tid == 0) {
+  if (cnt == 0) {
+    if (is_producer) return;
+  } else {
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);                        // the producer's arrive.expect_tx
-      mbar_init(&empty_bar[s], kRasterThreads / 32);     // one arrive per consumer warp
-    }
-    mbar_fence_init();
-    s_nseg = 0;
-    s_total = 0;
-    s_next = 0;
-  }
-  __syncthreads();
-
-  const int prow = (tid & (kRasterThreads - 1)) >> 3, pcol = (tid & 7) * 8;
-  const int n_entries = d.n_setup_ctas;
-  uint32_t cc = 0;                           // chunks streamed so far (ring position, all rounds)
-
-  for (int round = 0; round * kSegCap < n_entries || round == 0; ++round) {
-    // ---- segment list of this tile: one (start, count) per setup CTA, empty ones dropped ----
-    if (round > 0) {
-      __syncthreads();                       // everybody is done with the previous list
-      if (tid == 0) { s_nseg = 0; s_total = 0; s_next = 0; }
-      __syncthreads();
-    }
-    {
-      const int hi = min(n_entries, (round + 1) * kSegCap);
-      for (int e = round * kSegCap + tid; e < hi; e += kRasterBlock) {
-        const uint2 en = __ldg(table + e);
-        if (en.y) {
-          const uint32_t k = atomicAdd(&s_nseg, 1u);
-          seg_src[k] = en.x; seg_cnt[k] = en.y;
-          seg_off[k] = atomicAdd(&s_total, en.y);
-        }
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full_bar[s], 1);                        // the producer's arrive.expect_tx
+        mbar_init(&empty_bar[s], kChunk / 32);             // one arrive per batch of 32 records
       }
+      mbar_fence_init();
+      s_next = 0;
     }
     __syncthreads();
-    const uint32_t nseg = s_nseg, cnt = s_total;
-    const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
+  }
 
-    if (is_producer) {
-      // ===== producer warp: every segment piece that falls into the chunk is one bulk copy =====
-      for (int c = 0; c < nchunks; ++c, ++cc) {
-        const int stage = (int)(cc % kStages);
-        const uint32_t use = cc / kStages;
+  const int prow = (tid & (kRasterThreads - 1)) >> 3, pcol = (tid & 7) * 8;
+  const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
+
+  if (is_producer) {
+    // ===== producer warp: the tile's list is contiguous, one bulk copy per chunk =====
+    if (lane == 0) {
+      const TriRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % kStages;
+        const uint32_t use = (uint32_t)c / kStages;
         if (use > 0) mbar_wait(&empty_bar[stage], (use - 1) & 1);   // consumers drained the previous content
-        const uint32_t lo = (uint32_t)c * kChunk, hi = min(lo + (uint32_t)kChunk, cnt);
-        if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (hi - lo) * (uint32_t)sizeof(TriRec));
-        for (uint32_t sg = lane; sg < nseg; sg += 32) {
-          const uint32_t so = seg_off[sg], se = so + seg_cnt[sg];
-          const uint32_t a = max(so, lo), b = min(se, hi);
-          if (a < b)
-            bulk_g2s(&sbuf[stage][a - lo], bins + seg_src[sg] + (a - so), (b - a) * (uint32_t)sizeof(TriRec),
-                     &full_bar[stage]);
-        }
+        const uint32_t lo = (uint32_t)c * kChunk, n = min((uint32_t)kChunk, cnt - lo);
+        mbar_arrive_expect_tx(&full_bar[stage], n * (uint32_t)sizeof(TriRec));
+        bulk_g2s(&sbuf[stage][0], list + lo, n * (uint32_t)sizeof(TriRec), &full_bar[stage]);
       }
-    } else {
-      // ===== consumer warps =====
-      if (round == 0) {
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  float zr[8];                                  // this thread's 8 pixels of the z tile
+  {
+    {
+      {
         // big list: pixel-parallel, every thread owns 8 consecutive pixels of one tile row
-        float zr[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) zr[i] = 1.0f;       // glClear depth
         const uint32_t nbig = min(ctr[kCtrBig], d.cap_big);
@@ -776,25 +752,30 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           }
           if (b0 + kRasterThreads < nbig) consumer_bar_sync();   // s_bigcls is rewritten next round
         }
+      }
+    }
+  }
+  if (cnt) {
+    {
+      {
         uint4 *zp = reinterpret_cast<uint4 *>(&sz[prow * kTileW + pcol]);
         zp[0] = make_uint4(__float_as_uint(zr[0]), __float_as_uint(zr[1]), __float_as_uint(zr[2]), __float_as_uint(zr[3]));
         zp[1] = make_uint4(__float_as_uint(zr[4]), __float_as_uint(zr[5]), __float_as_uint(zr[6]), __float_as_uint(zr[7]));
         consumer_bar_sync();                  // the z tile is initialised for all consumer warps
       }
 
-      // binned triangles: the chunk's 256 records are 8 batches of 32; warps claim batches from a
-      // shared counter (a warp that drew light triangles simply takes the next batch), and a stage goes
-      // back to the producer once its 8 batches sit in registers.
+      // binned triangles: a chunk's records are batches of 32; warps claim batches from a shared
+      // counter (a warp that drew light triangles simply takes the next batch), and a stage goes
+      // back to the producer once all its batches sit in registers.
       const uint32_t nbatches = (cnt + 31u) / 32u;
       for (;;) {
         uint32_t bt = 0;
         if (lane == 0) bt = smem_add(smem_u32(&s_next), 1u);
         bt = __shfl_sync(0xffffffffu, bt, 0);
         if (bt >= nbatches) break;
-        const int c = (int)(bt / (kChunk / 32));
-        const uint32_t gc = cc + (uint32_t)c;                 // ring position of the chunk
-        const int stage = (int)(gc % kStages);
-        mbar_wait(&full_bar[stage], (gc / kStages) & 1);
+        const int c = (int)(bt / (kChunk / 32));              // ring position of the chunk
+        const int stage = c % kStages;
+        mbar_wait(&full_bar[stage], ((uint32_t)c / kStages) & 1);
         const uint32_t nrec = min(cnt - (uint32_t)c * kChunk, (uint32_t)kChunk);
         const uint32_t idx = (bt % (kChunk / 32)) * 32u + (uint32_t)lane;
         // ---- phase 1: one lane per record: clip to the tile, derive the incremental edge setup ----
@@ -914,23 +895,21 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           else raster_warp<true>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz_addr, lane);
         }
       }
-      cc += (uint32_t)nchunks;
     }
-    if (!((round + 1) * kSegCap < n_entries)) break;
+    consumer_bar_sync();                      // every record of the tile has been rasterised
+    const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol]);
+    const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol + 4]);
+    zr[0] = __uint_as_float(zq0.x); zr[1] = __uint_as_float(zq0.y); zr[2] = __uint_as_float(zq0.z);
+    zr[3] = __uint_as_float(zq0.w); zr[4] = __uint_as_float(zq1.x); zr[5] = __uint_as_float(zq1.y);
+    zr[6] = __uint_as_float(zq1.z); zr[7] = __uint_as_float(zq1.w);
   }
-  __syncthreads();
-  if (is_producer) return;
 
   // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
   const int gy = tile_y0 + prow, gx = tile_x0 + pcol;
   if (gy >= d.H || gx >= d.W) return;
   const size_t img = (size_t)frame * d.W * d.H;
   const size_t base = img + (size_t)gy * d.W + gx;
-  const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol]);
-  const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol + 4]);
-  const float zw[8] = {__uint_as_float(zq0.x), __uint_as_float(zq0.y), __uint_as_float(zq0.z),
-                       __uint_as_float(zq0.w), __uint_as_float(zq1.x), __uint_as_float(zq1.y),
-                       __uint_as_float(zq1.z), __uint_as_float(zq1.w)};
+  const float (&zw)[8] = zr;
   const bool full = fb.vec_ok && (gx + 8 <= d.W);
   if (full) {
     // to_linear_depth (frag:14-17,22) once per distinct z of this thread's run: background pixels
@@ -1200,12 +1179,12 @@ cudaError_t check_kernel_image()
 
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
                           const double *d_proj, const double *d_view, const double *d_part_model,
-                          const double *d_lookat, float bg_z, int enc, const ShaderParams &sp,
+                          const double *d_lookat, int enc, const ShaderParams &sp,
                           const FrameBuffers &fb, cudaStream_t s, int *n_launches, cudaEvent_t *ev)
 {
   cudaError_t err;
   int launches = 0;
-  err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_frames * kCtrWords * sizeof(uint32_t), s);
+  err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_frames * d.ctr_stride * sizeof(uint32_t), s);
   if (err != cudaSuccess) return err;
   if (ev) cudaEventRecord(ev[0], s);
   {
@@ -1216,19 +1195,18 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (ev) cudaEventRecord(ev[1], s);
   }
   {
-    dim3 grid((unsigned)d.n_setup_ctas, (unsigned)n_frames);
+    dim3 grid((unsigned)d.n_meshlets, (unsigned)n_frames);
     const size_t smem = (size_t)d.ntiles * 2 * sizeof(uint32_t);
-    ruf_setup_bin_kernel<kTrisPerThread><<<grid, kSetupThreads, smem, s>>>(m, ws.mvp, d, bg_z, ws.big, ws.bins,
-                                                                         ws.table, ws.ctr);
+    ruf_setup_bin_kernel<<<grid, kSetupThreads, smem, s>>>(m, ws.mvp, d, ws.big, ws.bins, ws.ctr);
     ++launches;
     if (ev) cudaEventRecord(ev[2], s);
   }
   {
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (enc == 1)
-      ruf_raster_filter_kernel<1><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, ws.status, sp, fb);
+      ruf_raster_filter_kernel<1><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
     else
-      ruf_raster_filter_kernel<0><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.table, ws.ctr, ws.status, sp, fb);
+      ruf_raster_filter_kernel<0><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
     ++launches;
     if (ev) cudaEventRecord(ev[3], s);
   }
