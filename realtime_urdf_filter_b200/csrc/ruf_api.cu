@@ -92,8 +92,8 @@ static int fail(ruf_context *c, int code, const char *fmt, ...)
 
 static void free_workspace(ruf_context *c)
 {
-  cudaFree(c->ws.mvp); cudaFree(c->ws.ctr); cudaFree(c->ws.big); cudaFree(c->ws.bins);
-  c->ws.mvp = nullptr; c->ws.ctr = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
+  cudaFree(c->ws.mvp); cudaFree(c->ws.vis); cudaFree(c->ws.ctr); cudaFree(c->ws.big); cudaFree(c->ws.bins);
+  c->ws.mvp = nullptr; c->ws.vis = nullptr; c->ws.ctr = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
   c->max_batch = 0;
 }
 
@@ -133,6 +133,7 @@ static int ensure_workspace(ruf_context *c, int frames)
   c->dims.ctr_stride = kCtrWords + c->dims.ntiles;
   const size_t f = (size_t)frames;
   RUF_CUDA(c, cudaMalloc(&c->ws.mvp, f * (c->n_parts + 1) * 16 * sizeof(float)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.vis, f * (c->n_parts + 1)));
   RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * c->dims.ctr_stride * sizeof(uint32_t)));
   RUF_CUDA(c, cudaMalloc(&c->ws.big, f * cap_big * sizeof(TriRec)));
   RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * c->dims.ntiles * cap_tile * sizeof(TriRec)));

@@ -44,13 +44,16 @@ constexpr int kMaxUnits = RUF_MAX_UNITS;                   // row-block units (1
 #define RUF_SETUP_THREADS 256
 #endif
 #ifndef RUF_MESH_VERTS
-#define RUF_MESH_VERTS 256
+#define RUF_MESH_VERTS 512
 #endif
 #ifndef RUF_MESH_TRIS
-#define RUF_MESH_TRIS 512
+#define RUF_MESH_TRIS 1023
+#endif
+#ifndef RUF_SETUP_FRAMES
+#define RUF_SETUP_FRAMES 4
 #endif
 #ifndef RUF_SETUP_MIN_BLOCKS
-#define RUF_SETUP_MIN_BLOCKS 4
+#define RUF_SETUP_MIN_BLOCKS 5
 #endif
 #ifndef RUF_RASTER_MIN_BLOCKS
 #define RUF_RASTER_MIN_BLOCKS 4
@@ -62,7 +65,8 @@ constexpr int kSetupThreads = RUF_SETUP_THREADS;
 constexpr int kMeshVerts = RUF_MESH_VERTS;
 constexpr int kMeshTris = RUF_MESH_TRIS;
 constexpr int kMeshParts = 32;
-constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   // surviving triangles per thread
+constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   // triangles per thread
+constexpr int kSetupFrames = RUF_SETUP_FRAMES;  // frames a setup CTA loops over with its meshlet in registers
 static_assert(kMeshVerts <= 1024 && kMeshTris <= 1023, "meshlet indices are packed in 10 bits");
 constexpr int kMaxTiles = 4096;
 
@@ -117,6 +121,7 @@ struct FrameBuffers {
 
 struct Workspace {
   float *mvp;            // [frame][n_parts + 1][16]
+  uint8_t *vis;          // [frame][n_parts + 1] 0 = the part is outside the view volume in this frame
   uint32_t *ctr;         // [frame][ctr_stride]
   TriRec *big;           // [frame][cap_big]
   TriRec *bins;          // [frame][tile][cap_tile] one record list per tile

@@ -61,48 +61,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // ------------------------------------------------------------------------------------------
-// K0: MVP table.  gl_ModelViewProjectionMatrix of every drawn part, composed in double in the
-// order the GL matrix stack does (PROJECTION * MODELVIEW, MODELVIEW = view * part_model) and
-// rounded once to float.  Row n_parts is the background quad: P * LookAt
-// (src/urdf_filter.cpp:576-596).  One thread per matrix element.
-// ------------------------------------------------------------------------------------------
-__global__ void ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view,
-                                const double *__restrict__ part_model, const double *__restrict__ lookat,
-                                int n_parts, int n_frames, float *__restrict__ mvp)
-{
-  const int rows = n_parts + 1;
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)n_frames * rows * 16;
-  if (gid >= total) return;
-  const int e = (int)(gid & 15);
-  const long long mat = gid >> 4;
-  const int p = (int)(mat % rows);
-  const int f = (int)(mat / rows);
-  const int r = e & 3, c = e >> 2;
-  double s;
-  if (p == n_parts) {
-    s = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s += proj[k * 4 + r] * lookat[c * 4 + k];
-  } else {
-    const double *V = view + 16 * (long long)f;
-    const double *M = part_model + 16 * ((long long)f * n_parts + p);
-    double pv[4];   // row r of P*V
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      double a = 0.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) a += proj[j * 4 + r] * V[k * 4 + j];
-      pv[k] = a;
-    }
-    s = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s += pv[k] * M[c * 4 + k];
-  }
-  mvp[gid] = (float)s;
-}
-
-// ------------------------------------------------------------------------------------------
 // vertex stage + primitive setup: building blocks of K1
 // ------------------------------------------------------------------------------------------
 struct V4 { float x, y, z, w; };
@@ -233,23 +191,109 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: vertex stage + primitive setup + binning, one CTA per (meshlet, frame).
+// K0: MVP table + per-part view-volume culling.
 //
-// The model is stored as meshlets (built once on the host, ruf_api.cu): runs of consecutive
+// gl_ModelViewProjectionMatrix of every drawn part, composed in double in the order the GL matrix stack
+// does (PROJECTION * MODELVIEW, MODELVIEW = view * part_model) and rounded once to float.  Row n_parts is
+// the background quad: P * LookAt (src/urdf_filter.cpp:576-596).  One thread per matrix element; a block
+// of 256 threads owns 16 matrices.
+//
+// Culling (result-neutral, DESIGN.md "Setup-stage rejects"): the 8 corners of a part's object-space box
+// go through the part's MVP; if all 8 lie beyond one clip plane by a margin, every triangle of the part
+// would be rejected one by one by the setup kernel, so vis[frame][part] = 0 lets it skip the part's
+// vertices wholesale.  8 threads per matrix.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view, const double *__restrict__ part_model,
+                const double *__restrict__ lookat, const float *__restrict__ part_aabb, int n_parts, int n_frames,
+                float *__restrict__ mvp, uint8_t *__restrict__ vis)
+{
+  __shared__ __align__(16) float s_m[16][16];
+  const int rows = n_parts + 1;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_mats = (long long)n_frames * rows;
+  float val = 0.0f;
+  if (gid < n_mats * 16) {
+    const int e = (int)(gid & 15);
+    const long long mat = gid >> 4;
+    const int p = (int)(mat % rows);
+    const int f = (int)(mat / rows);
+    const int r = e & 3, c = e >> 2;
+    double s;
+    if (p == n_parts) {
+      s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += proj[k * 4 + r] * lookat[c * 4 + k];
+    } else {
+      const double *V = view + 16 * (long long)f;
+      const double *M = part_model + 16 * ((long long)f * n_parts + p);
+      double pv[4];   // row r of P*V
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a += proj[j * 4 + r] * V[k * 4 + j];
+        pv[k] = a;
+      }
+      s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += pv[k] * M[c * 4 + k];
+    }
+    val = (float)s;
+    mvp[gid] = val;
+  }
+  s_m[threadIdx.x >> 4][threadIdx.x & 15] = val;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int mi = threadIdx.x >> 3, corner = threadIdx.x & 7;
+    const long long mat = (long long)blockIdx.x * 16 + mi;
+    const bool have = mat < n_mats;
+    const int p = have ? (int)(mat % rows) : n_parts;
+    uint32_t out = 0;        // bit k: this corner is beyond plane k (near, +x, -x, +y, -y)
+    if (p < n_parts) {
+      const float *bb = part_aabb + 6 * (size_t)p;
+      const float px = __ldg(bb + ((corner & 1) ? 3 : 0)), py = __ldg(bb + ((corner & 2) ? 4 : 1)),
+                  pz = __ldg(bb + ((corner & 4) ? 5 : 2));
+      const float4 *M = reinterpret_cast<const float4 *>(s_m[mi]);
+      const V4 c = xform(M[0], M[1], M[2], M[3], px, py, pz);
+      if (finite4(c)) {
+        // margins: 1 % on the side planes, 1e-3 relative on the near plane -- far larger than the
+        // float rounding of the per-triangle tests they stand in for
+        const float wm = 1.01f * c.w, tol = 1e-3f * (fabsf(c.z) + fabsf(c.w));
+        out = (c.z + c.w < -tol ? 1u : 0u) | (c.x > wm ? 2u : 0u) | (-c.x > wm ? 4u : 0u) |
+              (c.y > wm ? 8u : 0u) | (-c.y > wm ? 16u : 0u);
+      }
+    }
+    bool rejected = false;
+    const int group = (threadIdx.x & 31) >> 3;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      rejected |= ((__ballot_sync(0xffffffffu, (out >> k) & 1u) >> (8 * group)) & 0xffu) == 0xffu;
+    if (have && corner == 0) vis[mat] = rejected ? 0 : 1;    // the background row is never culled (out = 0)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: vertex stage + primitive setup + binning.  One CTA per (meshlet, run of frames).
+//
+// The model is stored as meshlets (built once on the host, ruf_meshlet.cpp): runs of consecutive
 // triangles whose bit-identical vertices are welded, so that the vertex shader
 // (include/shaders/urdf_filter.vert:5), the clip tests, the perspective divide and the viewport
 // snap run ONCE per distinct vertex instead of once per triangle corner.  The per-vertex result
 // is a pure function of (MVP, position), so sharing it cannot change a bit of the output.
 //
-//   P0  per-part view-volume culling (every warp evaluates the meshlet's <= 32 parts itself)
+// A CTA keeps its meshlet (positions, indices) in REGISTERS and loops over `frames_per_cta` frames;
+// per frame only the meshlet's MVP rows (contiguous, staged in shared memory one frame ahead) and
+// its parts' cull bytes are read.  Per frame:
 //   P1  thread per vertex:    clip = MVP * v, clip-plane flags, window coordinates -> shared memory
-//   P2  thread per triangle:  flag logic (reject / clip / keep), zero-area and empty-bbox tests;
-//                             the rare clipped triangles are emitted to the frame's big list here;
-//                             survivors are compacted into a list in shared memory
-//   P3  thread per SURVIVOR:  full setup (depth plane: two IEEE divisions), records stay in
-//                             registers; tile reference counts in shared memory
-//   P4  one global atomic per touched tile reserves a run of that tile's record list; the
-//       records are written there.  The raster kernel reads ONE contiguous list per tile.
+//   --  the only CTA-wide barrier of the frame; from here on every warp works on its own triangles --
+//   P2  lane per triangle:    flag logic (reject / clip / keep), zero-area and empty-bbox tests; survivors
+//                             and the rare clip candidates are compacted into the warp's list (ballots only)
+//   S3  lane per clip candidate: Sutherland-Hodgman, set-up, append to the frame's big list
+//   P3  lane per SURVIVOR (dense): full setup (depth plane: two IEEE divisions), record in registers
+//   P4  the lanes walk the tiles of their bboxes; lanes on the same tile (match.any) share ONE global
+//       atomic that reserves a run of that tile's record list, and write their records there.
+//       The raster kernel reads ONE contiguous list per tile.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kVfDead = 1u;     // part culled or non-finite clip coordinate: the triangle is dropped
 constexpr uint32_t kVfNear = 2u;     // z + w < 0
@@ -260,6 +304,7 @@ constexpr uint32_t kVfYn = 32u;      // -y > 1.001 w
 constexpr uint32_t kVfClip = 64u;    // outside the near plane or the guard band: the triangle goes through the clipper
 constexpr uint32_t kVfBadW = 128u;   // S4b: !(w > 0) or window coordinates out of range
 constexpr uint32_t kVfAllOut = kVfNear | kVfXp | kVfXn | kVfYp | kVfYn;
+constexpr uint32_t kNoTri = 0xffffffffu;
 
 // S1 + the per-vertex part of the setup-stage rejects, S3's inside tests and S4 for one vertex.
 // -> (X, Y, bits(z_w), flags)
@@ -306,178 +351,195 @@ __device__ __forceinline__ bool tri_may_touch(const uint4 &a, const uint4 &b, co
 }
 
 __global__ void __launch_bounds__(kSetupThreads, RUF_SETUP_MIN_BLOCKS)
-ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, Dims d, TriRec *big_all, TriRec *bins_all,
-                     uint32_t *ctr_all)
+ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *__restrict__ vis_all, Dims d,
+                     int n_frames, int frames_per_cta, TriRec *big_all, TriRec *bins_all, uint32_t *ctr_all)
 {
-  extern __shared__ uint32_t s_dyn[];            // [ntiles] counts, [ntiles] fill cursors
-  __shared__ uint4 s_vert[kMeshVerts];           // X, Y, bits(z_w), flags
-  __shared__ uint16_t s_list[kMeshTris];         // surviving triangles (meshlet-local index)
-  __shared__ uint32_t s_nsurv;
-  uint32_t *s_cnt = s_dyn, *s_cur = s_dyn + d.ntiles;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int frame = blockIdx.y;
-  TriRec *big = big_all + (size_t)frame * d.cap_big;
-  uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
+  constexpr int kVPT = (kMeshVerts + kSetupThreads - 1) / kSetupThreads;   // vertices per thread
+  constexpr int kTPT = kSetupSlots;                                       // triangles per thread
+  constexpr int kMPT = (kMeshParts * 16 + kSetupThreads - 1) / kSetupThreads;   // MVP floats staged per thread
+  constexpr int kWarpList = kTPT * 32;                                    // triangles a warp classifies per frame
+  __shared__ uint4 s_vert[2][kMeshVerts];        // X, Y, bits(z_w), flags; double-buffered over frames
+  __shared__ uint32_t s_list[kSetupThreads / 32][kWarpList];   // per warp: survivors from the front, clip candidates from the back
+  __shared__ __align__(16) float s_mvp[3][kMeshParts * 16];    // this meshlet's MVP rows, staged two frames ahead
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lanemask_lt = (1u << lane) - 1u;
 
   const uint4 hdr = __ldg(m.meshlets + blockIdx.x);
   const uint32_t vert_off = hdr.x, tri_off = hdr.y, part_lo = hdr.w;
   const int nverts = (int)(hdr.z & 1023u), ntris = (int)((hdr.z >> 10) & 1023u), npm1 = (int)(hdr.z >> 20);
-  const float *mvp_frame = mvp_all + 16 * ((size_t)frame * (d.n_parts + 1) + part_lo);
+  const int rows = d.n_parts + 1;
+  const int nmv = (npm1 + 1) * 16;               // floats of the meshlet's MVP rows (consecutive parts: contiguous)
+  const int f0 = blockIdx.y * frames_per_cta, f1 = min(n_frames, f0 + frames_per_cta);
 
-  // ---- P0: per-part view-volume culling (result-neutral, DESIGN.md "Setup-stage rejects"): the 8 corners
-  // of a part's object-space box go through the part's MVP; if all 8 lie beyond one clip plane by a margin,
-  // every triangle of the part would be rejected one by one below, so its vertices are not even transformed.
-  // Every warp evaluates the meshlet's parts itself -- same inputs, same result in all warps, so no barrier
-  // is needed and the decision to leave early is consistent across the CTA.
-  uint32_t pvis_bits = 0;                  // bit i: part part_lo + i may be visible
+  // the meshlet stays in registers for all frames of this CTA
+  float4 vq[kVPT];
+  uint32_t ix[kTPT];
+#pragma unroll
+  for (int k = 0; k < kVPT; ++k) {
+    const int v = k * kSetupThreads + tid;
+    vq[k] = (v < nverts) ? __ldg(m.verts + vert_off + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < kTPT; ++k) {
+    const int t = k * kSetupThreads + tid;
+    ix[k] = (t < ntris) ? __ldg(m.tris + tri_off + t) : kNoTri;
+  }
+
+  // stage the matrices of the first two frames; cull bytes -> one bit per part (every warp builds its own copy)
+  uint32_t pvis_next;
   {
-    const int corner = lane & 7;
-    for (int pass = 0; pass * 4 <= npm1; ++pass) {
-      const int slot = pass * 4 + (lane >> 3);
-      const uint32_t part = part_lo + (uint32_t)slot;
-      uint32_t out = 0;        // bit k: this corner is beyond plane k (near, +x, -x, +y, -y)
-      if (slot <= npm1 && part < (uint32_t)d.n_parts) {
-        const float *bb = m.part_aabb + 6 * (size_t)part;
-        const float px = __ldg(bb + ((corner & 1) ? 3 : 0)), py = __ldg(bb + ((corner & 2) ? 4 : 1)),
-                    pz = __ldg(bb + ((corner & 4) ? 5 : 2));
-        const float4 *M = reinterpret_cast<const float4 *>(mvp_frame + 16 * slot);
-        const V4 c = xform(__ldg(M), __ldg(M + 1), __ldg(M + 2), __ldg(M + 3), px, py, pz);
-        if (finite4(c)) {
-          // margins: 1 % on the side planes, 1e-3 relative on the near plane -- far larger than the
-          // float rounding of the per-triangle tests they stand in for
-          const float wm = 1.01f * c.w, tol = 1e-3f * (fabsf(c.z) + fabsf(c.w));
-          out = (c.z + c.w < -tol ? 1u : 0u) | (c.x > wm ? 2u : 0u) | (-c.x > wm ? 4u : 0u) |
-                (c.y > wm ? 8u : 0u) | (-c.y > wm ? 16u : 0u);
-        }
-      }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {          // the four parts of this pass
-        bool rejected = false;
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-          rejected |= ((__ballot_sync(0xffffffffu, (out >> k) & 1u) >> (8 * g)) & 0xffu) == 0xffu;
-        if (pass * 4 + g <= npm1 && !rejected) pvis_bits |= 1u << (pass * 4 + g);
+    for (int j = 0; j < 2; ++j) {
+      if (f0 + j < f1) {
+        const float *src = mvp_all + 16 * ((size_t)(f0 + j) * rows + part_lo);
+        for (int i = tid; i < nmv; i += kSetupThreads) s_mvp[j][i] = __ldg(src + i);
       }
     }
-    if (pvis_bits == 0) return;            // nothing of this meshlet can be visible
-  }
-
-  for (int i = tid; i < d.ntiles; i += kSetupThreads) s_cnt[i] = 0;
-  if (tid == 0) s_nsurv = 0;
-
-  // ---- P1: vertex stage, once per welded vertex ----
-  for (int v = tid; v < nverts; v += kSetupThreads) {
-    const float4 q = __ldg(m.verts + vert_off + v);
-    const uint32_t slot = __float_as_uint(q.w);
-    uint4 r = make_uint4(0u, 0u, 0u, kVfDead);
-    if ((pvis_bits >> (slot & 31u)) & 1u) {
-      const float4 *M = reinterpret_cast<const float4 *>(mvp_frame + 16 * slot);
-      r = vertex_stage(__ldg(M), __ldg(M + 1), __ldg(M + 2), __ldg(M + 3), q.x, q.y, q.z, d);
-    }
-    s_vert[v] = r;
+    const uint32_t vb = (lane <= npm1) ? (uint32_t)__ldg(vis_all + (size_t)f0 * rows + part_lo + lane) : 0u;
+    pvis_next = __ballot_sync(0xffffffffu, vb != 0u);
   }
   __syncthreads();
 
-  // ---- P2: per triangle: flag logic, cheap rejects, clipper for the rare crossers; survivors compacted ----
-  for (int t0 = 0; t0 < ntris; t0 += kSetupThreads) {
-    const int t = t0 + tid;
-    bool keep = false;
-    if (t < ntris) {
-      const uint32_t ix = __ldg(m.tris + tri_off + t);
-      const uint32_t ia = ix & 1023u, ib = (ix >> 10) & 1023u, ic = ix >> 20;
-      const uint4 a = s_vert[ia], b = s_vert[ib], c = s_vert[ic];
-      const uint32_t f_or = a.w | b.w | c.w, f_and = a.w & b.w & c.w;
-      if (!(f_or & kVfDead) && !(f_and & kVfAllOut)) {
-        if (f_or & kVfClip) {
-          // S3: recompute the three clip-space vertices (same inputs, same bits as P1) and clip
-          const float4 qa = __ldg(m.verts + vert_off + ia), qb = __ldg(m.verts + vert_off + ib),
-                       qc = __ldg(m.verts + vert_off + ic);
-          const float4 *M = reinterpret_cast<const float4 *>(mvp_frame + 16 * __float_as_uint(qa.w));
-          const float4 c0 = __ldg(M), c1 = __ldg(M + 1), c2 = __ldg(M + 2), c3 = __ldg(M + 3);
-          clip_and_emit(xform(c0, c1, c2, c3, qa.x, qa.y, qa.z), xform(c0, c1, c2, c3, qb.x, qb.y, qb.z),
-                        xform(c0, c1, c2, c3, qc.x, qc.y, qc.z), d, big, ctr);
-        } else if (!(f_or & kVfBadW)) {
-          keep = tri_may_touch(a, b, c, d);
-        }
+  // One barrier per frame (B1: the frame's vertices are in shared memory).  Between two B1 the warps run
+  // independently: a warp classifies ITS triangles, compacts ITS survivors and reserves list space itself.
+  for (int f = f0; f < f1; ++f) {
+    const int it = f - f0, vbuf = it & 1, mbuf = it % 3;
+    const uint32_t pvis_bits = pvis_next;        // bit i: part part_lo + i may be visible in frame f
+    // prefetch: matrices of frame f + 2 (stored to shared memory at the end of this iteration, read after
+    // B1 of frame f + 1), cull bytes of frame f + 1
+    float mv_pre[kMPT];
+    const bool stage = f + 2 < f1;
+    if (stage) {
+      const float *src = mvp_all + 16 * ((size_t)(f + 2) * rows + part_lo);
+#pragma unroll
+      for (int k = 0; k < kMPT; ++k) {
+        const int i = k * kSetupThreads + tid;
+        mv_pre[k] = (i < nmv) ? __ldg(src + i) : 0.0f;
       }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (bal) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&s_nsurv, (uint32_t)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (keep) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
-    }
-  }
-  __syncthreads();
-  const int nsurv = (int)s_nsurv;
+    uint32_t vb_next = 0;
+    if (f + 1 < f1 && lane <= npm1) vb_next = (uint32_t)__ldg(vis_all + (size_t)(f + 1) * rows + part_lo + lane);
+    pvis_next = __ballot_sync(0xffffffffu, vb_next != 0u);
 
-  // ---- P3: full setup of the survivors, one thread per survivor (dense), records stay in registers ----
-  TriRec rec[kSetupSlots];
-  uint32_t tiles[kSetupSlots];
-  bool valid[kSetupSlots];
+    if (pvis_bits != 0) {
+      // ---- P1: vertex stage, once per welded vertex ----
 #pragma unroll
-  for (int k = 0; k < kSetupSlots; ++k) {
-    const int s = k * kSetupThreads + tid;
-    valid[k] = false;
-    if (s < nsurv) {
-      const uint32_t ix = __ldg(m.tris + tri_off + s_list[s]);
-      const uint4 a = s_vert[ix & 1023u], b = s_vert[(ix >> 10) & 1023u], c = s_vert[ix >> 20];
-      WV wa, wb, wc;
-      wa.X = (int)a.x; wa.Y = (int)a.y; wa.z = __uint_as_float(a.z);
-      wb.X = (int)b.x; wb.Y = (int)b.y; wb.z = __uint_as_float(b.z);
-      wc.X = (int)c.x; wc.Y = (int)c.y; wc.z = __uint_as_float(c.z);
-      if (setup_window_tri(wa, wb, wc, d, rec[k])) {
-        const int tx0 = (int)(rec[k].bx & 0xffffu) / kTileW, tx1 = (int)(rec[k].bx >> 16) / kTileW;
-        const int ty0 = (int)(rec[k].by & 0xffffu) / kTileH, ty1 = (int)(rec[k].by >> 16) / kTileH;
-        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) {
-          push_big(rec[k], d, big, ctr);          // read by every tile
-        } else {
-          valid[k] = true;
-          tiles[k] = (uint32_t)tx0 | ((uint32_t)tx1 << 8) | ((uint32_t)ty0 << 16) | ((uint32_t)ty1 << 24);
-          for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * d.tiles_x + tx], 1u);
+      for (int k = 0; k < kVPT; ++k) {
+        const int v = k * kSetupThreads + tid;
+        if (v < nverts) {
+          const uint32_t slot = __float_as_uint(vq[k].w);
+          uint4 r = make_uint4(0u, 0u, 0u, kVfDead);
+          if ((pvis_bits >> (slot & 31u)) & 1u) {
+            const float4 *M = reinterpret_cast<const float4 *>(&s_mvp[mbuf][16 * slot]);
+            r = vertex_stage(M[0], M[1], M[2], M[3], vq[k].x, vq[k].y, vq[k].z, d);
+          }
+          s_vert[vbuf][v] = r;
         }
       }
     }
-  }
-  {
-    uint32_t kept = 0;
-#pragma unroll
-    for (int k = 0; k < kSetupSlots; ++k) kept += valid[k] ? 1u : 0u;
-    kept = __reduce_add_sync(0xffffffffu, kept);
-    if (lane == 0 && kept) atomicAdd(&ctr[kCtrKept], kept);     // statistics only
-  }
-  __syncthreads();
+    __syncthreads();                               // B1 (also taken when the whole meshlet is culled in this frame)
+    if (pvis_bits != 0) {
+      TriRec *big = big_all + (size_t)f * d.cap_big;
+      uint32_t *ctr = ctr_all + (size_t)f * d.ctr_stride;
+      const uint4 *sv = s_vert[vbuf];
+      uint32_t *list = s_list[warp];
 
-  // ---- P4: reserve a run in the record list of every touched tile, then fill ----
-  for (int i = tid; i < d.ntiles; i += kSetupThreads) {
-    const uint32_t c = s_cnt[i];
-    if (c) {
-      const uint32_t base = atomicAdd(&ctr[kCtrWords + i], c);
-      if (base + c > d.cap_tile) atomicOr(&ctr[kCtrFlags], kFlagBinOverflow);   // the host grows cap_tile and retries
-      s_cur[i] = base;
-    }
-  }
-  __syncthreads();
-  TriRec *bins = bins_all + (size_t)frame * d.ntiles * d.cap_tile;
+      // ---- P2: per triangle: flag logic, cheap rejects; survivors and clip candidates compacted per warp ----
+      int nkeep = 0, nclip = 0;                    // warp-uniform
 #pragma unroll
-  for (int k = 0; k < kSetupSlots; ++k) {
-    if (!valid[k]) continue;
-    const uint4 q0 = make_uint4((uint32_t)rec[k].x0, (uint32_t)rec[k].y0, (uint32_t)rec[k].x1, (uint32_t)rec[k].y1);
-    const uint4 q1 = make_uint4((uint32_t)rec[k].x2, (uint32_t)rec[k].y2, __float_as_uint(rec[k].z0),
-                                __float_as_uint(rec[k].gx));
-    const uint4 q2 = make_uint4(__float_as_uint(rec[k].gy), rec[k].bx, rec[k].by, 0u);
-    const int tx0 = tiles[k] & 255, tx1 = (tiles[k] >> 8) & 255, ty0 = (tiles[k] >> 16) & 255, ty1 = tiles[k] >> 24;
-    for (int ty = ty0; ty <= ty1; ++ty)
-      for (int tx = tx0; tx <= tx1; ++tx) {
-        const int tile = ty * d.tiles_x + tx;
-        const uint32_t pos = atomicAdd(&s_cur[tile], 1u);
-        if (pos < d.cap_tile) {
-          uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)tile * d.cap_tile + pos);
-          dst[0] = q0; dst[1] = q1; dst[2] = q2;
+      for (int k = 0; k < kTPT; ++k) {
+        bool keep = false, clip = false;
+        if (ix[k] != kNoTri) {
+          const uint4 a = sv[ix[k] & 1023u], b = sv[(ix[k] >> 10) & 1023u], c = sv[ix[k] >> 20];
+          const uint32_t f_or = a.w | b.w | c.w, f_and = a.w & b.w & c.w;
+          if (!(f_or & kVfDead) && !(f_and & kVfAllOut)) {
+            if (f_or & kVfClip) clip = true;
+            else if (!(f_or & kVfBadW)) keep = tri_may_touch(a, b, c, d);
+          }
+        }
+        const unsigned bk = __ballot_sync(0xffffffffu, keep), bc = __ballot_sync(0xffffffffu, clip);
+        if (keep) list[nkeep + __popc(bk & lanemask_lt)] = ix[k];
+        if (clip) list[kWarpList - 1 - nclip - __popc(bc & lanemask_lt)] = ix[k];
+        nkeep += __popc(bk);
+        nclip += __popc(bc);
+      }
+      __syncwarp();
+
+      // ---- S3 for the rare triangles that cross the near plane or the guard band: recompute the three
+      // clip-space vertices (same inputs, same bits as P1), clip, set up, append to the frame's big list ----
+      for (int s = lane; s < nclip; s += 32) {
+        const uint32_t ixs = list[kWarpList - 1 - s];
+        const float4 qa = __ldg(m.verts + vert_off + (ixs & 1023u)), qb = __ldg(m.verts + vert_off + ((ixs >> 10) & 1023u)),
+                     qc = __ldg(m.verts + vert_off + (ixs >> 20));
+        const float4 *M = reinterpret_cast<const float4 *>(&s_mvp[mbuf][16 * __float_as_uint(qa.w)]);
+        const float4 c0 = M[0], c1 = M[1], c2 = M[2], c3 = M[3];
+        clip_and_emit(xform(c0, c1, c2, c3, qa.x, qa.y, qa.z), xform(c0, c1, c2, c3, qb.x, qb.y, qb.z),
+                      xform(c0, c1, c2, c3, qc.x, qc.y, qc.z), d, big, ctr);
+      }
+
+      // ---- P3 + P4: one lane per SURVIVOR (dense): full setup, then the warp reserves list space per tile ----
+      TriRec *bins = bins_all + (size_t)f * d.ntiles * d.cap_tile;
+      for (int s0 = 0; s0 < nkeep; s0 += 32) {
+        const int s = s0 + lane;
+        TriRec rec;
+        int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+        bool has = false;
+        if (s < nkeep) {
+          const uint32_t ixs = list[s];
+          const uint4 a = sv[ixs & 1023u], b = sv[(ixs >> 10) & 1023u], c = sv[ixs >> 20];
+          WV wa, wb, wc;
+          wa.X = (int)a.x; wa.Y = (int)a.y; wa.z = __uint_as_float(a.z);
+          wb.X = (int)b.x; wb.Y = (int)b.y; wb.z = __uint_as_float(b.z);
+          wc.X = (int)c.x; wc.Y = (int)c.y; wc.z = __uint_as_float(c.z);
+          if (setup_window_tri(wa, wb, wc, d, rec)) {
+            tx0 = (int)(rec.bx & 0xffffu) / kTileW; tx1 = (int)(rec.bx >> 16) / kTileW;
+            ty0 = (int)(rec.by & 0xffffu) / kTileH; ty1 = (int)(rec.by >> 16) / kTileH;
+            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) push_big(rec, d, big, ctr);     // read by every tile
+            else has = true;
+          }
+        }
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (lane == 0 && act) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
+        const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, (uint32_t)rec.x1, (uint32_t)rec.y1);
+        const uint4 q1 = make_uint4((uint32_t)rec.x2, (uint32_t)rec.y2, __float_as_uint(rec.z0), __float_as_uint(rec.gx));
+        const uint4 q2 = make_uint4(__float_as_uint(rec.gy), rec.bx, rec.by, 0u);
+        // every lane walks the tiles of its bbox; lanes that are on the same tile in the same step share one
+        // global atomic (consecutive triangles of a mesh mostly fall into one or two tiles)
+        int tx = tx0, ty = ty0;
+        while (act) {
+          const int tile = has ? ty * d.tiles_x + tx : -1 - lane;
+          const unsigned grp = __match_any_sync(0xffffffffu, tile);
+          const int leader = __ffs(grp) - 1;
+          uint32_t base = 0;
+          if (has && lane == leader) {
+            const uint32_t c = (uint32_t)__popc(grp);
+            base = atomicAdd(&ctr[kCtrWords + tile], c);
+            if (base + c > d.cap_tile) atomicOr(&ctr[kCtrFlags], kFlagBinOverflow);   // the host grows cap_tile and retries
+          }
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (has) {
+            const uint32_t pos = base + (uint32_t)__popc(grp & lanemask_lt);
+            if (pos < d.cap_tile) {
+              uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)tile * d.cap_tile + pos);
+              dst[0] = q0; dst[1] = q1; dst[2] = q2;
+            }
+            if (++tx > tx1) { tx = tx0; ++ty; }
+            has = ty <= ty1;
+          }
+          act = __ballot_sync(0xffffffffu, has);
         }
       }
+      __syncwarp();                                // the warp's list is rewritten in the next frame
+    }
+    // hand the matrices of frame f + 2 over (their loads were issued at the top of this iteration)
+    if (stage) {
+      float *dst = s_mvp[(it + 2) % 3];
+#pragma unroll
+      for (int k = 0; k < kMPT; ++k) {
+        const int i = k * kSetupThreads + tid;
+        if (i < nmv) dst[i] = mv_pre[k];
+      }
+    }
   }
 }
 
@@ -1190,14 +1252,17 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
   {
     long long total = (long long)n_frames * (d.n_parts + 1) * 16;
     unsigned blocks = (unsigned)((total + 255) / 256);
-    ruf_pose_kernel<<<blocks, 256, 0, s>>>(d_proj, d_view, d_part_model, d_lookat, d.n_parts, n_frames, ws.mvp);
+    ruf_pose_kernel<<<blocks, 256, 0, s>>>(d_proj, d_view, d_part_model, d_lookat, m.part_aabb, d.n_parts, n_frames,
+                                           ws.mvp, ws.vis);
     ++launches;
     if (ev) cudaEventRecord(ev[1], s);
   }
   {
-    dim3 grid((unsigned)d.n_meshlets, (unsigned)n_frames);
-    const size_t smem = (size_t)d.ntiles * 2 * sizeof(uint32_t);
-    ruf_setup_bin_kernel<<<grid, kSetupThreads, smem, s>>>(m, ws.mvp, d, ws.big, ws.bins, ws.ctr);
+    // a CTA keeps its meshlet in registers over a run of frames; short batches still fill the machine
+    int fpc = kSetupFrames;
+    while (fpc > 1 && (long long)d.n_meshlets * ((n_frames + fpc - 1) / fpc) < 2048) fpc >>= 1;
+    dim3 grid((unsigned)d.n_meshlets, (unsigned)((n_frames + fpc - 1) / fpc));
+    ruf_setup_bin_kernel<<<grid, kSetupThreads, 0, s>>>(m, ws.mvp, ws.vis, d, n_frames, fpc, ws.big, ws.bins, ws.ctr);
     ++launches;
     if (ev) cudaEventRecord(ev[2], s);
   }
