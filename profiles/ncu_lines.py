@@ -2,7 +2,7 @@
 """Per-source-line hot spots of one kernel: joins the SASS sampling page of an .ncu-rep (ncu --set full
 --import-source on) with nvdisasm's line table of the library that was profiled (-lineinfo build).
 
-    python profiles/ncu_lines.py gpurun_out/prof.ncu-rep ruf_setup_bin [top] [lib.so]
+    python profiles/ncu_lines.py gpurun_out/prof.ncu-rep ruf_setup_bin [top] [lib.so|-] [mangled-name substring]
 """
 import collections
 import csv
@@ -41,7 +41,9 @@ def line_table(lib, kernel):
     return []
 
 
-def main(rep, kernel, top=45, lib=None):
+def main(rep, kernel, top=45, lib=None, mangled=None):
+    """kernel: regex for ncu's (demangled) kernel name; mangled: substring of the mangled name in the cubin"""
+    mangled = mangled or kernel
     lib = lib or os.path.join(ROOT, "realtime_urdf_filter_b200", "libruf_b200.so")
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel],
                          capture_output=True, text=True).stdout
@@ -57,7 +59,7 @@ def main(rep, kernel, top=45, lib=None):
             break
         n_inst += 1
     body = body[:n_inst]
-    lt = line_table(lib, kernel)
+    lt = line_table(lib, mangled)
     if len(lt) != len(body):
         print(f"warning: {len(body)} profiled instructions vs {len(lt)} in {lib}: line numbers may be off", file=sys.stderr)
     col = {n: i for i, n in enumerate(hdr)}
@@ -86,4 +88,5 @@ def main(rep, kernel, top=45, lib=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 45, sys.argv[4] if len(sys.argv) > 4 else None)
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 45, sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None,
+         sys.argv[5] if len(sys.argv) > 5 else None)

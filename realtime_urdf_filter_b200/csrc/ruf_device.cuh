@@ -26,10 +26,9 @@ constexpr int kMaxPoly = 12;
 constexpr int kTileW = 64;
 constexpr int kTileH = 32;
 constexpr int kTilePix = kTileW * kTileH;       // 2048
-constexpr int kRasterThreads = 256;             // consumer threads: 8 pixels of one tile row each
-constexpr int kRasterBlock = kRasterThreads + 32;   // + one producer warp (bulk async copies)
+constexpr int kRasterThreads = 256;             // threads of a raster CTA: 8 pixels of one tile row each
 #ifndef RUF_CHUNK
-#define RUF_CHUNK 256
+#define RUF_CHUNK 128
 #endif
 constexpr int kChunk = RUF_CHUNK;               // records per ring stage (a multiple of 32)
 constexpr int kStages = 2;                      // ring depth (a stage is released as soon as its records sit in registers)
@@ -37,8 +36,16 @@ constexpr int kBigTiles = 12;                   // bbox touching more tiles -> p
 #ifndef RUF_MAX_UNITS
 #define RUF_MAX_UNITS 32
 #endif
-constexpr int kMaxUnits = RUF_MAX_UNITS;                   // row-block units (1 row x 8 samples) per record dealt to lanes;
-                                                // larger records are rasterised by the whole warp
+constexpr int kMaxUnits = RUF_MAX_UNITS;        // units per record dealt to lanes; larger records are rasterised by the whole warp
+#ifndef RUF_UNIT_W
+#define RUF_UNIT_W 4
+#endif
+#ifndef RUF_UNIT_H
+#define RUF_UNIT_H 2
+#endif
+constexpr int kUW = RUF_UNIT_W, kUH = RUF_UNIT_H;   // a unit = kUW x kUH samples handled by one lane in one round
+static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && kUH == 1) || (kUW == 8 && kUH == 2),
+              "unsupported unit shape");
 // tuning knobs (overridable with -D for experiments; the defaults are the measured best)
 #ifndef RUF_SETUP_THREADS
 #define RUF_SETUP_THREADS 256
@@ -56,8 +63,12 @@ constexpr int kMaxUnits = RUF_MAX_UNITS;                   // row-block units (1
 #define RUF_SETUP_MIN_BLOCKS 5
 #endif
 #ifndef RUF_RASTER_MIN_BLOCKS
-#define RUF_RASTER_MIN_BLOCKS 4
+#define RUF_RASTER_MIN_BLOCKS 5
 #endif
+#ifndef RUF_PREFETCH_DEPTH
+#define RUF_PREFETCH_DEPTH 0
+#endif
+constexpr bool kPrefetchDepth = RUF_PREFETCH_DEPTH != 0;   // raster kernel: cp.async the tile's sensor pixels at kernel entry
 constexpr int kSetupThreads = RUF_SETUP_THREADS;
 // A meshlet is the unit of work of one setup CTA: up to kMeshTris consecutive triangles of the model whose
 // bit-identical vertices were welded (at most kMeshVerts distinct ones, local indices of 10 bits) and whose

@@ -45,6 +45,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS); completion is per thread (cp.async.wait_all)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
   asm volatile(
@@ -584,29 +593,17 @@ __device__ __forceinline__ TriRec load_rec_global(const TriRec *p)
   return r;
 }
 
-// shared-memory min on the z tile (explicit .shared so that no generic-address atomic is generated)
-__device__ __forceinline__ void smem_min(uint32_t saddr, uint32_t v)
-{
-  asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint32_t smem_add(uint32_t saddr, uint32_t v)
 {
   uint32_t old;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
   return old;
 }
-__device__ __forceinline__ uint32_t smem_ld(uint32_t saddr)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
-
 // a whole warp covers the tile-clipped bbox in 8x4 footprints.  WIDE = false: every factor of the
 // edge functions is below 2^14, so 32-bit arithmetic is exact; WIDE = true: 64-bit.
 template <bool WIDE>
 __device__ __forceinline__ void raster_warp(const TriRec &r, int i0, int i1, int j0, int j1, int tile_x0,
-                                            int tile_y0, uint32_t sz_addr, int lane)
+                                            int tile_y0, uint32_t *sz, int lane)
 {
   typedef typename std::conditional<WIDE, long long, int>::type acc_t;
   const Edges e = make_edges(r);
@@ -626,8 +623,8 @@ __device__ __forceinline__ void raster_warp(const TriRec &r, int i0, int i1, int
       const acc_t e2 = (acc_t)e.A2 * (px - r.x2) + c2;
       if (i <= i1 && j <= j1 && (e0 | e1 | e2) >= 0) {
         const uint32_t z = __float_as_uint(clamp_z(fmaf(r.gx, (float)(px - r.x0), rowz)));
-        const uint32_t addr = sz_addr + 4u * (uint32_t)((j - tile_y0) * kTileW + (i - tile_x0));
-        if (z < 0x3f800000u && z < smem_ld(addr)) smem_min(addr, z);
+        uint32_t *p = sz + ((j - tile_y0) * kTileW + (i - tile_x0));
+        if (z < 0x3f800000u && z < *p) atomicMin(p, z);
       }
     }
   }
@@ -655,7 +652,7 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
 }
 __device__ __forceinline__ void consumer_bar_sync()
 {
-  asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory");
+  __syncthreads();
 }
 
 // saturate_cast<ushort>(cvRound(x * 1000.f)) -- cv::Mat::convertTo(CV_16U, 1000.0), src/urdf_filter.cpp:311
@@ -681,12 +678,13 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
 }
 
 template <int ENC>
-__global__ void __launch_bounds__(kRasterBlock, RUF_RASTER_MIN_BLOCKS)
+__global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
                          const uint32_t *__restrict__ ctr_all, uint32_t *status, ShaderParams sp, FrameBuffers fb)
 {
-  // Warp roles: warps 0..7 (kRasterThreads = 256 threads) rasterise and shade; warp 8 is the producer
-  // that streams the tile's record list into the shared-memory ring with bulk async copies.
+  // 8 warps rasterise and shade.  The tile's record list streams into a shared-memory ring by bulk async
+  // copies (TMA): thread 0 starts the first kStages chunks, later refills are issued by whichever warp
+  // takes the last batch of a chunk (there is no dedicated producer warp holding registers).
   // dynamic shared memory (more than the 48 KB static limit): record ring, then the unit tables
   extern __shared__ __align__(128) unsigned char s_raster_dyn[];
   TriRec (*sbuf)[kChunk] = reinterpret_cast<TriRec (*)[kChunk]>(s_raster_dyn);
@@ -696,13 +694,13 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ uint32_t s_next;
   __shared__ uint8_t s_bigcls[kRasterThreads];
+  // this tile of the sensor image, fetched by cp.async at kernel entry and consumed by the fragment stage
+  __shared__ __align__(16) unsigned char s_depth[kPrefetchDepth ? kTilePix * (ENC == 1 ? 2 : 4) : 16];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool is_producer = warp == kRasterThreads / 32;
   const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
   const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
   const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
-  const uint32_t sz_addr = smem_u32(sz);
   // records binned to this tile (CTA-uniform).  Two thirds of the tiles of a typical frame see only the
   // background quad: they take the register-only path below (no ring, no z tile, no CTA-wide barrier).
   const uint32_t cnt = min(__ldg(ctr + kCtrWords + tile), d.cap_tile);
@@ -711,41 +709,46 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     const uint32_t flags = ctr[kCtrFlags];
     if (flags) atomicOr(status, flags);
   }
-  if (cnt == 0) {
-    if (is_producer) return;
-  } else {
+  const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
+  const TriRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
+  if (cnt) {
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < kStages; ++s) {
-        mbar_init(&full_bar[s], 1);                        // the producer's arrive.expect_tx
+        mbar_init(&full_bar[s], 1);                        // the issuing thread's arrive.expect_tx
         mbar_init(&empty_bar[s], kChunk / 32);             // one arrive per batch of 32 records
       }
       mbar_fence_init();
       s_next = 0;
+#pragma unroll
+      for (int c = 0; c < kStages; ++c) {
+        if (c < nchunks) {
+          const uint32_t lo = (uint32_t)c * kChunk, n = min((uint32_t)kChunk, cnt - lo);
+          mbar_arrive_expect_tx(&full_bar[c], n * (uint32_t)sizeof(TriRec));
+          bulk_g2s(&sbuf[c][0], list + lo, n * (uint32_t)sizeof(TriRec), &full_bar[c]);
+        }
+      }
     }
     __syncthreads();
   }
 
-  const int prow = (tid & (kRasterThreads - 1)) >> 3, pcol = (tid & 7) * 8;
-  const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
-
-  if (is_producer) {
-    // ===== producer warp: the tile's list is contiguous, one bulk copy per chunk =====
-    if (lane == 0) {
-      const TriRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
-      for (int c = 0; c < nchunks; ++c) {
-        const int stage = c % kStages;
-        const uint32_t use = (uint32_t)c / kStages;
-        if (use > 0) mbar_wait(&empty_bar[stage], (use - 1) & 1);   // consumers drained the previous content
-        const uint32_t lo = (uint32_t)c * kChunk, n = min((uint32_t)kChunk, cnt - lo);
-        mbar_arrive_expect_tx(&full_bar[stage], n * (uint32_t)sizeof(TriRec));
-        bulk_g2s(&sbuf[stage][0], list + lo, n * (uint32_t)sizeof(TriRec), &full_bar[stage]);
-      }
-    }
-    return;
-  }
+  const int prow = tid >> 3, pcol = (tid & 7) * 8;
 
   // ===== consumer warps =====
+  // every thread shades 8 consecutive pixels of one tile row at the end; their sensor values start their
+  // way from HBM now (cp.async into shared memory: no registers held, nobody else reads them)
+  const int gy = tile_y0 + prow, gx = tile_x0 + pcol;
+  const size_t pix = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
+  const bool full = fb.vec_ok && gy < d.H && (gx + 8 <= d.W);
+  unsigned char *my_depth = s_depth + (size_t)(prow * kTileW + pcol) * (ENC == 1 ? 2 : 4);
+  if (full && kPrefetchDepth) {
+    if (ENC == 1) {
+      cp_async16(my_depth, static_cast<const uint16_t *>(fb.depth_in) + pix);
+    } else {
+      cp_async16(my_depth, static_cast<const float *>(fb.depth_in) + pix);
+      cp_async16(my_depth + 16, static_cast<const float *>(fb.depth_in) + pix + 4);
+    }
+  }
   float zr[8];                                  // this thread's 8 pixels of the z tile
   {
     {
@@ -759,7 +762,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         const int py = (tile_y0 + prow) * kSubpix + kSubpixHalf;
         const int tpx = tile_x0 * kSubpix + kSubpixHalf, tpy = tile_y0 * kSubpix + kSubpixHalf;
         for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
-          // classify 256 records in parallel (one per thread): 0 = no sample of this tile can be
+          // classify 256 records in parallel (one per thread; a typical frame has just the two triangles of
+          // the background quad, so only warp 0 does any work here): 0 = no sample of this tile can be
           // covered, 1 = every sample is covered, 2 = mixed.  Edge values are linear over the tile's
           // sample grid, so their min / max sit on its corners.
           uint32_t cls = 0;
@@ -846,6 +850,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         int kind = 0;       // 0 nothing, 1 dealt out as row-block units, 2 warp-wide 32-bit, 3 warp-wide 64-bit
         int sA0 = 0, sA1 = 0, sA2 = 0, sB0 = 0, sB1 = 0, sB2 = 0, r0 = 0, r1 = 0, r2 = 0;
         int ncb = 0, nunits = 0;
+        int geo = 0, bx = 0, by = 0;   // tile-local bbox origin and extent (packed); sample (i0, j0) relative to vertex 0
         if (idx < nrec) {
           r = load_rec_smem(&sbuf[stage][idx]);
           i0 = max((int)(r.bx & 0xffffu), tile_x0); i1 = min((int)(r.bx >> 16), tile_x0 + kTileW - 1);
@@ -853,17 +858,19 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           const int ex = max(r.x0, max(r.x1, r.x2)) - min(r.x0, min(r.x1, r.x2));
           const int ey = max(r.y0, max(r.y1, r.y2)) - min(r.y0, min(r.y1, r.y2));
           const bool narrow = ex < 16384 && ey < 16384;     // every edge-function factor < 2^14: int32 is exact
-          ncb = (i1 - i0 + 8) >> 3;                          // 8-sample blocks per row
-          nunits = ncb * (j1 - j0 + 1);
+          ncb = (i1 - i0 + kUW) / kUW;                       // unit columns
+          nunits = ncb * ((j1 - j0 + kUH) / kUH);
           kind = narrow ? ((nunits <= kMaxUnits) ? 1 : 2) : 3;
           if (kind == 1) {
             const Edges e = make_edges(r);
             const int px0 = i0 * kSubpix + kSubpixHalf, py0 = j0 * kSubpix + kSubpixHalf;
-            r0 = e.A0 * (px0 - r.x0) + e.B0 * (py0 - r.y0) + e.bias0;
+            bx = px0 - r.x0; by = py0 - r.y0;
+            r0 = e.A0 * bx + e.B0 * by + e.bias0;
             r1 = e.A1 * (px0 - r.x1) + e.B1 * (py0 - r.y1) + e.bias1;
             r2 = e.A2 * (px0 - r.x2) + e.B2 * (py0 - r.y2) + e.bias2;
             sA0 = e.A0 * kSubpix; sA1 = e.A1 * kSubpix; sA2 = e.A2 * kSubpix;
             sB0 = e.B0 * kSubpix; sB1 = e.B1 * kSubpix; sB2 = e.B2 * kSubpix;
+            geo = (i0 - tile_x0) | ((j0 - tile_y0) << 6) | ((i1 - i0) << 11) | ((j1 - j0) << 17);
           } else {
             nunits = 0;
           }
@@ -872,16 +879,38 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         }
         __syncwarp();
         if (lane == 0) {
-          // this batch sits in registers.  A short last chunk has fewer than 8 batches: whoever drew its
+          // this batch sits in registers.  A short last chunk has fewer batches: whoever drew its
           // first batch also arrives for the missing ones so that the barrier phase always completes.
           const uint32_t in_chunk = (nrec + 31u) / 32u;
           const uint32_t extra = ((bt % (kChunk / 32)) == 0) ? (kChunk / 32 - in_chunk) : 0u;
           mbar_arrive_n(&empty_bar[stage], 1u + extra);
+          // whoever took the chunk's last batch refills the stage with chunk c + kStages once all batches of
+          // chunk c sit in registers (the other warps are at most a few shared-memory loads away from that)
+          const int cn = c + kStages;
+          if ((bt % (kChunk / 32)) == (kChunk / 32) - 1 && cn < nchunks) {
+            mbar_wait(&empty_bar[stage], ((uint32_t)c / kStages) & 1);
+            const uint32_t lo = (uint32_t)cn * kChunk, n = min((uint32_t)kChunk, cnt - lo);
+            mbar_arrive_expect_tx(&full_bar[stage], n * (uint32_t)sizeof(TriRec));
+            bulk_g2s(&sbuf[stage][0], list + lo, n * (uint32_t)sizeof(TriRec), &full_bar[stage]);
+          }
         }
 
-        // ---- phase 2: the row-block units (one row x 8 samples) of the 32 records are dealt out to
-        // the lanes round by round, so every lane does the same amount of branch-free work.  Unit
-        // table in shared memory: owner lane | row << 5 | block << 10.
+        // big or wide records first (the full record dies after this, which keeps the unit loop's register
+        // footprint small): the whole warp covers one triangle at a time
+        unsigned wide = __ballot_sync(0xffffffffu, kind >= 2);
+        while (wide) {
+          const int src = __ffs(wide) - 1;
+          wide &= wide - 1;
+          const TriRec q = shfl_rec(r, src);
+          const int qi0 = __shfl_sync(0xffffffffu, i0, src), qi1 = __shfl_sync(0xffffffffu, i1, src);
+          const int qj0 = __shfl_sync(0xffffffffu, j0, src), qj1 = __shfl_sync(0xffffffffu, j1, src);
+          if (__shfl_sync(0xffffffffu, kind, src) == 2) raster_warp<false>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz, lane);
+          else raster_warp<true>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz, lane);
+        }
+
+        // ---- phase 2: the units (kUW x kUH samples) of the 32 records are dealt out to the lanes
+        // round by round, so every lane does the same amount of branch-free work.  Unit table in
+        // shared memory: owner lane | unit row << 5 | unit column << 10.
         int incl = nunits;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -903,7 +932,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           const int x = base + lane;
           const bool act = x < items;
           const uint32_t ent = act ? (uint32_t)utab[x] : 0u;
-          const int o = (int)(ent & 31u), row = (int)((ent >> 5) & 31u), cb = (int)(ent >> 10);
+          const int o = (int)(ent & 31u), urow = (int)((ent >> 5) & 31u), ucol = (int)(ent >> 10);
           // fetch the owner's setup (all lanes shuffle; inactive lanes read lane 0 and discard)
           const int qA0 = __shfl_sync(0xffffffffu, sA0, o), qA1 = __shfl_sync(0xffffffffu, sA1, o),
                     qA2 = __shfl_sync(0xffffffffu, sA2, o);
@@ -911,51 +940,52 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
                     qB2 = __shfl_sync(0xffffffffu, sB2, o);
           int e0 = __shfl_sync(0xffffffffu, r0, o), e1 = __shfl_sync(0xffffffffu, r1, o),
               e2 = __shfl_sync(0xffffffffu, r2, o);
-          const int qi0 = __shfl_sync(0xffffffffu, i0, o), qi1 = __shfl_sync(0xffffffffu, i1, o);
-          const int qj0 = __shfl_sync(0xffffffffu, j0, o);
-          const int qx0 = __shfl_sync(0xffffffffu, r.x0, o), qy0 = __shfl_sync(0xffffffffu, r.y0, o);
+          const int qgeo = __shfl_sync(0xffffffffu, geo, o);
+          const int qbx = __shfl_sync(0xffffffffu, bx, o), qby = __shfl_sync(0xffffffffu, by, o);
           const float qz0 = __shfl_sync(0xffffffffu, r.z0, o), qgx = __shfl_sync(0xffffffffu, r.gx, o),
                       qgy = __shfl_sync(0xffffffffu, r.gy, o);
           if (act) {
-            const int col = qi0 + cb * 8, j = qj0 + row;
-            e0 += row * qB0 + cb * 8 * qA0;
-            e1 += row * qB1 + cb * 8 * qA1;
-            e2 += row * qB2 + cb * 8 * qA2;
+            const int dx = ucol * kUW, dy = urow * kUH;          // unit origin relative to the bbox origin
+            e0 += dy * qB0 + dx * qA0;
+            e1 += dy * qB1 + dx * qA1;
+            e2 += dy * qB2 + dx * qA2;
             uint32_t m = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              m = __funnelshift_l((uint32_t)(e0 | e1 | e2), m, 1);   // shifts in 1 for "outside"
-              e0 += qA0; e1 += qA1; e2 += qA2;
-            }
-            // bit (7 - k) of ~m <=> sample col + k is covered; samples beyond i1 belong to another tile
-            const int valid = min(8, qi1 - col + 1);
-            m = (~m) & 0xffu & (0xff00u >> valid);
-            if (m) {
-              const int py = j * kSubpix + kSubpixHalf;
-              const float rowz = fmaf(qgy, (float)(py - qy0), qz0);
-              const float f0 = (float)(col * kSubpix + kSubpixHalf - qx0);   // exact: |value| < 2^24
-              const uint32_t addr = sz_addr + 4u * (uint32_t)((j - tile_y0) * kTileW + (col - tile_x0));
+            for (int rr = 0; rr < kUH; ++rr) {
+              int f0 = e0, f1 = e1, f2 = e2;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                // float(px - x0) for sample k = f0 + 256 k (integers below 2^24: the sum is exact)
-                const uint32_t z = __float_as_uint(clamp_z(fmaf(qgx, f0 + (float)(k * kSubpix), rowz)));
-                if ((m & (0x80u >> k)) && z < 0x3f800000u) smem_min(addr + 4u * k, z);
+              for (int k = 0; k < kUW; ++k) {
+                m = __funnelshift_l((uint32_t)(f0 | f1 | f2), m, 1);   // shifts in 1 for "outside"
+                f0 += qA0; f1 += qA1; f2 += qA2;
+              }
+              e0 += qB0; e1 += qB1; e2 += qB2;
+            }
+            // bit (kUW*kUH - 1 - (rr*kUW + k)) of ~m <=> sample (dx + k, dy + rr) is covered; samples beyond
+            // the bbox (clipped to the tile) belong to another tile or cannot be covered
+            const int wrem = ((qgeo >> 11) & 63) + 1 - dx, hrem = ((qgeo >> 17) & 31) + 1 - dy;
+            constexpr uint32_t kRowMask = (1u << kUW) - 1u, kAll = (kUH == 1) ? kRowMask : ((1u << (kUW * kUH)) - 1u);
+            uint32_t vm = (kRowMask << kUW >> min(kUW, wrem)) & kRowMask;      // valid columns, MSB = k = 0
+            if (kUH == 2) vm = (vm << kUW) | (hrem > 1 ? vm : 0u);
+            m = (~m) & kAll & vm;
+            if (m) {
+              const float fx0 = (float)(qbx + dx * kSubpix);                  // exact: |value| < 2^24
+              // (plain atomicMin on the static __shared__ array: direct shared addressing, immediate offsets)
+              uint32_t *zp = sz + ((((qgeo >> 6) & 31) + dy) * kTileW + (qgeo & 63) + dx);
+#pragma unroll
+              for (int rr = 0; rr < kUH; ++rr) {
+                const float rowz = fmaf(qgy, (float)(qby + (dy + rr) * kSubpix), qz0);
+#pragma unroll
+                for (int k = 0; k < kUW; ++k) {
+                  // float(px - x0) for sample k = fx0 + 256 k (integers below 2^24: the sum is exact)
+                  const uint32_t z = __float_as_uint(clamp_z(fmaf(qgx, fx0 + (float)(k * kSubpix), rowz)));
+                  if ((m & (1u << (kUW * kUH - 1 - (rr * kUW + k)))) && z < 0x3f800000u)
+                    atomicMin(zp + (rr * kTileW + k), z);
+                }
               }
             }
           }
         }
         __syncwarp();                          // the unit table is rewritten by the next batch
-        // big or wide records: the whole warp covers one triangle at a time
-        unsigned wide = __ballot_sync(0xffffffffu, kind >= 2);
-        while (wide) {
-          const int src = __ffs(wide) - 1;
-          wide &= wide - 1;
-          const TriRec q = shfl_rec(r, src);
-          const int qi0 = __shfl_sync(0xffffffffu, i0, src), qi1 = __shfl_sync(0xffffffffu, i1, src);
-          const int qj0 = __shfl_sync(0xffffffffu, j0, src), qj1 = __shfl_sync(0xffffffffu, j1, src);
-          if (__shfl_sync(0xffffffffu, kind, src) == 2) raster_warp<false>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz_addr, lane);
-          else raster_warp<true>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz_addr, lane);
-        }
       }
     }
     consumer_bar_sync();                      // every record of the tile has been rasterised
@@ -967,13 +997,11 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   }
 
   // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
-  const int gy = tile_y0 + prow, gx = tile_x0 + pcol;
   if (gy >= d.H || gx >= d.W) return;
-  const size_t img = (size_t)frame * d.W * d.H;
-  const size_t base = img + (size_t)gy * d.W + gx;
+  const size_t base = pix;
   const float (&zw)[8] = zr;
-  const bool full = fb.vec_ok && (gx + 8 <= d.W);
   if (full) {
+    if (kPrefetchDepth) cp_async_wait_all();    // this thread's own copies: no barrier needed
     // to_linear_depth (frag:14-17,22) once per distinct z of this thread's run: background pixels
     // share one window z, so most threads divide once instead of eight times
     float virt[8];
@@ -987,7 +1015,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
     uint32_t om[8];
     if (ENC == 1) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + base));
+      const uint4 q = kPrefetchDepth ? *reinterpret_cast<const uint4 *>(my_depth)
+                                     : __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + base));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
       const uint32_t repl = f32_to_u16(sp.replace_value);       // convertTo(CV_16U, 1000) of the replaced pixels, :311
       uint32_t u[8];
@@ -1006,8 +1035,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       o.x = u[0] | (u[1] << 16); o.y = u[2] | (u[3] << 16); o.z = u[4] | (u[5] << 16); o.w = u[6] | (u[7] << 16);
       *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
     } else {
-      const float4 *p = reinterpret_cast<const float4 *>(static_cast<const float *>(fb.depth_in) + base);
-      const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+      const float4 *p = kPrefetchDepth ? reinterpret_cast<const float4 *>(my_depth)
+                                       : reinterpret_cast<const float4 *>(static_cast<const float *>(fb.depth_in) + base);
+      const float4 q0 = p[0], q1 = p[1];
       const float sensor[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
       float od[8];
 #pragma unroll
@@ -1269,9 +1299,9 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
   {
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (enc == 1)
-      ruf_raster_filter_kernel<1><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
+      ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
     else
-      ruf_raster_filter_kernel<0><<<grid, kRasterBlock, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
+      ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
     ++launches;
     if (ev) cudaEventRecord(ev[3], s);
   }
