@@ -365,7 +365,6 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
 {
   constexpr int kVPT = (kMeshVerts + kSetupThreads - 1) / kSetupThreads;   // vertices per thread
   constexpr int kTPT = kSetupSlots;                                       // triangles per thread
-  constexpr int kMPT = (kMeshParts * 16 + kSetupThreads - 1) / kSetupThreads;   // MVP floats staged per thread
   constexpr int kWarpList = kTPT * 32;                                    // triangles a warp classifies per frame
   __shared__ uint4 s_vert[2][kMeshVerts];        // X, Y, bits(z_w), flags; double-buffered over frames
   __shared__ uint32_t s_list[kSetupThreads / 32][kWarpList];   // per warp: survivors from the front, clip candidates from the back
@@ -414,18 +413,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
   for (int f = f0; f < f1; ++f) {
     const int it = f - f0, vbuf = it & 1, mbuf = it % 3;
     const uint32_t pvis_bits = pvis_next;        // bit i: part part_lo + i may be visible in frame f
-    // prefetch: matrices of frame f + 2 (stored to shared memory at the end of this iteration, read after
-    // B1 of frame f + 1), cull bytes of frame f + 1
-    float mv_pre[kMPT];
-    const bool stage = f + 2 < f1;
-    if (stage) {
-      const float *src = mvp_all + 16 * ((size_t)(f + 2) * rows + part_lo);
-#pragma unroll
-      for (int k = 0; k < kMPT; ++k) {
-        const int i = k * kSetupThreads + tid;
-        mv_pre[k] = (i < nmv) ? __ldg(src + i) : 0.0f;
-      }
-    }
+    // prefetch the cull bytes of frame f + 1
     uint32_t vb_next = 0;
     if (f + 1 < f1 && lane <= npm1) vb_next = (uint32_t)__ldg(vis_all + (size_t)(f + 1) * rows + part_lo + lane);
     pvis_next = __ballot_sync(0xffffffffu, vb_next != 0u);
@@ -446,7 +434,15 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         }
       }
     }
+    cp_async_wait_all();                           // this thread's share of the matrices of frame f + 1 has landed
     __syncthreads();                               // B1 (also taken when the whole meshlet is culled in this frame)
+    // matrices of frame f + 2 -> shared memory (cp.async: no registers held).  Their buffer was last read in
+    // frame f - 1, which every warp has left by now; they are read after B1 of frame f + 1.
+    if (f + 2 < f1) {
+      const float *src = mvp_all + 16 * ((size_t)(f + 2) * rows + part_lo);
+      float *dst = s_mvp[(it + 2) % 3];
+      for (int i = tid; i < nmv / 4; i += kSetupThreads) cp_async16(dst + 4 * i, src + 4 * i);
+    }
     if (pvis_bits != 0) {
       TriRec *big = big_all + (size_t)f * d.cap_big;
       uint32_t *ctr = ctr_all + (size_t)f * d.ctr_stride;
@@ -539,15 +535,6 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         }
       }
       __syncwarp();                                // the warp's list is rewritten in the next frame
-    }
-    // hand the matrices of frame f + 2 over (their loads were issued at the top of this iteration)
-    if (stage) {
-      float *dst = s_mvp[(it + 2) % 3];
-#pragma unroll
-      for (int k = 0; k < kMPT; ++k) {
-        const int i = k * kSetupThreads + tid;
-        if (i < nmv) dst[i] = mv_pre[k];
-      }
     }
   }
 }
