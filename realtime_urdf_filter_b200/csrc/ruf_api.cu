@@ -23,6 +23,11 @@ struct ruf_context {
 
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;       // copy streams of the host-batch pipeline
+  // large device-resident batches are cut into slices that alternate between two auxiliary streams, so that
+  // the (latency-bound) setup kernel of one slice overlaps the (issue-bound) raster kernel of the previous one
+  int slice_frames = 0;                               // 0 = off
+  cudaStream_t s_aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
   // model
   long long n_tris = 0;
@@ -197,9 +202,49 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
     ev = c->ev_pool.data() + c->ev_used;
     c->ev_used += kNumStages + 1;
   }
-  cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, enc,
-                                sp, fb, s, &launches, ev);
-  if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  const int S = c->slice_frames;
+  if (!ev && S > 0 && n_frames >= 2 * S) {
+    // fork: slices alternate between the two auxiliary streams; join back into `s`
+    if (!c->s_aux[0]) {
+      for (int i = 0; i < 2; ++i) {
+        RUF_CUDA(c, cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
+        RUF_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+      }
+      RUF_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    }
+    RUF_CUDA(c, cudaEventRecord(c->ev_fork, s));
+    for (int i = 0; i < 2; ++i) RUF_CUDA(c, cudaStreamWaitEvent(c->s_aux[i], c->ev_fork, 0));
+    const size_t es = (enc == RUF_ENC_U16_MM) ? 2 : 4, img = (size_t)c->W * c->H;
+    const int P = c->n_parts;
+    int k = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += S, ++k) {
+      const int nf = (n_frames - f0 < S) ? (n_frames - f0) : S;
+      Workspace ws = c->ws;
+      ws.mvp += (size_t)f0 * (P + 1) * 16;
+      ws.vis += (size_t)f0 * (P + 1);
+      ws.ctr += (size_t)f0 * c->dims.ctr_stride;
+      ws.big += (size_t)f0 * c->dims.cap_big;
+      ws.bins += (size_t)f0 * c->dims.ntiles * c->dims.cap_tile;
+      FrameBuffers fs = fb;
+      fs.depth_in = (const char *)d_in + f0 * img * es;
+      fs.depth_out = (char *)d_out + f0 * img * es;
+      fs.mask_out = d_mask ? d_mask + f0 * img : nullptr;
+      fs.zbuf_out = d_zbuf ? d_zbuf + f0 * img : nullptr;
+      int l = 0;
+      cudaError_t e = launch_frames(c->dims, m, ws, nf, d_proj, d_view + 16 * (size_t)f0, d_model + 16 * (size_t)f0 * P,
+                                    c->d_lookat, enc, sp, fs, c->s_aux[k & 1], &l, nullptr);
+      if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+      launches += l;
+    }
+    for (int i = 0; i < 2; ++i) {
+      RUF_CUDA(c, cudaEventRecord(c->ev_join[i], c->s_aux[i]));
+      RUF_CUDA(c, cudaStreamWaitEvent(s, c->ev_join[i], 0));
+    }
+  } else {
+    cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, enc,
+                                  sp, fb, s, &launches, ev);
+    if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  }
   c->stats.kernel_launches += launches;
   return RUF_OK;
 }
@@ -234,6 +279,10 @@ int ruf_create(ruf_context **out, int device, int width, int height, double z_ne
   if ((e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   c->stream = c->own_stream;
+  if (const char *e2 = getenv("RUF_SLICE_FRAMES")) {    // tuning aid
+    const int v = atoi(e2);
+    if (v >= 0 && v <= 65535) c->slice_frames = v;
+  }
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
@@ -284,6 +333,11 @@ int ruf_destroy(ruf_context *c)
     if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
   }
   for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
+  for (int i = 0; i < 2; ++i) {
+    if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);

@@ -60,7 +60,7 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #define RUF_SETUP_FRAMES 4
 #endif
 #ifndef RUF_SETUP_MIN_BLOCKS
-#define RUF_SETUP_MIN_BLOCKS 5
+#define RUF_SETUP_MIN_BLOCKS 6
 #endif
 #ifndef RUF_RASTER_MIN_BLOCKS
 #define RUF_RASTER_MIN_BLOCKS 5

@@ -379,6 +379,14 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
   const int nmv = (npm1 + 1) * 16;               // floats of the meshlet's MVP rows (consecutive parts: contiguous)
   const int f0 = blockIdx.y * frames_per_cta, f1 = min(n_frames, f0 + frames_per_cta);
 
+  // nothing of this meshlet visible in any frame of the run (per-part cull bytes of the pose kernel)? leave
+  // before touching the model.  Every warp decides by itself from the same bytes: consistent across the CTA.
+  {
+    bool any = false;
+    for (int f = f0; f < f1; ++f)
+      any |= (lane <= npm1) && __ldg(vis_all + (size_t)f * rows + part_lo + lane) != 0;
+    if (!__any_sync(0xffffffffu, any)) return;
+  }
   // the meshlet stays in registers for all frames of this CTA
   float4 vq[kVPT];
   uint32_t ix[kTPT];
@@ -503,35 +511,53 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
             else has = true;
           }
         }
-        unsigned act = __ballot_sync(0xffffffffu, has);
-        if (lane == 0 && act) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
+        const unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!act) continue;
+        if (lane == 0) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
         const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, (uint32_t)rec.x1, (uint32_t)rec.y1);
         const uint4 q1 = make_uint4((uint32_t)rec.x2, (uint32_t)rec.y2, __float_as_uint(rec.z0), __float_as_uint(rec.gx));
         const uint4 q2 = make_uint4(__float_as_uint(rec.gy), rec.bx, rec.by, 0u);
-        // every lane walks the tiles of its bbox; lanes that are on the same tile in the same step share one
-        // global atomic (consecutive triangles of a mesh mostly fall into one or two tiles)
-        int tx = tx0, ty = ty0;
-        while (act) {
-          const int tile = has ? ty * d.tiles_x + tx : -1 - lane;
-          const unsigned grp = __match_any_sync(0xffffffffu, tile);
-          const int leader = __ffs(grp) - 1;
-          uint32_t base = 0;
-          if (has && lane == leader) {
-            const uint32_t c = (uint32_t)__popc(grp);
-            base = atomicAdd(&ctr[kCtrWords + tile], c);
-            if (base + c > d.cap_tile) atomicOr(&ctr[kCtrFlags], kFlagBinOverflow);   // the host grows cap_tile and retries
+        // P4.  The round's records fall into a few tiles (consecutive triangles of a mesh).  The warp walks the
+        // union rectangle of the lanes' tile ranges twice: pass 1 counts the records of every tile (one ballot
+        // each) and parks the count in the lane with the tile's ordinal; ALL reservations are then issued at
+        // once (one global atomic per touched tile, their latencies overlap); pass 2 hands the bases out and
+        // the lanes write their records.
+        if (!has) { tx0 = 0x7fff; ty0 = 0x7fff; tx1 = -1; ty1 = -1; }
+        const int ux0 = __reduce_min_sync(0xffffffffu, tx0), ux1 = __reduce_max_sync(0xffffffffu, tx1);
+        const int uy0 = __reduce_min_sync(0xffffffffu, ty0), uy1 = __reduce_max_sync(0xffffffffu, ty1);
+        const int un = (ux1 - ux0 + 1) * (uy1 - uy0 + 1);
+        for (int t0 = 0, cx = ux0, cy = uy0; t0 < un; t0 += 32) {
+          const int nt = min(32, un - t0);
+          uint32_t mycnt = 0;
+          int mytile = 0;
+          int tx = cx, ty = cy;
+          for (int t = 0; t < nt; ++t) {
+            const unsigned in = __ballot_sync(0xffffffffu, tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1);
+            if (lane == t) { mycnt = (uint32_t)__popc(in); mytile = ty * d.tiles_x + tx; }
+            if (++tx > ux1) { tx = ux0; ++ty; }
           }
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (has) {
-            const uint32_t pos = base + (uint32_t)__popc(grp & lanemask_lt);
-            if (pos < d.cap_tile) {
-              uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)tile * d.cap_tile + pos);
-              dst[0] = q0; dst[1] = q1; dst[2] = q2;
+          uint32_t mybase = 0;
+          if (mycnt) {
+            mybase = atomicAdd(&ctr[kCtrWords + mytile], mycnt);
+            if (mybase + mycnt > d.cap_tile) atomicOr(&ctr[kCtrFlags], kFlagBinOverflow);   // the host grows cap_tile and retries
+          }
+          tx = cx; ty = cy;
+          for (int t = 0; t < nt; ++t) {
+            const bool mine = tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1;
+            const unsigned in = __ballot_sync(0xffffffffu, mine);
+            if (in) {
+              const uint32_t base = __shfl_sync(0xffffffffu, mybase, t);
+              if (mine) {
+                const uint32_t pos = base + (uint32_t)__popc(in & lanemask_lt);
+                if (pos < d.cap_tile) {
+                  uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)(ty * d.tiles_x + tx) * d.cap_tile + pos);
+                  dst[0] = q0; dst[1] = q1; dst[2] = q2;
+                }
+              }
             }
-            if (++tx > tx1) { tx = tx0; ++ty; }
-            has = ty <= ty1;
+            if (++tx > ux1) { tx = ux0; ++ty; }
           }
-          act = __ballot_sync(0xffffffffu, has);
+          cx = tx; cy = ty;
         }
       }
       __syncwarp();                                // the warp's list is rewritten in the next frame
