@@ -135,7 +135,8 @@ static int ensure_workspace(ruf_context *c, int frames)
   c->dims.cap_big = (uint32_t)cap_big;
   c->dims.cap_tile = (uint32_t)cap_tile;
   c->dims.n_meshlets = c->n_meshlets;
-  c->dims.ctr_stride = kCtrWords + c->dims.ntiles;
+  c->dims.ctr_stride = kCtrWords + 2 * c->dims.ntiles;
+  static_assert(kPartStride == kPartStrideHost, "part table stride");
   const size_t f = (size_t)frames;
   RUF_CUDA(c, cudaMalloc(&c->ws.mvp, f * (c->n_parts + 1) * 16 * sizeof(float)));
   RUF_CUDA(c, cudaMalloc(&c->ws.vis, f * (c->n_parts + 1)));
@@ -721,7 +722,10 @@ int ruf_get_stats(ruf_context *c, ruf_stats *out)
       const uint32_t *p = h.data() + (size_t)f * stride;
       s.visible_tris += p[kCtrKept];
       s.big_tris += p[kCtrBig];
-      for (int t = 0; t < c->dims.ntiles; ++t) s.binned_refs += p[kCtrWords + t];
+#ifdef RUF_CULL_STATS
+      s.h2d_bytes += p[1] & 0xffffu; s.d2h_bytes += p[1] >> 16;      // debug: depth-cull tested / culled records
+#endif
+      for (int t = 0; t < 2 * c->dims.ntiles; ++t) s.binned_refs += p[kCtrWords + t];
     }
   }
   *out = s;

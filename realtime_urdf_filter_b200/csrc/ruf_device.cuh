@@ -69,6 +69,10 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #define RUF_PREFETCH_DEPTH 0
 #endif
 constexpr bool kPrefetchDepth = RUF_PREFETCH_DEPTH != 0;   // raster kernel: cp.async the tile's sensor pixels at kernel entry
+#ifndef RUF_DEPTH_CULL
+#define RUF_DEPTH_CULL 1
+#endif
+constexpr bool kDepthCull = RUF_DEPTH_CULL != 0;   // raster kernel: drop units of away-facing triangles that cannot win the depth test
 constexpr int kSetupThreads = RUF_SETUP_THREADS;
 // A meshlet is the unit of work of one setup CTA: up to kMeshTris consecutive triangles of the model whose
 // bit-identical vertices were welded (at most kMeshVerts distinct ones, local indices of 10 bits) and whose
@@ -80,6 +84,8 @@ constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   /
 constexpr int kSetupFrames = RUF_SETUP_FRAMES;  // frames a setup CTA loops over with its meshlet in registers
 static_assert(kMeshVerts <= 1024 && kMeshTris <= 1023, "meshlet indices are packed in 10 bits");
 constexpr int kMaxTiles = 4096;
+constexpr int kPartStride = 8;                  // floats per part in Model::part_aabb
+constexpr int kZPad = 72;                       // zero words after the z tile (the depth-cull reads may run past its end)
 
 constexpr int kNumStages = 3;                   // pose, setup+bin, raster+filter
 constexpr uint32_t kFlagBigOverflow = 1u;
@@ -102,7 +108,8 @@ static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 constexpr size_t kRasterDynSmem = sizeof(TriRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
 
 // Per-frame counter block (uint32 words): [0] big-list entries  [1] unused  [2] flags
-// [3] kept (binned) triangles  [4 .. 4 + ntiles) records in every tile's list
+// [3] kept (binned) triangles  [4 + 2 t], [5 + 2 t]: records at the FRONT of tile t's list (triangles facing
+// the camera) and at its BACK (facing away: drawn last, depth-culled); one 8-byte word per tile
 constexpr int kCtrBig = 0, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
 
 struct Dims {
@@ -112,7 +119,7 @@ struct Dims {
   long long n_tris;
   uint32_t cap_big, cap_tile;  // capacities: big list per frame, record list per (frame, tile)
   int n_meshlets;              // setup CTAs per frame
-  int ctr_stride;              // uint32 words of one frame's counter block = kCtrWords + ntiles
+  int ctr_stride;              // uint32 words of one frame's counter block = kCtrWords + 2 * ntiles
   float halfw, halfh, guard_x, guard_y;
 };
 
@@ -132,7 +139,8 @@ struct FrameBuffers {
 
 struct Workspace {
   float *mvp;            // [frame][n_parts + 1][16]
-  uint8_t *vis;          // [frame][n_parts + 1] 0 = the part is outside the view volume in this frame
+  uint8_t *vis;          // [frame][n_parts + 1] bit 0: the part may be visible in this frame; bit 1: its triangles with
+                         // POSITIVE window area face the camera (else the negative ones do)
   uint32_t *ctr;         // [frame][ctr_stride]
   TriRec *big;           // [frame][cap_big]
   TriRec *bins;          // [frame][tile][cap_tile] one record list per tile
@@ -143,7 +151,7 @@ struct Model {
   const uint4 *meshlets;    // [n_meshlets] vert_off, tri_off, nverts | ntris << 10 | (nparts - 1) << 20, lowest part
   const float4 *verts;      // welded vertices of all meshlets: xyz, w = bits(part - meshlet's lowest part)
   const uint32_t *tris;     // local vertex indices i0 | i1 << 10 | i2 << 20
-  const float *part_aabb;   // [n_parts][6] object-space min xyz, max xyz
+  const float *part_aabb;   // [n_parts][kPartStride] object-space min xyz, max xyz, winding (+1 / -1), pad
 };
 
 // cudaSuccess iff the loaded module has an image the current device can run (sm_100a only)

@@ -128,10 +128,11 @@ __device__ __forceinline__ bool to_window(const V4 &c, float halfw, float halfh,
 }
 
 // S5/S8: orientation, pixel bbox, depth plane.  Returns false when the triangle cannot touch a pixel.
-__device__ __forceinline__ bool setup_window_tri(WV a, WV b, WV c, const Dims &d, TriRec &r)
+__device__ __forceinline__ bool setup_window_tri(WV a, WV b, WV c, const Dims &d, TriRec &r, bool *positive = nullptr)
 {
   long long area2 = (long long)(b.X - a.X) * (c.Y - a.Y) - (long long)(c.X - a.X) * (b.Y - a.Y);
   if (area2 == 0) return false;
+  if (positive) *positive = area2 > 0;
   if (area2 < 0) { WV t = b; b = c; c = t; area2 = -area2; }
 
   int xmin = min(a.X, min(b.X, c.X)), xmax = max(a.X, max(b.X, c.X));
@@ -260,7 +261,7 @@ ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view
     const int p = have ? (int)(mat % rows) : n_parts;
     uint32_t out = 0;        // bit k: this corner is beyond plane k (near, +x, -x, +y, -y)
     if (p < n_parts) {
-      const float *bb = part_aabb + 6 * (size_t)p;
+      const float *bb = part_aabb + kPartStride * (size_t)p;
       const float px = __ldg(bb + ((corner & 1) ? 3 : 0)), py = __ldg(bb + ((corner & 2) ? 4 : 1)),
                   pz = __ldg(bb + ((corner & 4) ? 5 : 2));
       const float4 *M = reinterpret_cast<const float4 *>(s_m[mi]);
@@ -278,7 +279,18 @@ ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view
 #pragma unroll
     for (int k = 0; k < 5; ++k)
       rejected |= ((__ballot_sync(0xffffffffu, (out >> k) & 1u) >> (8 * group)) & 0xffu) == 0xffu;
-    if (have && corner == 0) vis[mat] = rejected ? 0 : 1;    // the background row is never culled (out = 0)
+    if (have && corner == 0) {
+      // Which triangles face the camera?  With A = rows (x, y, w) x columns (0..2) of the MVP, the window-space
+      // doubled area of a triangle (a, b, c) has the sign of det(A) * (a - eye) . ((b - a) x (c - a)): for a mesh
+      // wound counter-clockwise seen from outside, positive area means "facing away" iff det(A) > 0.  Only a
+      // drawing-order hint for the raster kernel (front first, then the rest depth-culled).
+      const float *m = s_m[mi];
+      const float det = m[0] * (m[5] * m[11] - m[9] * m[7]) - m[4] * (m[1] * m[11] - m[9] * m[3]) +
+                        m[8] * (m[1] * m[7] - m[5] * m[3]);
+      const bool inward = (p < n_parts) && __ldg(part_aabb + kPartStride * (size_t)p + 6) < 0.0f;
+      const bool pos_is_front = (det < 0.0f) != inward;
+      vis[mat] = (uint8_t)((rejected ? 0 : 1) | (pos_is_front ? 2 : 0));    // the background row is never culled (out = 0)
+    }
   }
 }
 
@@ -341,7 +353,7 @@ __device__ __forceinline__ uint4 vertex_stage(const float4 &c0, const float4 &c1
   w.X = 0; w.Y = 0; w.z = 0.0f;
   if (need) fl |= kVfClip;
   else if (!(p.w > 0.0f) || !to_window(p, d.halfw, d.halfh, w)) fl |= kVfBadW;
-  return make_uint4((uint32_t)w.X, (uint32_t)w.Y, __float_as_uint(w.z), fl);
+  return make_uint4((uint32_t)w.X, (uint32_t)w.Y, __float_as_uint(w.z), fl);   // the caller adds the part slot << 8
 }
 
 // S5 (zero area) and the pixel bbox of S6: can the triangle touch a sample at all?
@@ -384,7 +396,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
   {
     bool any = false;
     for (int f = f0; f < f1; ++f)
-      any |= (lane <= npm1) && __ldg(vis_all + (size_t)f * rows + part_lo + lane) != 0;
+      any |= (lane <= npm1) && (__ldg(vis_all + (size_t)f * rows + part_lo + lane) & 1) != 0;
     if (!__any_sync(0xffffffffu, any)) return;
   }
   // the meshlet stays in registers for all frames of this CTA
@@ -402,7 +414,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
   }
 
   // stage the matrices of the first two frames; cull bytes -> one bit per part (every warp builds its own copy)
-  uint32_t pvis_next;
+  uint32_t pvis_next, pfront_next;
   {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -412,7 +424,8 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
       }
     }
     const uint32_t vb = (lane <= npm1) ? (uint32_t)__ldg(vis_all + (size_t)f0 * rows + part_lo + lane) : 0u;
-    pvis_next = __ballot_sync(0xffffffffu, vb != 0u);
+    pvis_next = __ballot_sync(0xffffffffu, (vb & 1u) != 0u);
+    pfront_next = __ballot_sync(0xffffffffu, (vb & 2u) != 0u);
   }
   __syncthreads();
 
@@ -421,10 +434,12 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
   for (int f = f0; f < f1; ++f) {
     const int it = f - f0, vbuf = it & 1, mbuf = it % 3;
     const uint32_t pvis_bits = pvis_next;        // bit i: part part_lo + i may be visible in frame f
+    const uint32_t pfront_bits = pfront_next;    // bit i: that part's positive-area triangles face the camera
     // prefetch the cull bytes of frame f + 1
     uint32_t vb_next = 0;
     if (f + 1 < f1 && lane <= npm1) vb_next = (uint32_t)__ldg(vis_all + (size_t)(f + 1) * rows + part_lo + lane);
-    pvis_next = __ballot_sync(0xffffffffu, vb_next != 0u);
+    pvis_next = __ballot_sync(0xffffffffu, (vb_next & 1u) != 0u);
+    pfront_next = __ballot_sync(0xffffffffu, (vb_next & 2u) != 0u);
 
     if (pvis_bits != 0) {
       // ---- P1: vertex stage, once per welded vertex ----
@@ -437,6 +452,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
           if ((pvis_bits >> (slot & 31u)) & 1u) {
             const float4 *M = reinterpret_cast<const float4 *>(&s_mvp[mbuf][16 * slot]);
             r = vertex_stage(M[0], M[1], M[2], M[3], vq[k].x, vq[k].y, vq[k].z, d);
+            r.w |= slot << 8;
           }
           s_vert[vbuf][v] = r;
         }
@@ -496,7 +512,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         const int s = s0 + lane;
         TriRec rec;
         int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
-        bool has = false;
+        bool has = false, back = false;            // back: the triangle faces away from the camera (drawing-order hint)
         if (s < nkeep) {
           const uint32_t ixs = list[s];
           const uint4 a = sv[ixs & 1023u], b = sv[(ixs >> 10) & 1023u], c = sv[ixs >> 20];
@@ -504,7 +520,9 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
           wa.X = (int)a.x; wa.Y = (int)a.y; wa.z = __uint_as_float(a.z);
           wb.X = (int)b.x; wb.Y = (int)b.y; wb.z = __uint_as_float(b.z);
           wc.X = (int)c.x; wc.Y = (int)c.y; wc.z = __uint_as_float(c.z);
-          if (setup_window_tri(wa, wb, wc, d, rec)) {
+          bool positive = false;
+          if (setup_window_tri(wa, wb, wc, d, rec, &positive)) {
+            back = positive != (((pfront_bits >> ((a.w >> 8) & 31u)) & 1u) != 0u);
             tx0 = (int)(rec.bx & 0xffffu) / kTileW; tx1 = (int)(rec.bx >> 16) / kTileW;
             ty0 = (int)(rec.by & 0xffffu) / kTileH; ty1 = (int)(rec.by >> 16) / kTileH;
             if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) push_big(rec, d, big, ctr);     // read by every tile
@@ -526,31 +544,39 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         const int ux0 = __reduce_min_sync(0xffffffffu, tx0), ux1 = __reduce_max_sync(0xffffffffu, tx1);
         const int uy0 = __reduce_min_sync(0xffffffffu, ty0), uy1 = __reduce_max_sync(0xffffffffu, ty1);
         const int un = (ux1 - ux0 + 1) * (uy1 - uy0 + 1);
+        const unsigned backmask = __ballot_sync(0xffffffffu, back);
         for (int t0 = 0, cx = ux0, cy = uy0; t0 < un; t0 += 32) {
           const int nt = min(32, un - t0);
-          uint32_t mycnt = 0;
+          uint32_t mycnt = 0;                      // lane t: front records (low half) | back records (high half) of tile t
           int mytile = 0;
           int tx = cx, ty = cy;
           for (int t = 0; t < nt; ++t) {
-            const unsigned in = __ballot_sync(0xffffffffu, tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1);
-            if (lane == t) { mycnt = (uint32_t)__popc(in); mytile = ty * d.tiles_x + tx; }
+            const bool mine = tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1;
+            const unsigned in = __ballot_sync(0xffffffffu, mine), inf = in & ~backmask, inb = in & backmask;
+            if (lane == t) { mycnt = (uint32_t)__popc(inf) | ((uint32_t)__popc(inb) << 16); mytile = ty * d.tiles_x + tx; }
             if (++tx > ux1) { tx = ux0; ++ty; }
           }
-          uint32_t mybase = 0;
+          // front records fill the tile's list from its start, back records from its end; the raster kernel
+          // flags an overflow when the two runs meet (front + back > cap_tile)
+          uint32_t basef = 0, baseb = 0;
           if (mycnt) {
-            mybase = atomicAdd(&ctr[kCtrWords + mytile], mycnt);
-            if (mybase + mycnt > d.cap_tile) atomicOr(&ctr[kCtrFlags], kFlagBinOverflow);   // the host grows cap_tile and retries
+            // the two counters of a tile are one 8-byte word: front count low, back count high (neither can carry)
+            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(ctr + kCtrWords) + mytile,
+                                                     (unsigned long long)(mycnt & 0xffffu) | ((unsigned long long)(mycnt >> 16) << 32));
+            basef = (uint32_t)old; baseb = (uint32_t)(old >> 32);
           }
           tx = cx; ty = cy;
           for (int t = 0; t < nt; ++t) {
             const bool mine = tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1;
-            const unsigned in = __ballot_sync(0xffffffffu, mine);
+            const unsigned in = __ballot_sync(0xffffffffu, mine), inf = in & ~backmask, inb = in & backmask;
             if (in) {
-              const uint32_t base = __shfl_sync(0xffffffffu, mybase, t);
+              const uint32_t bf = __shfl_sync(0xffffffffu, basef, t), bb = __shfl_sync(0xffffffffu, baseb, t);
               if (mine) {
-                const uint32_t pos = base + (uint32_t)__popc(in & lanemask_lt);
+                // position counted from the start (front) or from the end (back) of the tile's list
+                const uint32_t pos = back ? bb + (uint32_t)__popc(inb & lanemask_lt) : bf + (uint32_t)__popc(inf & lanemask_lt);
                 if (pos < d.cap_tile) {
-                  uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)(ty * d.tiles_x + tx) * d.cap_tile + pos);
+                  const size_t slot = back ? (size_t)d.cap_tile - 1 - pos : (size_t)pos;
+                  uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)(ty * d.tiles_x + tx) * d.cap_tile + slot);
                   dst[0] = q0; dst[1] = q1; dst[2] = q2;
                 }
               }
@@ -703,10 +729,12 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   TriRec (*sbuf)[kChunk] = reinterpret_cast<TriRec (*)[kChunk]>(s_raster_dyn);
   uint16_t (*s_units)[32 * kMaxUnits] =
       reinterpret_cast<uint16_t (*)[32 * kMaxUnits]>(s_raster_dyn + sizeof(TriRec) * kStages * kChunk);
-  __shared__ __align__(16) uint32_t sz[kTilePix];
+  __shared__ __align__(16) uint32_t sz[kTilePix + kZPad];
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
-  __shared__ uint32_t s_next;
+  __shared__ uint32_t s_next[2];                 // batch claim counters of the two passes
+  __shared__ uint32_t s_zblk[128];               // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
+  __shared__ float s_bigz[kRasterThreads];
   // this tile of the sensor image, fetched by cp.async at kernel entry and consumed by the fragment stage
   __shared__ __align__(16) unsigned char s_depth[kPrefetchDepth ? kTilePix * (ENC == 1 ? 2 : 4) : 16];
 
@@ -714,16 +742,35 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
   const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
   const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
-  // records binned to this tile (CTA-uniform).  Two thirds of the tiles of a typical frame see only the
-  // background quad: they take the register-only path below (no ring, no z tile, no CTA-wide barrier).
-  const uint32_t cnt = min(__ldg(ctr + kCtrWords + tile), d.cap_tile);
-  // fold this frame's overflow flags into the context's sticky status word (one thread per frame)
-  if (tile == 0 && threadIdx.x == 0) {
-    const uint32_t flags = ctr[kCtrFlags];
+  // records binned to this tile (CTA-uniform): nf at the front of its list (triangles facing the camera, drawn
+  // first), nb at the back (facing away: drawn last and depth-culled against what is already there).  Two
+  // thirds of the tiles of a typical frame see only the background quad: they take the register-only path
+  // below (no ring, no z tile, no CTA-wide barrier).
+  const uint2 nfb = __ldg(reinterpret_cast<const uint2 *>(ctr + kCtrWords) + tile);
+  uint32_t nf = nfb.x, nb = nfb.y;
+  const bool list_overflow = nf + nb > d.cap_tile;            // the two runs met: the host grows cap_tile and retries
+  nf = min(nf, d.cap_tile);
+  nb = min(nb, d.cap_tile - nf);
+  const uint32_t cnt = nf + nb;
+  // fold this frame's overflow flags into the context's sticky status word
+  if (threadIdx.x == 0) {
+    uint32_t flags = list_overflow ? kFlagBinOverflow : 0u;
+    if (tile == 0) flags |= ctr[kCtrFlags];
     if (flags) atomicOr(status, flags);
   }
   const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
   const TriRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
+  // chunk c of the virtual list "front run, then back run": at most two bulk copies into one ring stage
+  auto issue_chunk = [&](int c, int stage) {
+    const uint32_t lo = (uint32_t)c * kChunk, hi = min(lo + (uint32_t)kChunk, cnt);
+    mbar_arrive_expect_tx(&full_bar[stage], (hi - lo) * (uint32_t)sizeof(TriRec));
+    const uint32_t fhi = min(hi, nf);
+    if (lo < fhi) bulk_g2s(&sbuf[stage][0], list + lo, (fhi - lo) * (uint32_t)sizeof(TriRec), &full_bar[stage]);
+    const uint32_t blo = max(lo, nf);
+    if (blo < hi)
+      bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(TriRec),
+               &full_bar[stage]);
+  };
   if (cnt) {
     if (tid == 0) {
 #pragma unroll
@@ -732,16 +779,12 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         mbar_init(&empty_bar[s], kChunk / 32);             // one arrive per batch of 32 records
       }
       mbar_fence_init();
-      s_next = 0;
+      s_next[0] = 0; s_next[1] = 0;
 #pragma unroll
-      for (int c = 0; c < kStages; ++c) {
-        if (c < nchunks) {
-          const uint32_t lo = (uint32_t)c * kChunk, n = min((uint32_t)kChunk, cnt - lo);
-          mbar_arrive_expect_tx(&full_bar[c], n * (uint32_t)sizeof(TriRec));
-          bulk_g2s(&sbuf[c][0], list + lo, n * (uint32_t)sizeof(TriRec), &full_bar[c]);
-        }
-      }
+      for (int c = 0; c < kStages; ++c)
+        if (c < nchunks) issue_chunk(c, c);
     }
+    if (tid < kZPad) sz[kTilePix + tid] = 0u;              // the depth cull may read past the tile's last row
     __syncthreads();
   }
 
@@ -796,6 +839,10 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
               const long long mx1 = t1 + max(a1, 0LL) + max(c1, 0LL), mn1 = t1 + min(a1, 0LL) + min(c1, 0LL);
               const long long mx2 = t2 + max(a2, 0LL) + max(c2, 0LL), mn2 = t2 + min(a2, 0LL) + min(c2, 0LL);
               if ((mx0 | mx1 | mx2) >= 0) cls = ((mn0 | mn1 | mn2) >= 0) ? 1u : 2u;
+              // a covering record with a constant depth plane (the background quad: every vertex has the same
+              // window z, so both gradients are exactly 0 and z(P) = fma(0, ., fma(0, ., z0)) = z0): hand the
+              // value over instead of the record
+              if (cls == 1u && r.gx == 0.0f && r.gy == 0.0f) { cls = 3u; s_bigz[tid] = clamp_z(r.z0); }
             }
           }
           s_bigcls[tid] = (uint8_t)cls;
@@ -804,6 +851,14 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           for (uint32_t b = 0; b < nb; ++b) {
             const uint32_t c = s_bigcls[b];
             if (c == 0) continue;
+            if (c == 3) {
+              const float z = s_bigz[b];
+              if (z < 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) zr[i] = fminf(zr[i], z);
+              }
+              continue;
+            }
             const TriRec r = load_rec_global(big + b0 + b);
             const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
             if (c == 1) {
@@ -846,12 +901,36 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       // binned triangles: a chunk's records are batches of 32; warps claim batches from a shared
       // counter (a warp that drew light triangles simply takes the next batch), and a stage goes
       // back to the producer once all its batches sit in registers.
+      //
+      // Two passes over the list.  Pass 0: the batches holding the front run (triangles facing the camera).
+      // Pass 1: the back run (triangles facing away), depth-culled per record (result-neutral): after a CTA
+      // barrier the maximum of every 4x4 block of the z tile is taken once; a record whose nearest bbox sample
+      // is not in front of the block maxima under its bbox cannot change a pixel (z-tile values only ever
+      // decrease) and is dropped before any unit is dealt.  On closed meshes that is nearly all of them.
       const uint32_t nbatches = (cnt + 31u) / 32u;
+      const uint32_t nb_front = kDepthCull ? min(nbatches, (nf + 31u) / 32u) : nbatches;
+      for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t b_lo = pass ? nb_front : 0u, b_hi = pass ? nbatches : nb_front;
+      if (pass) {
+        if (b_lo >= b_hi) break;
+        __syncthreads();                      // every front record is in the z tile
+        if (tid < 128) {
+          const uint4 *row = reinterpret_cast<const uint4 *>(&sz[(tid >> 4) * 4 * kTileW + (tid & 15) * 4]);
+          uint32_t m = 0;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint4 q = row[rr * (kTileW / 4)];
+            m = max(max(m, max(q.x, q.y)), max(q.z, q.w));
+          }
+          s_zblk[tid] = m;
+        }
+        __syncthreads();
+      }
       for (;;) {
         uint32_t bt = 0;
-        if (lane == 0) bt = smem_add(smem_u32(&s_next), 1u);
+        if (lane == 0) bt = b_lo + smem_add(smem_u32(&s_next[pass]), 1u);
         bt = __shfl_sync(0xffffffffu, bt, 0);
-        if (bt >= nbatches) break;
+        if (bt >= b_hi) break;
         const int c = (int)(bt / (kChunk / 32));              // ring position of the chunk
         const int stage = c % kStages;
         mbar_wait(&full_bar[stage], ((uint32_t)c / kStages) & 1);
@@ -874,6 +953,26 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           ncb = (i1 - i0 + kUW) / kUW;                       // unit columns
           nunits = ncb * ((j1 - j0 + kUH) / kUH);
           kind = narrow ? ((nunits <= kMaxUnits) ? 1 : 2) : 3;
+          if (pass) {
+            // depth cull: z is monotone in both sample coordinates (every step is a correctly rounded fma), so
+            // its minimum over the bbox sits on a corner sample, evaluated with the rasteriser's own expressions
+            const int cx0 = (i0 - tile_x0) >> 2, cx1 = (i1 - tile_x0) >> 2, cy0 = (j0 - tile_y0) >> 2, cy1 = (j1 - tile_y0) >> 2;
+            if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 16) {
+              uint32_t zmaxb = 0;
+              for (int yy = cy0; yy <= cy1; ++yy)
+                for (int xx = cx0; xx <= cx1; ++xx) zmaxb = max(zmaxb, s_zblk[yy * 16 + xx]);
+              const float fxa = (float)(i0 * kSubpix + kSubpixHalf - r.x0), fxb = (float)(i1 * kSubpix + kSubpixHalf - r.x0);
+              const float rza = fmaf(r.gy, (float)(j0 * kSubpix + kSubpixHalf - r.y0), r.z0);
+              const float rzb = fmaf(r.gy, (float)(j1 * kSubpix + kSubpixHalf - r.y0), r.z0);
+              const uint32_t zaa = __float_as_uint(clamp_z(fmaf(r.gx, fxa, rza))), zba = __float_as_uint(clamp_z(fmaf(r.gx, fxb, rza)));
+              const uint32_t zab = __float_as_uint(clamp_z(fmaf(r.gx, fxa, rzb))), zbb = __float_as_uint(clamp_z(fmaf(r.gx, fxb, rzb)));
+              const uint32_t zmin = min(min(zaa, zba), min(zab, zbb));
+              if (zmin >= zmaxb || zmin >= 0x3f800000u) { kind = 0; nunits = 0; }
+            }
+#ifdef RUF_CULL_STATS
+            atomicAdd(const_cast<uint32_t *>(ctr) + 1, 1u | (kind == 0 ? 0x10000u : 0u));   // debug: tested | culled << 16
+#endif
+          }
           if (kind == 1) {
             const Edges e = make_edges(r);
             const int px0 = i0 * kSubpix + kSubpixHalf, py0 = j0 * kSubpix + kSubpixHalf;
@@ -902,9 +1001,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           const int cn = c + kStages;
           if ((bt % (kChunk / 32)) == (kChunk / 32) - 1 && cn < nchunks) {
             mbar_wait(&empty_bar[stage], ((uint32_t)c / kStages) & 1);
-            const uint32_t lo = (uint32_t)cn * kChunk, n = min((uint32_t)kChunk, cnt - lo);
-            mbar_arrive_expect_tx(&full_bar[stage], n * (uint32_t)sizeof(TriRec));
-            bulk_g2s(&sbuf[stage][0], list + lo, n * (uint32_t)sizeof(TriRec), &full_bar[stage]);
+            issue_chunk(cn, stage);
           }
         }
 
@@ -999,6 +1096,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           }
         }
         __syncwarp();                          // the unit table is rewritten by the next batch
+      }
       }
     }
     consumer_bar_sync();                      // every record of the tile has been rasterised

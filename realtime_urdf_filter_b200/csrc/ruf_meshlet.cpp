@@ -31,9 +31,10 @@ void build_meshlets(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tr
 {
   out = MeshletModel();
   std::vector<float> &box = out.part_aabb;
-  box.assign((size_t)(n_parts > 0 ? n_parts : 1) * 6, 0.0f);
+  box.assign((size_t)(n_parts > 0 ? n_parts : 1) * kPartStrideHost, 0.0f);
   for (int p = 0; p < n_parts; ++p)
-    for (int k = 0; k < 3; ++k) { box[6 * p + k] = 3.0e38f; box[6 * p + 3 + k] = -3.0e38f; }
+    for (int k = 0; k < 3; ++k) { box[kPartStrideHost * p + k] = 3.0e38f; box[kPartStrideHost * p + 3 + k] = -3.0e38f; }
+  std::vector<double> volume((size_t)(n_parts > 0 ? n_parts : 1), 0.0);   // 6 x signed volume of every part's mesh
   out.verts.reserve((size_t)(n_tris + 2) * 4);
   out.tris.reserve((size_t)n_tris + 2);
   std::unordered_map<VKey, uint32_t, VKeyHash> local;
@@ -85,13 +86,22 @@ void build_meshlets(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tr
       for (int k = 0; k < 3; ++k) {
         const float x = tri_xyz[9 * t + 3 * v + k];
         // NaN / inf vertices never tighten the box (such triangles are dropped by the vertex stage anyway)
-        if (x < box[6 * p + k]) box[6 * p + k] = x;
-        if (x > box[6 * p + 3 + k]) box[6 * p + 3 + k] = x;
-        if (!(x == x) || x > 3.0e38f || x < -3.0e38f) { box[6 * p + k] = -3.0e38f; box[6 * p + 3 + k] = 3.0e38f; }
+        if (x < box[kPartStrideHost * p + k]) box[kPartStrideHost * p + k] = x;
+        if (x > box[kPartStrideHost * p + 3 + k]) box[kPartStrideHost * p + 3 + k] = x;
+        if (!(x == x) || x > 3.0e38f || x < -3.0e38f) { box[kPartStrideHost * p + k] = -3.0e38f; box[kPartStrideHost * p + 3 + k] = 3.0e38f; }
       }
+    {
+      const float *q = tri_xyz + 9 * t;
+      const double ax = q[0], ay = q[1], az = q[2], bx = q[3], by = q[4], bz = q[5], cx = q[6], cy = q[7], cz = q[8];
+      volume[p] += ax * (by * cz - bz * cy) - ay * (bx * cz - bz * cx) + az * (bx * cy - by * cx);
+    }
     add_triangle(tri_xyz + 9 * t, p);
   }
   close();
+  // winding of every part: +1 when its triangles are counter-clockwise seen from outside (positive signed
+  // volume), -1 when clockwise.  Only a hint: it decides which half of a closed mesh the raster kernel draws
+  // first (the half facing the camera) so that the other half can be depth-culled; it never changes a pixel.
+  for (int p = 0; p < n_parts; ++p) box[kPartStrideHost * p + 6] = (volume[p] < 0.0) ? -1.0f : 1.0f;
   // background quad: glVertex3f(+-100, +-100, far_plane_*0.99) (src/urdf_filter.cpp:591-596) as the two
   // triangles (q0,q1,q2), (q0,q2,q3); it is drawn with MODELVIEW = LookAt, which is matrix row n_parts
   const float q[4][3] = {{-100.f, -100.f, bg_z}, {100.f, -100.f, bg_z}, {100.f, 100.f, bg_z}, {-100.f, 100.f, bg_z}};

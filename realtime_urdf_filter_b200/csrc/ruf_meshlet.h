@@ -14,11 +14,14 @@
 
 namespace ruf {
 
+constexpr int kPartStrideHost = 8;   // floats per part in MeshletModel::part_aabb (== kPartStride of ruf_device.cuh)
+
 struct MeshletModel {
   std::vector<uint32_t> hdr;     // 4 words per meshlet: vert_off, tri_off, nverts | ntris << 10 | (nparts - 1) << 20, lowest part
   std::vector<float> verts;      // 4 floats per vertex: x, y, z, bits(part - lowest part of its meshlet)
   std::vector<uint32_t> tris;    // local vertex indices i0 | i1 << 10 | i2 << 20
-  std::vector<float> part_aabb;  // 6 floats per part: object-space min xyz, max xyz (inverted when the part is empty)
+  std::vector<float> part_aabb;  // kPartStrideHost floats per part: object-space min xyz, max xyz (inverted when the part is
+                                 // empty), winding (+1 counter-clockwise seen from outside, -1 clockwise), pad
   size_t n_meshlets() const { return hdr.size() / 4; }
 };
 
