@@ -25,7 +25,7 @@ struct ruf_context {
   cudaStream_t s_in = nullptr, s_out = nullptr;       // copy streams of the host-batch pipeline
   // large device-resident batches are cut into slices that alternate between two auxiliary streams, so that
   // the (latency-bound) setup kernel of one slice overlaps the (issue-bound) raster kernel of the previous one
-  int slice_frames = 0;                               // 0 = off
+  int slice_frames = 256;                             // frames per slice (0 = never slice); RUF_SLICE_FRAMES overrides
   cudaStream_t s_aux[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 

@@ -255,3 +255,69 @@ def test_concurrent_contexts_are_independent():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def _facing_scene():
+    """Meshes that defeat every assumption of the raster kernel's drawing-order hint (front faces first, the
+    rest depth-culled): a blob wound clockwise, a mirrored blob (negative scale), an open half blob seen from
+    its inside, two interpenetrating blobs, a doubled (coplanar) blob and one lying across the near plane.  The
+    hint may only cost time -- every pixel must still match the oracle."""
+    rng = np.random.default_rng(11)
+    links = [synth.Link("world", -1, (0, 0, 0), (0, 0, 0))]
+    parts, tris, pidx = [], [], []
+    blob = lambda r, n: synth.blob_for_budget(rng, r, n)
+    m = blob((0.25, 0.2, 0.3), 3000)
+    synth.add_mesh(parts, tris, pidx, 0, m[:, [0, 1, 2, 6, 7, 8, 3, 4, 5]], off_t=(-0.7, 0.3, 1.6))      # clockwise
+    synth.add_mesh(parts, tris, pidx, 0, blob((0.25, 0.2, 0.3), 3000), scale=(-1.0, 1.0, 1.0), off_t=(0.7, 0.3, 1.6))
+    half = blob((0.4, 0.4, 0.4), 4000)
+    synth.add_mesh(parts, tris, pidx, 0, half[half[:, [2, 5, 8]].max(1) <= 0.0], off_t=(0.0, -0.4, 1.2))  # open, inside visible
+    synth.add_mesh(parts, tris, pidx, 0, blob((0.3, 0.3, 0.3), 3000), off_t=(-0.15, 0.35, 2.4))
+    synth.add_mesh(parts, tris, pidx, 0, blob((0.3, 0.3, 0.3), 3000), off_t=(0.15, 0.35, 2.5))            # interpenetrating
+    dbl = blob((0.2, 0.2, 0.2), 2000)
+    synth.add_mesh(parts, tris, pidx, 0, np.concatenate([dbl, dbl]), off_t=(0.0, 0.9, 2.0))               # coplanar twice
+    synth.add_mesh(parts, tris, pidx, 0, blob((0.3, 0.3, 0.5), 3000), off_t=(0.5, -0.5, 0.3))             # across the near plane
+    tri, tp = synth._finish(tris, pidx)
+    return synth.Scene("facing", 640, 480, synth.kinect_P(640, 480), links, parts, tri, tp, -1, (0, 0, 0), np.eye(3),
+                       label="adversarial winding / mirroring / open meshes")
+
+
+def test_depth_cull_hint_is_result_neutral_on_adversarial_meshes():
+    sc = _facing_scene()
+    for enc in ("u16", "f32"):
+        st, m = run_and_compare(sc, k=0, enc=enc)
+        assert st["visible_tris"] > 5000 and 0.02 < (m == 255).mean() < 0.9
+
+
+def test_sliced_two_stream_launch_matches_single_launch(monkeypatch):
+    """Batches of >= 512 frames are cut into slices that alternate between two streams: same bits as one launch."""
+    import torch
+    sc = synth.pr2_like_scene(160, 120, n_tris=6000, name="pr2_160x120")
+    proj, _, _ = sc.proj()
+    n = 530
+    views, pms = sc.frames([k % 40 for k in range(n)])
+    rng = np.random.default_rng(3)
+    depth = rng.integers(0, 4000, (n, sc.height, sc.width)).astype(np.uint16)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_in, d_proj, d_view, d_pm = t(depth.view(np.int16)), t(proj), t(views), t(pms)
+    outs = []
+    for slice_frames in ("256", "0"):
+        monkeypatch.setenv("RUF_SLICE_FRAMES", slice_frames)
+        d_out = torch.zeros_like(d_in)
+        d_mask = torch.zeros(d_in.shape, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        with ruf.Context(sc.width, sc.height) as ctx:
+            ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+            ctx.filter_batch_device(n, d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                                    sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
+            ctx.sync()
+            launches = ctx.stats()["kernel_launches"]
+        outs.append((d_out.cpu().numpy().view(np.uint16), d_mask.cpu().numpy(), launches))
+    assert outs[0][2] == 9 and outs[1][2] == 3          # 3 slices x 3 kernels vs one launch sequence
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    # and a few frames against the oracle
+    for k in (0, 255, 256, 529):
+        want_d, want_m, _ = orc.filter_frame(depth[k], sc.tri, sc.tri_part, helpers.oracle_mvp(sc, views[k], pms[k]),
+                                             np.float32(synth.Z_NEAR), np.float32(synth.Z_FAR), np.float32(sc.max_diff),
+                                             np.float32(sc.replace_value))
+        assert np.array_equal(outs[0][0][k], want_d) and np.array_equal(outs[0][1][k], want_m)
