@@ -65,10 +65,12 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #ifndef RUF_RASTER_MIN_BLOCKS
 #define RUF_RASTER_MIN_BLOCKS 5
 #endif
-#ifndef RUF_PREFETCH_DEPTH
-#define RUF_PREFETCH_DEPTH 0
+#ifndef RUF_EARLY_SENSOR
+#define RUF_EARLY_SENSOR 0
 #endif
-constexpr bool kPrefetchDepth = RUF_PREFETCH_DEPTH != 0;   // raster kernel: cp.async the tile's sensor pixels at kernel entry
+#ifndef RUF_MIN_BACK_BATCHES
+#define RUF_MIN_BACK_BATCHES 6u
+#endif
 #ifndef RUF_DEPTH_CULL
 #define RUF_DEPTH_CULL 1
 #endif

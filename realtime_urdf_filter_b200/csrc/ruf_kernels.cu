@@ -735,8 +735,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ uint32_t s_zblk[128];               // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
   __shared__ float s_bigz[kRasterThreads];
-  // this tile of the sensor image, fetched by cp.async at kernel entry and consumed by the fragment stage
-  __shared__ __align__(16) unsigned char s_depth[kPrefetchDepth ? kTilePix * (ENC == 1 ? 2 : 4) : 16];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
@@ -791,20 +789,26 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   const int prow = tid >> 3, pcol = (tid & 7) * 8;
 
   // ===== consumer warps =====
-  // every thread shades 8 consecutive pixels of one tile row at the end; their sensor values start their
-  // way from HBM now (cp.async into shared memory: no registers held, nobody else reads them)
+  // every thread shades 8 consecutive pixels of one tile row at the end.  Their sensor values are requested
+  // early -- before the big list in tiles without records, before the last barrier otherwise -- so that the
+  // HBM latency is covered by work that does not need many registers.
   const int gy = tile_y0 + prow, gx = tile_x0 + pcol;
   const size_t pix = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
   const bool full = fb.vec_ok && gy < d.H && (gx + 8 <= d.W);
-  unsigned char *my_depth = s_depth + (size_t)(prow * kTileW + pcol) * (ENC == 1 ? 2 : 4);
-  if (full && kPrefetchDepth) {
-    if (ENC == 1) {
-      cp_async16(my_depth, static_cast<const uint16_t *>(fb.depth_in) + pix);
-    } else {
-      cp_async16(my_depth, static_cast<const float *>(fb.depth_in) + pix);
-      cp_async16(my_depth + 16, static_cast<const float *>(fb.depth_in) + pix + 4);
+  uint4 sens0 = make_uint4(0u, 0u, 0u, 0u), sens1 = make_uint4(0u, 0u, 0u, 0u);
+  auto load_sensor = [&]() {
+    if (full) {
+      if (ENC == 1) {
+        sens0 = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + pix));
+      } else {
+        const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + pix);
+        sens0 = __ldg(p); sens1 = __ldg(p + 1);
+      }
     }
-  }
+  };
+#if RUF_EARLY_SENSOR
+  if (cnt == 0) load_sensor();
+#endif
   float zr[8];                                  // this thread's 8 pixels of the z tile
   {
     {
@@ -908,7 +912,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       // is not in front of the block maxima under its bbox cannot change a pixel (z-tile values only ever
       // decrease) and is dropped before any unit is dealt.  On closed meshes that is nearly all of them.
       const uint32_t nbatches = (cnt + 31u) / 32u;
-      const uint32_t nb_front = kDepthCull ? min(nbatches, (nf + 31u) / 32u) : nbatches;
+      uint32_t nb_front = kDepthCull ? min(nbatches, (nf + 31u) / 32u) : nbatches;
+      if (nbatches - nb_front < RUF_MIN_BACK_BATCHES) nb_front = nbatches;   // a second pass (two barriers) must pay for itself
       for (int pass = 0; pass < 2; ++pass) {
       const uint32_t b_lo = pass ? nb_front : 0u, b_hi = pass ? nbatches : nb_front;
       if (pass) {
@@ -1099,6 +1104,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
       }
     }
+#if RUF_EARLY_SENSOR
+    load_sensor();
+#endif
     consumer_bar_sync();                      // every record of the tile has been rasterised
     const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol]);
     const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol + 4]);
@@ -1112,23 +1120,27 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   const size_t base = pix;
   const float (&zw)[8] = zr;
   if (full) {
-    if (kPrefetchDepth) cp_async_wait_all();    // this thread's own copies: no barrier needed
-    // to_linear_depth (frag:14-17,22) once per distinct z of this thread's run: background pixels
-    // share one window z, so most threads divide once instead of eight times
-    float virt[8];
+#if !RUF_EARLY_SENSOR
+    load_sensor();
+#endif
+    // to_linear_depth (frag:14-17,22) and the threshold (frag:23) once per distinct z of this thread's run:
+    // background pixels share one window z, so most threads divide once instead of eight times.  Never-drawn
+    // pixels (z = 1: clear colour, :566) get +inf, so that `sensor > thr` is false for them.
+    float thr[8];
     {
-      float zprev = 1.0f, vprev = 0.0f;
+      float zprev = 1.0f, tprev = __int_as_float(0x7f800000);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (zw[i] != zprev) { vprev = sp.k1 / (zw[i] - sp.k2); zprev = zw[i]; }
-        virt[i] = vprev;                       // unused where zw == 1 (never drawn)
+        if (zw[i] != zprev) {
+          tprev = (zw[i] == 1.0f) ? __int_as_float(0x7f800000) : (sp.k1 / (zw[i] - sp.k2)) - sp.max_diff;
+          zprev = zw[i];
+        }
+        thr[i] = tprev;
       }
     }
     uint32_t om[8];
     if (ENC == 1) {
-      const uint4 q = kPrefetchDepth ? *reinterpret_cast<const uint4 *>(my_depth)
-                                     : __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + base));
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      const uint32_t w[4] = {sens0.x, sens0.y, sens0.z, sens0.w};
       const uint32_t repl = f32_to_u16(sp.replace_value);       // convertTo(CV_16U, 1000) of the replaced pixels, :311
       uint32_t u[8];
 #pragma unroll
@@ -1136,7 +1148,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         const uint32_t raw = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
         const float sensor = (float)raw * 0.001f;               // convertTo(CV_32F, 0.001), :288
         const bool drawn = zw[i] != 1.0f;                       // else clear colour: depth 0, mask 0 (:566)
-        const bool sflt = drawn && (sensor > (virt[i] - sp.max_diff));   // frag:23
+        const bool sflt = sensor > thr[i];                      // frag:23
         // an unfiltered pixel is sat_u16(rint((u * 0.001f) * 1000.f)), which is u itself for every
         // 16-bit u (exhaustively checked: tests/test_oracle_encodings.py::test_u16_roundtrip_identity_all_65536)
         u[i] = drawn ? (sflt ? repl : raw) : 0u;
@@ -1146,15 +1158,14 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       o.x = u[0] | (u[1] << 16); o.y = u[2] | (u[3] << 16); o.z = u[4] | (u[5] << 16); o.w = u[6] | (u[7] << 16);
       *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
     } else {
-      const float4 *p = kPrefetchDepth ? reinterpret_cast<const float4 *>(my_depth)
-                                       : reinterpret_cast<const float4 *>(static_cast<const float *>(fb.depth_in) + base);
-      const float4 q0 = p[0], q1 = p[1];
-      const float sensor[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      const float sensor[8] = {__uint_as_float(sens0.x), __uint_as_float(sens0.y), __uint_as_float(sens0.z),
+                               __uint_as_float(sens0.w), __uint_as_float(sens1.x), __uint_as_float(sens1.y),
+                               __uint_as_float(sens1.z), __uint_as_float(sens1.w)};
       float od[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const bool drawn = zw[i] != 1.0f;
-        const bool sflt = drawn && (sensor[i] > (virt[i] - sp.max_diff));
+        const bool sflt = sensor[i] > thr[i];
         od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
         om[i] = sflt ? 255u : 0u;
       }
