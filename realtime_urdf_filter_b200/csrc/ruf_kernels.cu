@@ -769,6 +769,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(TriRec),
                &full_bar[stage]);
   };
+  const int prow = tid >> 3, pcol = (tid & 7) * 8;
   if (cnt) {
     if (tid == 0) {
 #pragma unroll
@@ -782,13 +783,15 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       for (int c = 0; c < kStages; ++c)
         if (c < nchunks) issue_chunk(c, c);
     }
+    // the z tile starts at the cleared depth (glClear, 1.0); the per-frame big list (background quad, walls,
+    // clipped triangles) is merged in at the end on registers -- min is associative, the result is the same
+    uint4 *zp = reinterpret_cast<uint4 *>(&sz[prow * kTileW + pcol]);
+    zp[0] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+    zp[1] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
     if (tid < kZPad) sz[kTilePix + tid] = 0u;              // the depth cull may read past the tile's last row
-    __syncthreads();
   }
 
-  const int prow = tid >> 3, pcol = (tid & 7) * 8;
-
-  // ===== consumer warps =====
+  // ===== all warps =====
   // every thread shades 8 consecutive pixels of one tile row at the end.  Their sensor values are requested
   // early -- before the big list in tiles without records, before the last barrier otherwise -- so that the
   // HBM latency is covered by work that does not need many registers.
@@ -809,99 +812,45 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
 #if RUF_EARLY_SENSOR
   if (cnt == 0) load_sensor();
 #endif
-  float zr[8];                                  // this thread's 8 pixels of the z tile
-  {
-    {
-      {
-        // big list: pixel-parallel, every thread owns 8 consecutive pixels of one tile row
-#pragma unroll
-        for (int i = 0; i < 8; ++i) zr[i] = 1.0f;       // glClear depth
-        const uint32_t nbig = min(ctr[kCtrBig], d.cap_big);
-        const TriRec *big = big_all + (size_t)frame * d.cap_big;
-        const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
-        const int py = (tile_y0 + prow) * kSubpix + kSubpixHalf;
-        const int tpx = tile_x0 * kSubpix + kSubpixHalf, tpy = tile_y0 * kSubpix + kSubpixHalf;
-        for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
-          // classify 256 records in parallel (one per thread; a typical frame has just the two triangles of
-          // the background quad, so only warp 0 does any work here): 0 = no sample of this tile can be
-          // covered, 1 = every sample is covered, 2 = mixed.  Edge values are linear over the tile's
-          // sample grid, so their min / max sit on its corners.
-          uint32_t cls = 0;
-          if (b0 + tid < nbig) {
-            const TriRec r = load_rec_global(big + b0 + tid);
-            const int bi0 = (int)(r.bx & 0xffffu), bi1 = (int)(r.bx >> 16);
-            const int bj0 = (int)(r.by & 0xffffu), bj1 = (int)(r.by >> 16);
-            if (!(bi1 < tile_x0 || bi0 >= tile_x0 + kTileW || bj1 < tile_y0 || bj0 >= tile_y0 + kTileH)) {
-              const Edges e = make_edges(r);
-              const long long spanx = (long long)(kTileW - 1) * kSubpix, spany = (long long)(kTileH - 1) * kSubpix;
-              const long long t0 = (long long)e.A0 * (tpx - r.x0) + (long long)e.B0 * (tpy - r.y0) + e.bias0;
-              const long long t1 = (long long)e.A1 * (tpx - r.x1) + (long long)e.B1 * (tpy - r.y1) + e.bias1;
-              const long long t2 = (long long)e.A2 * (tpx - r.x2) + (long long)e.B2 * (tpy - r.y2) + e.bias2;
-              const long long a0 = e.A0 * spanx, c0 = e.B0 * spany, a1 = e.A1 * spanx, c1 = e.B1 * spany,
-                              a2 = e.A2 * spanx, c2 = e.B2 * spany;
-              const long long mx0 = t0 + max(a0, 0LL) + max(c0, 0LL), mn0 = t0 + min(a0, 0LL) + min(c0, 0LL);
-              const long long mx1 = t1 + max(a1, 0LL) + max(c1, 0LL), mn1 = t1 + min(a1, 0LL) + min(c1, 0LL);
-              const long long mx2 = t2 + max(a2, 0LL) + max(c2, 0LL), mn2 = t2 + min(a2, 0LL) + min(c2, 0LL);
-              if ((mx0 | mx1 | mx2) >= 0) cls = ((mn0 | mn1 | mn2) >= 0) ? 1u : 2u;
-              // a covering record with a constant depth plane (the background quad: every vertex has the same
-              // window z, so both gradients are exactly 0 and z(P) = fma(0, ., fma(0, ., z0)) = z0): hand the
-              // value over instead of the record
-              if (cls == 1u && r.gx == 0.0f && r.gy == 0.0f) { cls = 3u; s_bigz[tid] = clamp_z(r.z0); }
-            }
-          }
-          s_bigcls[tid] = (uint8_t)cls;
-          consumer_bar_sync();
-          const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
-          for (uint32_t b = 0; b < nb; ++b) {
-            const uint32_t c = s_bigcls[b];
-            if (c == 0) continue;
-            if (c == 3) {
-              const float z = s_bigz[b];
-              if (z < 1.0f) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) zr[i] = fminf(zr[i], z);
-              }
-              continue;
-            }
-            const TriRec r = load_rec_global(big + b0 + b);
-            const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
-            if (c == 1) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-                if (z < 1.0f) zr[i] = fminf(zr[i], z);
-              }
-              continue;
-            }
-            const Edges e = make_edges(r);
-            long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
-            long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
-            long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
-            const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix,
-                            s2 = (long long)e.A2 * kSubpix;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if ((e0 | e1 | e2) >= 0) {
-                float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-                if (z < 1.0f) zr[i] = fminf(zr[i], z);
-              }
-              e0 += s0; e1 += s1; e2 += s2;
-            }
-          }
-          if (b0 + kRasterThreads < nbig) consumer_bar_sync();   // s_bigcls is rewritten next round
-        }
+  // ---- per-frame big list, part 1: classify its first 256 records against this tile (one per thread; a
+  // typical frame has just the two triangles of the background quad, so only warp 0 does any work here):
+  // 0 = no sample of this tile can be covered, 1 = every sample is covered, 2 = mixed, 3 = covered with a
+  // constant depth.  Edge values are linear over the tile's sample grid, so their min / max sit on its corners.
+  const uint32_t nbig = min(ctr[kCtrBig], d.cap_big);
+  const TriRec *big = big_all + (size_t)frame * d.cap_big;
+  const int tpx = tile_x0 * kSubpix + kSubpixHalf, tpy = tile_y0 * kSubpix + kSubpixHalf;
+  auto classify = [&](uint32_t b0) {
+    uint32_t cls = 0;
+    if (b0 + tid < nbig) {
+      const TriRec r = load_rec_global(big + b0 + tid);
+      const int bi0 = (int)(r.bx & 0xffffu), bi1 = (int)(r.bx >> 16);
+      const int bj0 = (int)(r.by & 0xffffu), bj1 = (int)(r.by >> 16);
+      if (!(bi1 < tile_x0 || bi0 >= tile_x0 + kTileW || bj1 < tile_y0 || bj0 >= tile_y0 + kTileH)) {
+        const Edges e = make_edges(r);
+        const long long spanx = (long long)(kTileW - 1) * kSubpix, spany = (long long)(kTileH - 1) * kSubpix;
+        const long long t0 = (long long)e.A0 * (tpx - r.x0) + (long long)e.B0 * (tpy - r.y0) + e.bias0;
+        const long long t1 = (long long)e.A1 * (tpx - r.x1) + (long long)e.B1 * (tpy - r.y1) + e.bias1;
+        const long long t2 = (long long)e.A2 * (tpx - r.x2) + (long long)e.B2 * (tpy - r.y2) + e.bias2;
+        const long long a0 = e.A0 * spanx, c0 = e.B0 * spany, a1 = e.A1 * spanx, c1 = e.B1 * spany,
+                        a2 = e.A2 * spanx, c2 = e.B2 * spany;
+        const long long mx0 = t0 + max(a0, 0LL) + max(c0, 0LL), mn0 = t0 + min(a0, 0LL) + min(c0, 0LL);
+        const long long mx1 = t1 + max(a1, 0LL) + max(c1, 0LL), mn1 = t1 + min(a1, 0LL) + min(c1, 0LL);
+        const long long mx2 = t2 + max(a2, 0LL) + max(c2, 0LL), mn2 = t2 + min(a2, 0LL) + min(c2, 0LL);
+        if ((mx0 | mx1 | mx2) >= 0) cls = ((mn0 | mn1 | mn2) >= 0) ? 1u : 2u;
+        // a covering record with a constant depth plane (the background quad: every vertex has the same
+        // window z, so both gradients are exactly 0 and z(P) = fma(0, ., fma(0, ., z0)) = z0): hand the
+        // value over instead of the record
+        if (cls == 1u && r.gx == 0.0f && r.gy == 0.0f) { cls = 3u; s_bigz[tid] = clamp_z(r.z0); }
       }
     }
-  }
+    s_bigcls[tid] = (uint8_t)cls;
+  };
+  classify(0);
+  __syncthreads();          // the classification, the cleared z tile and the ring's barriers are visible
+
+  float zr[8];                                  // this thread's 8 pixels of the z tile
   if (cnt) {
     {
-      {
-        uint4 *zp = reinterpret_cast<uint4 *>(&sz[prow * kTileW + pcol]);
-        zp[0] = make_uint4(__float_as_uint(zr[0]), __float_as_uint(zr[1]), __float_as_uint(zr[2]), __float_as_uint(zr[3]));
-        zp[1] = make_uint4(__float_as_uint(zr[4]), __float_as_uint(zr[5]), __float_as_uint(zr[6]), __float_as_uint(zr[7]));
-        consumer_bar_sync();                  // the z tile is initialised for all consumer warps
-      }
-
       // binned triangles: a chunk's records are batches of 32; warps claim batches from a shared
       // counter (a warp that drew light triangles simply takes the next batch), and a stage goes
       // back to the producer once all its batches sit in registers.
@@ -1113,6 +1062,58 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     zr[0] = __uint_as_float(zq0.x); zr[1] = __uint_as_float(zq0.y); zr[2] = __uint_as_float(zq0.z);
     zr[3] = __uint_as_float(zq0.w); zr[4] = __uint_as_float(zq1.x); zr[5] = __uint_as_float(zq1.y);
     zr[6] = __uint_as_float(zq1.z); zr[7] = __uint_as_float(zq1.w);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) zr[i] = 1.0f;       // glClear depth
+  }
+
+  // ---- per-frame big list, part 2: pixel-parallel on registers, every thread owns 8 consecutive pixels ----
+  {
+    const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
+    const int py = (tile_y0 + prow) * kSubpix + kSubpixHalf;
+    for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
+      if (b0) {                                   // more than 256 records (clipping-heavy views): classify the next round
+        __syncthreads();
+        classify(b0);
+        __syncthreads();
+      }
+      const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
+      for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t c = s_bigcls[b];
+        if (c == 0) continue;
+        if (c == 3) {
+          const float z = s_bigz[b];
+          if (z < 1.0f) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zr[i] = fminf(zr[i], z);
+          }
+          continue;
+        }
+        const TriRec r = load_rec_global(big + b0 + b);
+        const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
+        if (c == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+            if (z < 1.0f) zr[i] = fminf(zr[i], z);
+          }
+          continue;
+        }
+        const Edges e = make_edges(r);
+        long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
+        long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
+        long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
+        const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix, s2 = (long long)e.A2 * kSubpix;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if ((e0 | e1 | e2) >= 0) {
+            float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+            if (z < 1.0f) zr[i] = fminf(zr[i], z);
+          }
+          e0 += s0; e1 += s1; e2 += s2;
+        }
+      }
+    }
   }
 
   // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
