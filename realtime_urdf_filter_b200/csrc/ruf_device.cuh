@@ -65,6 +65,9 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #ifndef RUF_RASTER_MIN_BLOCKS
 #define RUF_RASTER_MIN_BLOCKS 5
 #endif
+#ifndef RUF_WALK
+#define RUF_WALK 2
+#endif
 #ifndef RUF_EARLY_SENSOR
 #define RUF_EARLY_SENSOR 0
 #endif

@@ -535,55 +535,61 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, (uint32_t)rec.x1, (uint32_t)rec.y1);
         const uint4 q1 = make_uint4((uint32_t)rec.x2, (uint32_t)rec.y2, __float_as_uint(rec.z0), __float_as_uint(rec.gx));
         const uint4 q2 = make_uint4(__float_as_uint(rec.gy), rec.bx, rec.by, 0u);
-        // P4.  The round's records fall into a few tiles (consecutive triangles of a mesh).  The warp walks the
-        // union rectangle of the lanes' tile ranges twice: pass 1 counts the records of every tile (one ballot
-        // each) and parks the count in the lane with the tile's ordinal; ALL reservations are then issued at
-        // once (one global atomic per touched tile, their latencies overlap); pass 2 hands the bases out and
-        // the lanes write their records.
-        if (!has) { tx0 = 0x7fff; ty0 = 0x7fff; tx1 = -1; ty1 = -1; }
-        const int ux0 = __reduce_min_sync(0xffffffffu, tx0), ux1 = __reduce_max_sync(0xffffffffu, tx1);
-        const int uy0 = __reduce_min_sync(0xffffffffu, ty0), uy1 = __reduce_max_sync(0xffffffffu, ty1);
-        const int un = (ux1 - ux0 + 1) * (uy1 - uy0 + 1);
+        // P4.  Every lane walks the tiles of its bbox (1 for three quarters of the records, 2 or 4 for most of
+        // the rest); lanes that stand on the same tile in the same step (match.any) share ONE 8-byte global
+        // atomic that reserves room in that tile's list: front count in the low word, back count in the high
+        // word.  Front records fill the list from its start, back records from its end; the raster kernel flags
+        // an overflow when the two runs meet.  The first kWalk steps are unrolled so that their atomics are in
+        // flight together; the bases are consumed afterwards.
         const unsigned backmask = __ballot_sync(0xffffffffu, back);
-        for (int t0 = 0, cx = ux0, cy = uy0; t0 < un; t0 += 32) {
-          const int nt = min(32, un - t0);
-          uint32_t mycnt = 0;                      // lane t: front records (low half) | back records (high half) of tile t
-          int mytile = 0;
-          int tx = cx, ty = cy;
-          for (int t = 0; t < nt; ++t) {
-            const bool mine = tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1;
-            const unsigned in = __ballot_sync(0xffffffffu, mine), inf = in & ~backmask, inb = in & backmask;
-            if (lane == t) { mycnt = (uint32_t)__popc(inf) | ((uint32_t)__popc(inb) << 16); mytile = ty * d.tiles_x + tx; }
-            if (++tx > ux1) { tx = ux0; ++ty; }
+        unsigned long long *tile_ctr = reinterpret_cast<unsigned long long *>(ctr + kCtrWords);
+        auto put = [&](int tile, unsigned grp, unsigned long long base) {
+          const uint32_t pos = back ? (uint32_t)(base >> 32) + (uint32_t)__popc(grp & backmask & lanemask_lt)
+                                    : (uint32_t)base + (uint32_t)__popc(grp & ~backmask & lanemask_lt);
+          if (pos < d.cap_tile) {
+            const size_t slot = back ? (size_t)d.cap_tile - 1 - pos : (size_t)pos;
+            uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)tile * d.cap_tile + slot);
+            dst[0] = q0; dst[1] = q1; dst[2] = q2;
           }
-          // front records fill the tile's list from its start, back records from its end; the raster kernel
-          // flags an overflow when the two runs meet (front + back > cap_tile)
-          uint32_t basef = 0, baseb = 0;
-          if (mycnt) {
-            // the two counters of a tile are one 8-byte word: front count low, back count high (neither can carry)
-            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(ctr + kCtrWords) + mytile,
-                                                     (unsigned long long)(mycnt & 0xffffu) | ((unsigned long long)(mycnt >> 16) << 32));
-            basef = (uint32_t)old; baseb = (uint32_t)(old >> 32);
+        };
+        constexpr int kWalk = RUF_WALK;
+        int tx = tx0, ty = ty0;
+        bool more = has;
+        int tl[kWalk];
+        unsigned grp[kWalk];
+        unsigned long long base[kWalk];
+        bool on[kWalk];
+#pragma unroll
+        for (int k = 0; k < kWalk; ++k) {
+          on[k] = more;
+          tl[k] = more ? ty * d.tiles_x + tx : -1 - lane;
+          grp[k] = __match_any_sync(0xffffffffu, tl[k]);
+          base[k] = 0;
+          if (more && lane == __ffs(grp[k]) - 1)
+            base[k] = atomicAdd(tile_ctr + tl[k], (unsigned long long)__popc(grp[k] & ~backmask) |
+                                                      ((unsigned long long)__popc(grp[k] & backmask) << 32));
+          if (more) {
+            if (++tx > tx1) { tx = tx0; ++ty; }
+            more = ty <= ty1;
           }
-          tx = cx; ty = cy;
-          for (int t = 0; t < nt; ++t) {
-            const bool mine = tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1;
-            const unsigned in = __ballot_sync(0xffffffffu, mine), inf = in & ~backmask, inb = in & backmask;
-            if (in) {
-              const uint32_t bf = __shfl_sync(0xffffffffu, basef, t), bb = __shfl_sync(0xffffffffu, baseb, t);
-              if (mine) {
-                // position counted from the start (front) or from the end (back) of the tile's list
-                const uint32_t pos = back ? bb + (uint32_t)__popc(inb & lanemask_lt) : bf + (uint32_t)__popc(inf & lanemask_lt);
-                if (pos < d.cap_tile) {
-                  const size_t slot = back ? (size_t)d.cap_tile - 1 - pos : (size_t)pos;
-                  uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)(ty * d.tiles_x + tx) * d.cap_tile + slot);
-                  dst[0] = q0; dst[1] = q1; dst[2] = q2;
-                }
-              }
-            }
-            if (++tx > ux1) { tx = ux0; ++ty; }
+        }
+#pragma unroll
+        for (int k = 0; k < kWalk; ++k) {
+          const unsigned long long b = __shfl_sync(0xffffffffu, base[k], __ffs(grp[k]) - 1);
+          if (on[k]) put(tl[k], grp[k], b);
+        }
+        while (__ballot_sync(0xffffffffu, more)) {      // records that touch more than kWalk tiles
+          const int tile = more ? ty * d.tiles_x + tx : -1 - lane;
+          const unsigned g = __match_any_sync(0xffffffffu, tile);
+          unsigned long long b = 0;
+          if (more && lane == __ffs(g) - 1)
+            b = atomicAdd(tile_ctr + tile, (unsigned long long)__popc(g & ~backmask) | ((unsigned long long)__popc(g & backmask) << 32));
+          b = __shfl_sync(0xffffffffu, b, __ffs(g) - 1);
+          if (more) {
+            put(tile, g, b);
+            if (++tx > tx1) { tx = tx0; ++ty; }
+            more = ty <= ty1;
           }
-          cx = tx; cy = ty;
         }
       }
       __syncwarp();                                // the warp's list is rewritten in the next frame
