@@ -1,4 +1,5 @@
-import sys
+import os, sys
+os.environ["RUF_SETUP_FRAMES_FORCE"] = "2"      # exercise the frame loop of the setup kernel
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np
 import helpers, realtime_urdf_filter_b200 as ruf
@@ -20,3 +21,21 @@ with ruf.Context(100, 75) as ctx:
     ctx.reserve(1, 2, 64)
     d, m = ctx.filter(fr["depth"], proj, fr["view"], fr["pm"], sc.max_diff, sc.replace_value)
 print("odd ok")
+# a 5-frame device batch through the frame loop (runs of 2, 2, 1) and the two-pass raster (depth cull)
+import torch
+sc = helpers.scene("pr2_small"); proj, _, _ = sc.proj()
+frames = [helpers.make_frame(sc, k, "u16") for k in (0, 5, 9, 14, 21)]
+dev = torch.device("cuda:0"); t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+d_in = t(np.stack([f["depth"] for f in frames]).view(np.int16)); d_out = torch.empty_like(d_in)
+d_mask = torch.empty(d_in.shape, dtype=torch.uint8, device=dev)
+d_proj, d_view, d_pm = t(proj), t(np.stack([f["view"] for f in frames])), t(np.stack([f["pm"] for f in frames]))
+torch.cuda.synchronize()
+with ruf.Context(sc.width, sc.height) as ctx:
+    ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+    ctx.filter_batch_device(5, d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                            sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
+    ctx.sync()
+for i, fr in enumerate(frames):
+    want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+    assert np.array_equal(d_out[i].cpu().numpy().view(np.uint16), want_d) and np.array_equal(d_mask[i].cpu().numpy(), want_m)
+print("batch ok")

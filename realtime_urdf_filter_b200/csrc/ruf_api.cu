@@ -280,6 +280,10 @@ int ruf_create(ruf_context **out, int device, int width, int height, double z_ne
   if ((e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   c->stream = c->own_stream;
+  if (const char *e3 = getenv("RUF_SETUP_FRAMES_FORCE")) {   // testing aid: frames per setup CTA
+    const int v = atoi(e3);
+    if (v >= 1 && v <= 64) c->dims.force_fpc = v;
+  }
   if (const char *e2 = getenv("RUF_SLICE_FRAMES")) {    // tuning aid
     const int v = atoi(e2);
     if (v >= 0 && v <= 65535) c->slice_frames = v;

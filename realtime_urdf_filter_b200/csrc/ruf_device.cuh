@@ -125,6 +125,7 @@ struct Dims {
   uint32_t cap_big, cap_tile;  // capacities: big list per frame, record list per (frame, tile)
   int n_meshlets;              // setup CTAs per frame
   int ctr_stride;              // uint32 words of one frame's counter block = kCtrWords + 2 * ntiles
+  int force_fpc;               // > 0: frames per setup CTA (testing aid, RUF_SETUP_FRAMES_FORCE); 0 = heuristic
   float halfw, halfh, guard_x, guard_y;
 };
 

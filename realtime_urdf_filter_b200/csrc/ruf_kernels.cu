@@ -1421,6 +1421,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     // (about a dozen waves of 148 SMs x 6 CTAs keep the tail of the launch short: measured)
     int fpc = kSetupFrames;
     while (fpc > 1 && (long long)d.n_meshlets * ((n_frames + fpc - 1) / fpc) < 12000) fpc >>= 1;
+    if (d.force_fpc > 0) fpc = d.force_fpc;
     dim3 grid((unsigned)d.n_meshlets, (unsigned)((n_frames + fpc - 1) / fpc));
     ruf_setup_bin_kernel<<<grid, kSetupThreads, 0, s>>>(m, ws.mvp, ws.vis, d, n_frames, fpc, ws.big, ws.bins, ws.ctr);
     ++launches;

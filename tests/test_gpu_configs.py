@@ -321,3 +321,34 @@ def test_sliced_two_stream_launch_matches_single_launch(monkeypatch):
                                              np.float32(synth.Z_NEAR), np.float32(synth.Z_FAR), np.float32(sc.max_diff),
                                              np.float32(sc.replace_value))
         assert np.array_equal(outs[0][0][k], want_d) and np.array_equal(outs[0][1][k], want_m)
+
+
+@pytest.mark.parametrize("fpc", ["1", "4", "3"])
+def test_setup_frame_runs_match_the_oracle_frame_by_frame(monkeypatch, fpc):
+    """A setup CTA keeps its meshlet in registers over a run of frames (matrices staged two frames ahead, one
+    barrier per frame): force runs of 1 / 4 / 3 frames over a 10-frame batch with moving joints (parts enter and
+    leave the view volume between frames) and compare every frame with the oracle."""
+    import torch
+    monkeypatch.setenv("RUF_SETUP_FRAMES_FORCE", fpc)
+    sc = helpers.scene("pr2")
+    proj, _, _ = sc.proj()
+    ks = [0, 3, 7, 11, 17, 19, 23, 31, 40, 47]
+    frames = [helpers.make_frame(sc, k, "u16", nthreads=8) for k in ks]
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_in = t(np.stack([f["depth"] for f in frames]).view(np.int16))
+    d_out = torch.empty_like(d_in)
+    d_mask = torch.empty(d_in.shape, dtype=torch.uint8, device=dev)
+    d_z = torch.empty(d_in.shape, dtype=torch.float32, device=dev)
+    d_proj, d_view, d_pm = t(proj), t(np.stack([f["view"] for f in frames])), t(np.stack([f["pm"] for f in frames]))
+    torch.cuda.synchronize()
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        ctx.filter_batch_device(len(ks), d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                                sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), d_z.data_ptr())
+        ctx.sync()
+    out, mask, z = d_out.cpu().numpy().view(np.uint16), d_mask.cpu().numpy(), d_z.cpu().numpy()
+    for i, fr in enumerate(frames):
+        want_d, want_m, want_z = helpers.oracle_filter(sc, fr, nthreads=8)
+        assert np.array_equal(z[i].view(np.uint32), want_z.view(np.uint32)), f"frame {i}: z-buffer differs"
+        assert np.array_equal(out[i], want_d) and np.array_equal(mask[i], want_m), f"frame {i}"
