@@ -409,7 +409,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="frames per launch sequence")
+    ap.add_argument("--batch", type=int, default=1024, help="frames per launch sequence")
     ap.add_argument("--ring", type=int, default=2, help="launch sequences (distinct buffers) per step")
     ap.add_argument("--e2e-frames", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

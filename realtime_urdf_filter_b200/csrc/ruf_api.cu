@@ -23,9 +23,11 @@ struct ruf_context {
 
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;       // copy streams of the host-batch pipeline
-  // large device-resident batches are cut into slices that alternate between two auxiliary streams, so that
-  // the (latency-bound) setup kernel of one slice overlaps the (issue-bound) raster kernel of the previous one
-  int slice_frames = 256;                             // frames per slice (0 = never slice); RUF_SLICE_FRAMES overrides
+  // optional (RUF_SLICE_FRAMES=n): device-resident batches of >= 2n frames are cut into slices that alternate
+  // between two auxiliary streams, so that the setup kernel of one slice overlaps the raster kernel of the
+  // previous one.  Off by default: with the current kernels it no longer pays (profiles/r01_experiments.md),
+  // and kernel-replay profilers serialise the two streams.
+  int slice_frames = 0;
   cudaStream_t s_aux[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
