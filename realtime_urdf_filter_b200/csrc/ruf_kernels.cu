@@ -13,6 +13,8 @@
 // nvcc neither contracts nor reorders; divisions are IEEE (-prec-div=true is the default).
 #include "ruf_device.cuh"
 
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 namespace ruf {
@@ -738,6 +740,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ __align__(16) uint32_t sz[kTilePix + kZPad];
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ uint32_t s_next[2];                 // batch claim counters of the two passes
+  __shared__ int s_issued[kStages];              // latest chunk whose bulk copies were issued into each ring stage
   __shared__ uint32_t s_zblk[128];               // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
   __shared__ float s_bigz[kRasterThreads];
@@ -786,8 +789,10 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       mbar_fence_init();
       s_next[0] = 0; s_next[1] = 0;
 #pragma unroll
-      for (int c = 0; c < kStages; ++c)
-        if (c < nchunks) issue_chunk(c, c);
+      for (int c = 0; c < kStages; ++c) {
+        s_issued[c] = -1;
+        if (c < nchunks) { issue_chunk(c, c); s_issued[c] = c; }
+      }
     }
     // the z tile starts at the cleared depth (glClear, 1.0); the per-frame big list (background quad, walls,
     // clipped triangles) is merged in at the end on registers -- min is associative, the result is the same
@@ -893,6 +898,11 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         if (bt >= b_hi) break;
         const int c = (int)(bt / (kChunk / 32));              // ring position of the chunk
         const int stage = c % kStages;
+        // A parity wait can only tell the current phase from the one before it.  Warps whose batches were
+        // cheap (depth-culled) can claim a batch of a chunk that has not even been issued yet, while the
+        // stage's previous chunk is still landing: looking at the barrier then would mistake "one phase behind"
+        // for "complete".  So first wait until the chunk's copies have been issued into the stage.
+        while (*reinterpret_cast<volatile int *>(&s_issued[stage]) < c) {}
         mbar_wait(&full_bar[stage], ((uint32_t)c / kStages) & 1);
         const uint32_t nrec = min(cnt - (uint32_t)c * kChunk, (uint32_t)kChunk);
         const uint32_t idx = (bt % (kChunk / 32)) * 32u + (uint32_t)lane;
@@ -962,6 +972,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           if ((bt % (kChunk / 32)) == (kChunk / 32) - 1 && cn < nchunks) {
             mbar_wait(&empty_bar[stage], ((uint32_t)c / kStages) & 1);
             issue_chunk(cn, stage);
+            __threadfence_block();                          // the barrier's new phase is set up before the flag says so
+            *reinterpret_cast<volatile int *>(&s_issued[stage]) = cn;
           }
         }
 
@@ -1405,6 +1417,15 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
 {
   cudaError_t err;
   int launches = 0;
+  // RUF_DEBUG_SYNC=1: synchronise after every kernel and say which one failed (debugging aid)
+  static const bool debug_sync = getenv("RUF_DEBUG_SYNC") != nullptr;
+  auto check = [&](const char *what) -> cudaError_t {
+    if (!debug_sync) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) fprintf(stderr, "[ruf] %s failed: %s\n", what, cudaGetErrorString(e));
+    return e;
+  };
   err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_frames * d.ctr_stride * sizeof(uint32_t), s);
   if (err != cudaSuccess) return err;
   if (ev) cudaEventRecord(ev[0], s);
@@ -1414,6 +1435,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     ruf_pose_kernel<<<blocks, 256, 0, s>>>(d_proj, d_view, d_part_model, d_lookat, m.part_aabb, d.n_parts, n_frames,
                                            ws.mvp, ws.vis);
     ++launches;
+    if ((err = check("ruf_pose_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[1], s);
   }
   {
@@ -1425,6 +1447,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     dim3 grid((unsigned)d.n_meshlets, (unsigned)((n_frames + fpc - 1) / fpc));
     ruf_setup_bin_kernel<<<grid, kSetupThreads, 0, s>>>(m, ws.mvp, ws.vis, d, n_frames, fpc, ws.big, ws.bins, ws.ctr);
     ++launches;
+    if ((err = check("ruf_setup_bin_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[2], s);
   }
   {
@@ -1434,6 +1457,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     else
       ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
     ++launches;
+    if ((err = check("ruf_raster_filter_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[3], s);
   }
   if (n_launches) *n_launches = launches;

@@ -352,3 +352,37 @@ def test_setup_frame_runs_match_the_oracle_frame_by_frame(monkeypatch, fpc):
         want_d, want_m, want_z = helpers.oracle_filter(sc, fr, nthreads=8)
         assert np.array_equal(z[i].view(np.uint32), want_z.view(np.uint32)), f"frame {i}: z-buffer differs"
         assert np.array_equal(out[i], want_d) and np.array_equal(mask[i], want_m), f"frame {i}"
+
+
+def test_million_frames_stay_identical():
+    """Soak: ~1 M frames through the device path, output of the last launch == output of the first.  (The raster
+    kernel's record ring once mistook a not-yet-issued chunk for a landed one -- a parity wait two phases ahead --
+    about once per half a million frames, only when the depth-culled pass made batches cheap.)"""
+    import torch
+    sc = helpers.scene("pr2")
+    proj, _, _ = sc.proj()
+    n = 256
+    views, pms = sc.frames([k % 48 for k in range(n)])
+    frames = [helpers.make_frame(sc, k, "u16", nthreads=8)["depth"] for k in range(8)]
+    depth = np.stack([frames[k % 8] for k in range(n)])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_in, d_proj, d_view, d_pm = t(depth.view(np.int16)), t(proj), t(views), t(pms)
+    d_out = torch.zeros_like(d_in)
+    d_mask = torch.zeros(d_in.shape, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        ctx.reserve(n)
+        args = (n, d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
+        ctx.filter_batch_device(*args)
+        ctx.sync()
+        first_d, first_m = d_out.clone(), d_mask.clone()
+        for it in range(4000):
+            ctx.filter_batch_device(*args)
+            if it % 500 == 499:
+                ctx.sync()
+                assert torch.equal(d_out, first_d) and torch.equal(d_mask, first_m), f"differs after {it + 1} launches"
+        ctx.sync()
+    assert torch.equal(d_out, first_d) and torch.equal(d_mask, first_m)
