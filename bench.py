@@ -411,7 +411,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per launch sequence")
     ap.add_argument("--ring", type=int, default=2, help="launch sequences (distinct buffers) per step")
-    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--e2e-frames", type=int, default=1024, help="frames per ruf_filter_batch_host call")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

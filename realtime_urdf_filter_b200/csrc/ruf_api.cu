@@ -484,12 +484,18 @@ static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int
   const size_t es = elem_size(enc);
   const size_t img = (size_t)c->W * c->H;
   const int P = c->n_parts;
-  const int nchunks = (n_frames + chunk - 1) / chunk;
   cudaStream_t sk = c->stream;
-  for (int k = 0; k < nchunks; ++k) {
+  // The D2H copies are the bottleneck (2+1 bytes out vs 2 bytes in per pixel) and run back to back once they have
+  // started, so what the chunking can still save is the time until the first one starts: the first chunks are
+  // small (chunk/8, chunk/8, chunk/4, chunk/2), then full size.
+  int f0 = 0, nf = 0;
+  for (int k = 0; f0 + nf < n_frames; ++k) {
+    f0 += nf;
     const int slot = k & 1;
-    const int f0 = k * chunk;
-    const int nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
+    int want = chunk;
+    if (k < 2) want = chunk / 8; else if (k == 2) want = chunk / 4; else if (k == 3) want = chunk / 2;
+    if (want < 1) want = 1;
+    nf = (n_frames - f0 < want) ? (n_frames - f0) : want;
     if (k >= 2) {
       // slot reuse: input slot free once chunk k-2's kernels ran; pinned matrices likewise
       RUF_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_k[slot], 0));
@@ -512,6 +518,7 @@ static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int
     int rc = launch(c, nf, c->d_in[slot], enc, dm, dm + 16, dm + 16 + 16 * (size_t)nf, max_diff, replace_value,
                     c->d_out[slot], mask_out ? c->d_mask[slot] : nullptr, nullptr, sk);
     if (rc != RUF_OK) return rc;
+    c->last_frames = nf;                       // ruf_get_stats reads the counters of the last launch sequence
     RUF_CUDA(c, cudaEventRecord(c->ev_k[slot], sk));
 
     RUF_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[slot], 0));
@@ -539,7 +546,7 @@ int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, in
   if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
   RUF_CUDA(c, cudaSetDevice(c->device));
   // frames per pipeline chunk: large enough for efficient copies/launches, small enough to overlap (measured)
-  int chunk = n_frames >= 128 ? 32 : (n_frames >= 64 ? 16 : (n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1)));
+  int chunk = n_frames >= 512 ? 64 : (n_frames >= 128 ? 32 : (n_frames >= 64 ? 16 : (n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1))));
   if (const char *e = getenv("RUF_HOST_CHUNK")) {      // tuning aid
     const int v = atoi(e);
     if (v >= 1 && v <= 4096) chunk = v < n_frames ? v : n_frames;
