@@ -68,9 +68,6 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #ifndef RUF_WALK
 #define RUF_WALK 2
 #endif
-#ifndef RUF_EARLY_SENSOR
-#define RUF_EARLY_SENSOR 0
-#endif
 #ifndef RUF_MIN_BACK_BATCHES
 #define RUF_MIN_BACK_BATCHES 6u
 #endif

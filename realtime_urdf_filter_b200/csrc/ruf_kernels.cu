@@ -803,9 +803,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   }
 
   // ===== all warps =====
-  // every thread shades 8 consecutive pixels of one tile row at the end.  Their sensor values are requested
-  // early -- before the big list in tiles without records, before the last barrier otherwise -- so that the
-  // HBM latency is covered by work that does not need many registers.
+  // every thread shades 8 consecutive pixels of one tile row at the end (requesting the sensor values earlier --
+  // before the last barrier, or by cp.async at kernel entry -- was measured and lost: registers / shared memory)
   const int gy = tile_y0 + prow, gx = tile_x0 + pcol;
   const size_t pix = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
   const bool full = fb.vec_ok && gy < d.H && (gx + 8 <= d.W);
@@ -820,9 +819,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
     }
   };
-#if RUF_EARLY_SENSOR
-  if (cnt == 0) load_sensor();
-#endif
   // ---- per-frame big list, part 1: classify its first 256 records against this tile (one per thread; a
   // typical frame has just the two triangles of the background quad, so only warp 0 does any work here):
   // 0 = no sample of this tile can be covered, 1 = every sample is covered, 2 = mixed, 3 = covered with a
@@ -1071,9 +1067,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
       }
     }
-#if RUF_EARLY_SENSOR
-    load_sensor();
-#endif
     consumer_bar_sync();                      // every record of the tile has been rasterised
     const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol]);
     const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol + 4]);
@@ -1139,9 +1132,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   const size_t base = pix;
   const float (&zw)[8] = zr;
   if (full) {
-#if !RUF_EARLY_SENSOR
     load_sensor();
-#endif
     // to_linear_depth (frag:14-17,22) and the threshold (frag:23) once per distinct z of this thread's run:
     // background pixels share one window z, so most threads divide once instead of eight times.  Never-drawn
     // pixels (z = 1: clear colour, :566) get +inf, so that `sensor > thr` is false for them.
