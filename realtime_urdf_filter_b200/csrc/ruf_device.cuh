@@ -24,8 +24,13 @@ constexpr int kMaxPoly = 12;
 
 // ---- tiling ----
 constexpr int kTileW = 64;
-constexpr int kTileH = 32;
+#ifndef RUF_TILE_H
+#define RUF_TILE_H 64
+#endif
+constexpr int kTileH = RUF_TILE_H;               // 32 or 64 (a raster thread then shades two rows)
 constexpr int kTilePix = kTileW * kTileH;       // 2048
+constexpr int kRowsPerThread = kTileH / 32;
+static_assert(kTileH == 32 || kTileH == 64, "tile height");
 constexpr int kRasterThreads = 256;             // threads of a raster CTA: 8 pixels of one tile row each
 #ifndef RUF_CHUNK
 #define RUF_CHUNK 128
@@ -34,7 +39,7 @@ constexpr int kChunk = RUF_CHUNK;               // records per ring stage (a mul
 constexpr int kStages = 2;                      // ring depth (a stage is released as soon as its records sit in registers)
 constexpr int kBigTiles = 12;                   // bbox touching more tiles -> per-frame "big" list
 #ifndef RUF_MAX_UNITS
-#define RUF_MAX_UNITS 32
+#define RUF_MAX_UNITS 24
 #endif
 constexpr int kMaxUnits = RUF_MAX_UNITS;        // units per record dealt to lanes; larger records are rasterised by the whole warp
 #ifndef RUF_UNIT_W

@@ -741,7 +741,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ uint32_t s_next[2];                 // batch claim counters of the two passes
   __shared__ int s_issued[kStages];              // latest chunk whose bulk copies were issued into each ring stage
-  __shared__ uint32_t s_zblk[128];               // maxima of the 4x4 blocks of the z tile (depth cull)
+  __shared__ uint32_t s_zblk[(kTileH / 4) * 16]; // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
   __shared__ float s_bigz[kRasterThreads];
 
@@ -796,29 +796,16 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
     // the z tile starts at the cleared depth (glClear, 1.0); the per-frame big list (background quad, walls,
     // clipped triangles) is merged in at the end on registers -- min is associative, the result is the same
-    uint4 *zp = reinterpret_cast<uint4 *>(&sz[prow * kTileW + pcol]);
-    zp[0] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
-    zp[1] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+#pragma unroll
+    for (int half = 0; half < kRowsPerThread; ++half) {
+      uint4 *zp = reinterpret_cast<uint4 *>(&sz[(prow + 32 * half) * kTileW + pcol]);
+      zp[0] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+      zp[1] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+    }
     if (tid < kZPad) sz[kTilePix + tid] = 0u;              // the depth cull may read past the tile's last row
   }
 
   // ===== all warps =====
-  // every thread shades 8 consecutive pixels of one tile row at the end (requesting the sensor values earlier --
-  // before the last barrier, or by cp.async at kernel entry -- was measured and lost: registers / shared memory)
-  const int gy = tile_y0 + prow, gx = tile_x0 + pcol;
-  const size_t pix = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
-  const bool full = fb.vec_ok && gy < d.H && (gx + 8 <= d.W);
-  uint4 sens0 = make_uint4(0u, 0u, 0u, 0u), sens1 = make_uint4(0u, 0u, 0u, 0u);
-  auto load_sensor = [&]() {
-    if (full) {
-      if (ENC == 1) {
-        sens0 = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + pix));
-      } else {
-        const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + pix);
-        sens0 = __ldg(p); sens1 = __ldg(p + 1);
-      }
-    }
-  };
   // ---- per-frame big list, part 1: classify its first 256 records against this tile (one per thread; a
   // typical frame has just the two triangles of the background quad, so only warp 0 does any work here):
   // 0 = no sample of this tile can be covered, 1 = every sample is covered, 2 = mixed, 3 = covered with a
@@ -855,7 +842,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   classify(0);
   __syncthreads();          // the classification, the cleared z tile and the ring's barriers are visible
 
-  float zr[8];                                  // this thread's 8 pixels of the z tile
   if (cnt) {
     {
       // binned triangles: a chunk's records are batches of 32; warps claim batches from a shared
@@ -875,7 +861,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       if (pass) {
         if (b_lo >= b_hi) break;
         __syncthreads();                      // every front record is in the z tile
-        if (tid < 128) {
+        if (tid < (kTileH / 4) * 16) {
           const uint4 *row = reinterpret_cast<const uint4 *>(&sz[(tid >> 4) * 4 * kTileW + (tid & 15) * 4]);
           uint32_t m = 0;
 #pragma unroll
@@ -948,7 +934,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
             r2 = e.A2 * (px0 - r.x2) + e.B2 * (py0 - r.y2) + e.bias2;
             sA0 = e.A0 * kSubpix; sA1 = e.A1 * kSubpix; sA2 = e.A2 * kSubpix;
             sB0 = e.B0 * kSubpix; sB1 = e.B1 * kSubpix; sB2 = e.B2 * kSubpix;
-            geo = (i0 - tile_x0) | ((j0 - tile_y0) << 6) | ((i1 - i0) << 11) | ((j1 - j0) << 17);
+            geo = (i0 - tile_x0) | ((j0 - tile_y0) << 6) | ((i1 - i0) << 12) | ((j1 - j0) << 18);
           } else {
             nunits = 0;
           }
@@ -1040,7 +1026,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
             }
             // bit (kUW*kUH - 1 - (rr*kUW + k)) of ~m <=> sample (dx + k, dy + rr) is covered; samples beyond
             // the bbox (clipped to the tile) belong to another tile or cannot be covered
-            const int wrem = ((qgeo >> 11) & 63) + 1 - dx, hrem = ((qgeo >> 17) & 31) + 1 - dy;
+            const int wrem = ((qgeo >> 12) & 63) + 1 - dx, hrem = ((qgeo >> 18) & 63) + 1 - dy;
             constexpr uint32_t kRowMask = (1u << kUW) - 1u, kAll = (kUH == 1) ? kRowMask : ((1u << (kUW * kUH)) - 1u);
             uint32_t vm = (kRowMask << kUW >> min(kUW, wrem)) & kRowMask;      // valid columns, MSB = k = 0
             if (kUH == 2) vm = (vm << kUW) | (hrem > 1 ? vm : 0u);
@@ -1048,7 +1034,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
             if (m) {
               const float fx0 = (float)(qbx + dx * kSubpix);                  // exact: |value| < 2^24
               // (plain atomicMin on the static __shared__ array: direct shared addressing, immediate offsets)
-              uint32_t *zp = sz + ((((qgeo >> 6) & 31) + dy) * kTileW + (qgeo & 63) + dx);
+              uint32_t *zp = sz + ((((qgeo >> 6) & 63) + dy) * kTileW + (qgeo & 63) + dx);
 #pragma unroll
               for (int rr = 0; rr < kUH; ++rr) {
                 const float rowz = fmaf(qgy, (float)(qby + (dy + rr) * kSubpix), qz0);
@@ -1068,144 +1054,168 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
     }
     consumer_bar_sync();                      // every record of the tile has been rasterised
-    const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol]);
-    const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[prow * kTileW + pcol + 4]);
-    zr[0] = __uint_as_float(zq0.x); zr[1] = __uint_as_float(zq0.y); zr[2] = __uint_as_float(zq0.z);
-    zr[3] = __uint_as_float(zq0.w); zr[4] = __uint_as_float(zq1.x); zr[5] = __uint_as_float(zq1.y);
-    zr[6] = __uint_as_float(zq1.z); zr[7] = __uint_as_float(zq1.w);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) zr[i] = 1.0f;       // glClear depth
   }
 
-  // ---- per-frame big list, part 2: pixel-parallel on registers, every thread owns 8 consecutive pixels ----
-  {
-    const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
-    const int py = (tile_y0 + prow) * kSubpix + kSubpixHalf;
-    for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
-      if (b0) {                                   // more than 256 records (clipping-heavy views): classify the next round
-        __syncthreads();
-        classify(b0);
-        __syncthreads();
-      }
-      const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
-      for (uint32_t b = 0; b < nb; ++b) {
-        const uint32_t c = s_bigcls[b];
-        if (c == 0) continue;
-        if (c == 3) {
-          const float z = s_bigz[b];
-          if (z < 1.0f) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) zr[i] = fminf(zr[i], z);
-          }
-          continue;
-        }
-        const TriRec r = load_rec_global(big + b0 + b);
-        const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
-        if (c == 1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-            if (z < 1.0f) zr[i] = fminf(zr[i], z);
-          }
-          continue;
-        }
-        const Edges e = make_edges(r);
-        long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
-        long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
-        long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
-        const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix, s2 = (long long)e.A2 * kSubpix;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if ((e0 | e1 | e2) >= 0) {
-            float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-            if (z < 1.0f) zr[i] = fminf(zr[i], z);
-          }
-          e0 += s0; e1 += s1; e2 += s2;
+  // Every thread owns 8 consecutive pixels of kRowsPerThread tile rows (32 rows apart).  Per row: fetch the
+  // rasterised depths, merge the per-frame big list on registers, run the fragment stage.
+#pragma unroll 1
+  for (int half = 0; half < kRowsPerThread; ++half) {
+    const int trow = prow + 32 * half;
+    const int gy = tile_y0 + trow, gx = tile_x0 + pcol;
+    const size_t pix = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
+    const bool full = fb.vec_ok && gy < d.H && (gx + 8 <= d.W);
+    uint4 sens0 = make_uint4(0u, 0u, 0u, 0u), sens1 = make_uint4(0u, 0u, 0u, 0u);
+    auto load_sensor = [&]() {
+      if (full) {
+        if (ENC == 1) {
+          sens0 = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + pix));
+        } else {
+          const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + pix);
+          sens0 = __ldg(p); sens1 = __ldg(p + 1);
         }
       }
-    }
-  }
-
-  // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
-  if (gy >= d.H || gx >= d.W) return;
-  const size_t base = pix;
-  const float (&zw)[8] = zr;
-  if (full) {
-    load_sensor();
-    // to_linear_depth (frag:14-17,22) and the threshold (frag:23) once per distinct z of this thread's run:
-    // background pixels share one window z, so most threads divide once instead of eight times.  Never-drawn
-    // pixels (z = 1: clear colour, :566) get +inf, so that `sensor > thr` is false for them.
-    float thr[8];
-    {
-      float zprev = 1.0f, tprev = __int_as_float(0x7f800000);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (zw[i] != zprev) {
-          tprev = (zw[i] == 1.0f) ? __int_as_float(0x7f800000) : (sp.k1 / (zw[i] - sp.k2)) - sp.max_diff;
-          zprev = zw[i];
-        }
-        thr[i] = tprev;
-      }
-    }
-    uint32_t om[8];
-    if (ENC == 1) {
-      const uint32_t w[4] = {sens0.x, sens0.y, sens0.z, sens0.w};
-      const uint32_t repl = f32_to_u16(sp.replace_value);       // convertTo(CV_16U, 1000) of the replaced pixels, :311
-      uint32_t u[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t raw = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
-        const float sensor = (float)raw * 0.001f;               // convertTo(CV_32F, 0.001), :288
-        const bool drawn = zw[i] != 1.0f;                       // else clear colour: depth 0, mask 0 (:566)
-        const bool sflt = sensor > thr[i];                      // frag:23
-        // an unfiltered pixel is sat_u16(rint((u * 0.001f) * 1000.f)), which is u itself for every
-        // 16-bit u (exhaustively checked: tests/test_oracle_encodings.py::test_u16_roundtrip_identity_all_65536)
-        u[i] = drawn ? (sflt ? repl : raw) : 0u;
-        om[i] = sflt ? 255u : 0u;
-      }
-      uint4 o;
-      o.x = u[0] | (u[1] << 16); o.y = u[2] | (u[3] << 16); o.z = u[4] | (u[5] << 16); o.w = u[6] | (u[7] << 16);
-      *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
+    };
+    float zr[8];                                // this thread's 8 pixels of the z tile
+    if (cnt) {
+      const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[trow * kTileW + pcol]);
+      const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[trow * kTileW + pcol + 4]);
+      zr[0] = __uint_as_float(zq0.x); zr[1] = __uint_as_float(zq0.y); zr[2] = __uint_as_float(zq0.z);
+      zr[3] = __uint_as_float(zq0.w); zr[4] = __uint_as_float(zq1.x); zr[5] = __uint_as_float(zq1.y);
+      zr[6] = __uint_as_float(zq1.z); zr[7] = __uint_as_float(zq1.w);
     } else {
-      const float sensor[8] = {__uint_as_float(sens0.x), __uint_as_float(sens0.y), __uint_as_float(sens0.z),
-                               __uint_as_float(sens0.w), __uint_as_float(sens1.x), __uint_as_float(sens1.y),
-                               __uint_as_float(sens1.z), __uint_as_float(sens1.w)};
-      float od[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool drawn = zw[i] != 1.0f;
-        const bool sflt = sensor[i] > thr[i];
-        od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
-        om[i] = sflt ? 255u : 0u;
+      for (int i = 0; i < 8; ++i) zr[i] = 1.0f;     // glClear depth
+    }
+
+    // ---- per-frame big list, part 2: pixel-parallel on registers ----
+    {
+      const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
+      const int py = (tile_y0 + trow) * kSubpix + kSubpixHalf;
+      for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
+        if (b0 || (half && nbig > kRasterThreads)) {   // more than 256 records (clipping-heavy views): classify this round (again)
+          __syncthreads();
+          classify(b0);
+          __syncthreads();
+        }
+        const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
+        for (uint32_t b = 0; b < nb; ++b) {
+          const uint32_t c = s_bigcls[b];
+          if (c == 0) continue;
+          if (c == 3) {
+            const float z = s_bigz[b];
+            if (z < 1.0f) {
+  #pragma unroll
+              for (int i = 0; i < 8; ++i) zr[i] = fminf(zr[i], z);
+            }
+            continue;
+          }
+          const TriRec r = load_rec_global(big + b0 + b);
+          const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
+          if (c == 1) {
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+              if (z < 1.0f) zr[i] = fminf(zr[i], z);
+            }
+            continue;
+          }
+          const Edges e = make_edges(r);
+          long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
+          long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
+          long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
+          const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix, s2 = (long long)e.A2 * kSubpix;
+  #pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if ((e0 | e1 | e2) >= 0) {
+              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+              if (z < 1.0f) zr[i] = fminf(zr[i], z);
+            }
+            e0 += s0; e1 += s1; e2 += s2;
+          }
+        }
       }
-      float4 *po = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
-      po[0] = make_float4(od[0], od[1], od[2], od[3]);
-      po[1] = make_float4(od[4], od[5], od[6], od[7]);
     }
-    if (fb.mask_out) {
-      uint2 mq;
-      mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
-      mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
-      *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
-    }
-    if (fb.zbuf_out) {
-      float4 *p = reinterpret_cast<float4 *>(fb.zbuf_out + base);
-      p[0] = make_float4(zw[0], zw[1], zw[2], zw[3]);
-      p[1] = make_float4(zw[4], zw[5], zw[6], zw[7]);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (gx + i >= d.W) break;
-      float sensor;
-      if (ENC == 1) sensor = (float)static_cast<const uint16_t *>(fb.depth_in)[base + i] * 0.001f;
-      else sensor = static_cast<const float *>(fb.depth_in)[base + i];
-      const FragOut o = fragment(sensor, zw[i], sp);
-      if (ENC == 1) static_cast<uint16_t *>(fb.depth_out)[base + i] = (uint16_t)f32_to_u16(o.depth);
-      else static_cast<float *>(fb.depth_out)[base + i] = o.depth;
-      if (fb.mask_out) fb.mask_out[base + i] = (uint8_t)o.mask;
-      if (fb.zbuf_out) fb.zbuf_out[base + i] = zw[i];
+
+    // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
+    if (gy >= d.H || gx >= d.W) continue;
+    const size_t base = pix;
+    const float (&zw)[8] = zr;
+    if (full) {
+      load_sensor();
+      // to_linear_depth (frag:14-17,22) and the threshold (frag:23) once per distinct z of this thread's run:
+      // background pixels share one window z, so most threads divide once instead of eight times.  Never-drawn
+      // pixels (z = 1: clear colour, :566) get +inf, so that `sensor > thr` is false for them.
+      float thr[8];
+      {
+        float zprev = 1.0f, tprev = __int_as_float(0x7f800000);
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (zw[i] != zprev) {
+            tprev = (zw[i] == 1.0f) ? __int_as_float(0x7f800000) : (sp.k1 / (zw[i] - sp.k2)) - sp.max_diff;
+            zprev = zw[i];
+          }
+          thr[i] = tprev;
+        }
+      }
+      uint32_t om[8];
+      if (ENC == 1) {
+        const uint32_t w[4] = {sens0.x, sens0.y, sens0.z, sens0.w};
+        const uint32_t repl = f32_to_u16(sp.replace_value);       // convertTo(CV_16U, 1000) of the replaced pixels, :311
+        uint32_t u[8];
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t raw = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+          const float sensor = (float)raw * 0.001f;               // convertTo(CV_32F, 0.001), :288
+          const bool drawn = zw[i] != 1.0f;                       // else clear colour: depth 0, mask 0 (:566)
+          const bool sflt = sensor > thr[i];                      // frag:23
+          // an unfiltered pixel is sat_u16(rint((u * 0.001f) * 1000.f)), which is u itself for every
+          // 16-bit u (exhaustively checked: tests/test_oracle_encodings.py::test_u16_roundtrip_identity_all_65536)
+          u[i] = drawn ? (sflt ? repl : raw) : 0u;
+          om[i] = sflt ? 255u : 0u;
+        }
+        uint4 o;
+        o.x = u[0] | (u[1] << 16); o.y = u[2] | (u[3] << 16); o.z = u[4] | (u[5] << 16); o.w = u[6] | (u[7] << 16);
+        *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
+      } else {
+        const float sensor[8] = {__uint_as_float(sens0.x), __uint_as_float(sens0.y), __uint_as_float(sens0.z),
+                                 __uint_as_float(sens0.w), __uint_as_float(sens1.x), __uint_as_float(sens1.y),
+                                 __uint_as_float(sens1.z), __uint_as_float(sens1.w)};
+        float od[8];
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool drawn = zw[i] != 1.0f;
+          const bool sflt = sensor[i] > thr[i];
+          od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
+          om[i] = sflt ? 255u : 0u;
+        }
+        float4 *po = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
+        po[0] = make_float4(od[0], od[1], od[2], od[3]);
+        po[1] = make_float4(od[4], od[5], od[6], od[7]);
+      }
+      if (fb.mask_out) {
+        uint2 mq;
+        mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
+        mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
+        *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
+      }
+      if (fb.zbuf_out) {
+        float4 *p = reinterpret_cast<float4 *>(fb.zbuf_out + base);
+        p[0] = make_float4(zw[0], zw[1], zw[2], zw[3]);
+        p[1] = make_float4(zw[4], zw[5], zw[6], zw[7]);
+      }
+    } else {
+  #pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (gx + i >= d.W) break;
+        float sensor;
+        if (ENC == 1) sensor = (float)static_cast<const uint16_t *>(fb.depth_in)[base + i] * 0.001f;
+        else sensor = static_cast<const float *>(fb.depth_in)[base + i];
+        const FragOut o = fragment(sensor, zw[i], sp);
+        if (ENC == 1) static_cast<uint16_t *>(fb.depth_out)[base + i] = (uint16_t)f32_to_u16(o.depth);
+        else static_cast<float *>(fb.depth_out)[base + i] = o.depth;
+        if (fb.mask_out) fb.mask_out[base + i] = (uint8_t)o.mask;
+        if (fb.zbuf_out) fb.zbuf_out[base + i] = zw[i];
+      }
     }
   }
 }
