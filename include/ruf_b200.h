@@ -93,7 +93,7 @@ RUF_API int ruf_set_model_device(ruf_context *ctx, const void *d_tri_xyz, const 
                                  int64_t n_tris, int n_parts);
 
 /* Capacity control for device-resident batches: max frames per call, and (0 = automatic) the
- * capacities of the internal per-frame big-triangle list and of the record list every 64x32 tile owns. */
+ * capacities of the internal per-frame big-triangle list and of the record list every 64x64 tile owns. */
 RUF_API int ruf_reserve(ruf_context *ctx, int max_batch, int64_t big_capacity, int64_t tile_capacity);
 
 /* ------------------------------------------------------------------------------------ */

@@ -1,13 +1,17 @@
 // ruf_device.cuh -- shared device-side types and launch prototypes of the B200 hot path.
 //
 // Pipeline per batch of frames (DESIGN.md "Kernels"):
-//   K0 ruf_pose_kernel      fp64  P * V_f * M_{f,p}  -> fp32 MVP table     (vertex-stage matrices)
-//   K1 ruf_setup_bin_kernel one CTA / (frame, 512 triangles): vertex shader, clip, viewport, snap,
-//                           setup, cull; CTA-local tile binning in shared memory; tile-sorted
-//                           records + a (start,count) table entry per (tile, CTA)
-//   K2 ruf_raster_filter_kernel   one CTA / (frame, 64x32 tile): gathers its segments with bulk
-//                           async copies (TMA) into smem -> smem z-tile (min) -> fused fragment
-//                           shader + encode + store
+//   K0 ruf_pose_kernel      fp64  P * V_f * M_{f,p}  -> fp32 MVP table; per (frame, part): view-volume
+//                           cull bit and facing hint
+//   K1 ruf_setup_bin_kernel one CTA / (meshlet, run of frames): vertex shader once per welded vertex,
+//                           cheap per-triangle rejects, survivors compacted per warp, clip, set-up;
+//                           match.any walk over the bbox tiles, ONE 8-byte global atomic per (warp step,
+//                           tile) reserves room in that tile's record list (front run / back run)
+//   K2 ruf_raster_filter_kernel   one CTA / (frame, 64x64 tile): streams its tile's record list with bulk
+//                           async copies (TMA) into a shared-memory ring -> units of 4x2 samples dealt to
+//                           lanes -> z tile in shared memory (atomicMin), depth-culled second pass for the
+//                           back run -> per-frame big list merged on registers -> fused fragment shader +
+//                           encode + store; tiles without records never touch the z tile
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,7 +32,7 @@ constexpr int kTileW = 64;
 #define RUF_TILE_H 64
 #endif
 constexpr int kTileH = RUF_TILE_H;               // 32 or 64 (a raster thread then shades two rows)
-constexpr int kTilePix = kTileW * kTileH;       // 2048
+constexpr int kTilePix = kTileW * kTileH;
 constexpr int kRowsPerThread = kTileH / 32;
 static_assert(kTileH == 32 || kTileH == 64, "tile height");
 constexpr int kRasterThreads = 256;             // threads of a raster CTA: 8 pixels of one tile row each
