@@ -41,7 +41,10 @@ constexpr int kRasterThreads = 256;             // threads of a raster CTA: 8 pi
 #endif
 constexpr int kChunk = RUF_CHUNK;               // records per ring stage (a multiple of 32)
 constexpr int kStages = 2;                      // ring depth (a stage is released as soon as its records sit in registers)
-constexpr int kBigTiles = 12;                   // bbox touching more tiles -> per-frame "big" list
+#ifndef RUF_BIG_TILES
+#define RUF_BIG_TILES 12
+#endif
+constexpr int kBigTiles = RUF_BIG_TILES;                   // bbox touching more tiles -> per-frame "big" list
 #ifndef RUF_MAX_UNITS
 #define RUF_MAX_UNITS 24
 #endif

@@ -1056,9 +1056,83 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     consumer_bar_sync();                      // every record of the tile has been rasterised
   }
 
-  // Every thread owns 8 consecutive pixels of kRowsPerThread tile rows (32 rows apart).  Per row: fetch the
-  // rasterised depths, merge the per-frame big list on registers, run the fragment stage.
-#pragma unroll 1
+  // Every thread owns 8 consecutive pixels of kRowsPerThread tile rows (32 rows apart): fetch the rasterised
+  // depths, merge the per-frame big list on registers (one walk over the classified records for all rows),
+  // then run the fragment stage row by row.
+  float zall[kRowsPerThread][8];
+#pragma unroll
+  for (int half = 0; half < kRowsPerThread; ++half) {
+    if (cnt) {
+      const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[(prow + 32 * half) * kTileW + pcol]);
+      const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[(prow + 32 * half) * kTileW + pcol + 4]);
+      zall[half][0] = __uint_as_float(zq0.x); zall[half][1] = __uint_as_float(zq0.y); zall[half][2] = __uint_as_float(zq0.z);
+      zall[half][3] = __uint_as_float(zq0.w); zall[half][4] = __uint_as_float(zq1.x); zall[half][5] = __uint_as_float(zq1.y);
+      zall[half][6] = __uint_as_float(zq1.z); zall[half][7] = __uint_as_float(zq1.w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) zall[half][i] = 1.0f;     // glClear depth
+    }
+  }
+  // ---- per-frame big list, part 2: pixel-parallel on registers ----
+  {
+    const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
+    const int py0 = (tile_y0 + prow) * kSubpix + kSubpixHalf;
+    for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
+      if (b0) {                                   // more than 256 records (clipping-heavy views): classify the next round
+        __syncthreads();
+        classify(b0);
+        __syncthreads();
+      }
+      const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
+      for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t c = s_bigcls[b];
+        if (c == 0) continue;
+        if (c == 3) {
+          const float z = s_bigz[b];
+          if (z < 1.0f) {
+#pragma unroll
+            for (int half = 0; half < kRowsPerThread; ++half)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) zall[half][i] = fminf(zall[half][i], z);
+          }
+          continue;
+        }
+        const TriRec r = load_rec_global(big + b0 + b);
+        if (c == 1) {
+#pragma unroll
+          for (int half = 0; half < kRowsPerThread; ++half) {
+            const float rowz = fmaf(r.gy, (float)(py0 + 32 * half * kSubpix - r.y0), r.z0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+              if (z < 1.0f) zall[half][i] = fminf(zall[half][i], z);
+            }
+          }
+          continue;
+        }
+        const Edges e = make_edges(r);
+        const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix, s2 = (long long)e.A2 * kSubpix;
+#pragma unroll
+        for (int half = 0; half < kRowsPerThread; ++half) {
+          const int py = py0 + 32 * half * kSubpix;
+          const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
+          long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
+          long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
+          long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if ((e0 | e1 | e2) >= 0) {
+              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+              if (z < 1.0f) zall[half][i] = fminf(zall[half][i], z);
+            }
+            e0 += s0; e1 += s1; e2 += s2;
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
   for (int half = 0; half < kRowsPerThread; ++half) {
     const int trow = prow + 32 * half;
     const int gy = tile_y0 + trow, gx = tile_x0 + pcol;
@@ -1075,66 +1149,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         }
       }
     };
-    float zr[8];                                // this thread's 8 pixels of the z tile
-    if (cnt) {
-      const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[trow * kTileW + pcol]);
-      const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[trow * kTileW + pcol + 4]);
-      zr[0] = __uint_as_float(zq0.x); zr[1] = __uint_as_float(zq0.y); zr[2] = __uint_as_float(zq0.z);
-      zr[3] = __uint_as_float(zq0.w); zr[4] = __uint_as_float(zq1.x); zr[5] = __uint_as_float(zq1.y);
-      zr[6] = __uint_as_float(zq1.z); zr[7] = __uint_as_float(zq1.w);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) zr[i] = 1.0f;     // glClear depth
-    }
-
-    // ---- per-frame big list, part 2: pixel-parallel on registers ----
-    {
-      const int px0 = (tile_x0 + pcol) * kSubpix + kSubpixHalf;
-      const int py = (tile_y0 + trow) * kSubpix + kSubpixHalf;
-      for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
-        if (b0 || (half && nbig > kRasterThreads)) {   // more than 256 records (clipping-heavy views): classify this round (again)
-          __syncthreads();
-          classify(b0);
-          __syncthreads();
-        }
-        const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
-        for (uint32_t b = 0; b < nb; ++b) {
-          const uint32_t c = s_bigcls[b];
-          if (c == 0) continue;
-          if (c == 3) {
-            const float z = s_bigz[b];
-            if (z < 1.0f) {
-  #pragma unroll
-              for (int i = 0; i < 8; ++i) zr[i] = fminf(zr[i], z);
-            }
-            continue;
-          }
-          const TriRec r = load_rec_global(big + b0 + b);
-          const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
-          if (c == 1) {
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-              if (z < 1.0f) zr[i] = fminf(zr[i], z);
-            }
-            continue;
-          }
-          const Edges e = make_edges(r);
-          long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
-          long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
-          long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
-          const long long s0 = (long long)e.A0 * kSubpix, s1 = (long long)e.A1 * kSubpix, s2 = (long long)e.A2 * kSubpix;
-  #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if ((e0 | e1 | e2) >= 0) {
-              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-              if (z < 1.0f) zr[i] = fminf(zr[i], z);
-            }
-            e0 += s0; e1 += s1; e2 += s2;
-          }
-        }
-      }
-    }
+    const float (&zr)[8] = zall[half];
 
     // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
     if (gy >= d.H || gx >= d.W) continue;
