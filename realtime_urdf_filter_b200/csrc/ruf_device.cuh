@@ -83,6 +83,10 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #ifndef RUF_MIN_BACK_BATCHES
 #define RUF_MIN_BACK_BATCHES 6u
 #endif
+#ifndef RUF_OCCLUDE_MIN
+#define RUF_OCCLUDE_MIN 8
+#endif
+constexpr int kOccludeMin = RUF_OCCLUDE_MIN;     // big-list rounds with more records than this run the per-tile occlusion test
 #ifndef RUF_DEPTH_CULL
 #define RUF_DEPTH_CULL 1
 #endif

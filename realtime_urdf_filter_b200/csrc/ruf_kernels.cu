@@ -724,6 +724,38 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
   return o;
 }
 
+// Occlusion among the big-list records of one tile (result-neutral; every thread of the CTA calls it with its own
+// record, cls = 0 for none).  A record that covers every sample of the tile and is drawn everywhere (cls 1 / 3,
+// farthest corner in front of the far plane) hides every record whose NEAREST corner is not in front of its FARTHEST
+// corner -- min() cannot change there.  z is monotone in both sample coordinates (every step is a correctly rounded
+// fma), so its extremes over the tile's sample grid sit on the four corner samples, evaluated with the walk's own
+// expressions.  The occluder with the smallest farthest corner is kept (lowest index on ties); returns the record's
+// class, 0 if it is hidden.  Kept out of line: it only runs for frames with more than kOccludeMin big-list records.
+__device__ __noinline__ uint32_t occlusion_filter(uint32_t cls, int x0, int y0, float z0, float gx, float gy, int tpx,
+                                                  int tpy, int tid, uint32_t *s_zcut, uint32_t *s_zown)
+{
+  uint32_t zlo = 0, zhi = 0;
+  if (cls) {
+    const float fxa = (float)(tpx - x0), fxb = (float)(tpx + (kTileW - 1) * kSubpix - x0);
+    const float rza = fmaf(gy, (float)(tpy - y0), z0);
+    const float rzb = fmaf(gy, (float)(tpy + (kTileH - 1) * kSubpix - y0), z0);
+    const uint32_t zaa = __float_as_uint(clamp_z(fmaf(gx, fxa, rza))), zba = __float_as_uint(clamp_z(fmaf(gx, fxb, rza)));
+    const uint32_t zab = __float_as_uint(clamp_z(fmaf(gx, fxa, rzb))), zbb = __float_as_uint(clamp_z(fmaf(gx, fxb, rzb)));
+    zlo = min(min(zaa, zba), min(zab, zbb));
+    zhi = max(max(zaa, zba), max(zab, zbb));
+  }
+  const bool occluder = (cls == 1u || cls == 3u) && zhi < 0x3f800000u;
+  if (tid == 0) { *s_zcut = 0xffffffffu; *s_zown = 0xffffffffu; }
+  __syncthreads();
+  if (occluder) atomicMin(s_zcut, zhi);
+  __syncthreads();
+  const uint32_t zc = *s_zcut;
+  if (occluder && zhi == zc) atomicMin(s_zown, (uint32_t)tid);
+  __syncthreads();
+  if (cls && zlo >= zc && (uint32_t)tid != *s_zown) cls = 0u;
+  return cls;
+}
+
 template <int ENC>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
@@ -743,6 +775,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ int s_issued[kStages];              // latest chunk whose bulk copies were issued into each ring stage
   __shared__ uint32_t s_zblk[(kTileH / 4) * 16]; // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
+  __shared__ uint32_t s_zcut, s_zown;            // big-list occlusion: smallest farthest-corner z of a covering record, its index
   __shared__ float s_bigz[kRasterThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -815,6 +848,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   const int tpx = tile_x0 * kSubpix + kSubpixHalf, tpy = tile_y0 * kSubpix + kSubpixHalf;
   auto classify = [&](uint32_t b0) {
     uint32_t cls = 0;
+    int ox0 = 0, oy0 = 0;
+    float oz0 = 0.f, ogx = 0.f, ogy = 0.f;
+    const bool occlude = nbig - b0 > (uint32_t)kOccludeMin;     // CTA-uniform; a typical frame holds just the background quad
     if (b0 + tid < nbig) {
       const TriRec r = load_rec_global(big + b0 + tid);
       const int bi0 = (int)(r.bx & 0xffffu), bi1 = (int)(r.bx >> 16);
@@ -835,8 +871,10 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         // window z, so both gradients are exactly 0 and z(P) = fma(0, ., fma(0, ., z0)) = z0): hand the
         // value over instead of the record
         if (cls == 1u && r.gx == 0.0f && r.gy == 0.0f) { cls = 3u; s_bigz[tid] = clamp_z(r.z0); }
+        if (occlude) { ox0 = r.x0; oy0 = r.y0; oz0 = r.z0; ogx = r.gx; ogy = r.gy; }
       }
     }
+    if (occlude) cls = occlusion_filter(cls, ox0, oy0, oz0, ogx, ogy, tpx, tpy, tid, &s_zcut, &s_zown);
     s_bigcls[tid] = (uint8_t)cls;
   };
   classify(0);
