@@ -68,7 +68,8 @@ def parse_urdf(xml: str, geometry_type: str = "", scale: float = 1.0, ignore=(),
     n = L.ruf_facade_parse_urdf(xml.encode(), geometry_type.encode(), scale, ",".join(ignore).encode(),
                                 resource_root.encode(), None, None, 0, C.byref(n_parts), None)
     if n < 0:
-        raise ValueError("URDF failed to parse")
+        L.ruf_facade_last_parse_error.restype = C.c_char_p
+        raise ValueError("URDF failed to parse: " + L.ruf_facade_last_parse_error().decode())
     tri = np.zeros((n, 9), np.float32)
     part = np.zeros(n, np.uint32)
     pm = np.zeros((n_parts.value, 16))

@@ -155,6 +155,8 @@ RUF_API double ruf_facade_get_double(void *h, const char *name)
   if (n == "height") return f->height_;
   return -1e300;
 }
+static thread_local std::string g_parse_error;
+RUF_API const char *ruf_facade_last_parse_error() { return g_parse_error.c_str(); }
 // URDF parsing alone (no GPU): number of parts / triangles a description would produce
 RUF_API long ruf_facade_parse_urdf(const char *xml, const char *geometry_type, double scale, const char *ignore_csv,
                                    const char *resource_root, float *tri_out, uint32_t *part_out, long cap_tris,
@@ -169,6 +171,7 @@ RUF_API long ruf_facade_parse_urdf(const char *xml, const char *geometry_type, d
   std::vector<std::string> roots;
   if (resource_root && *resource_root) roots.push_back(resource_root);
   URDFRenderer r(xml, "", "cam", "fixed", tf, geometry_type, scale, ignore, roots);
+  g_parse_error = r.error();
   if (!r.ok()) return -1;
   const long n = (long)r.triangle_parts().size();
   if (n_parts) *n_parts = (long)r.parts().size();

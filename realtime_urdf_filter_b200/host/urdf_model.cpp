@@ -1,6 +1,7 @@
 // urdf_model.cpp -- see urdf_model.h.
 #include "urdf_model.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -8,6 +9,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <unordered_set>
 
 #include "../../include/ruf_b200.h"
 
@@ -164,6 +166,22 @@ struct XmlParser {
       return true;
     }
   }
+  static std::string decode_entities(const std::string &v)
+  {
+    if (v.find('&') == std::string::npos) return v;
+    static const struct { const char *ent; char ch; } kEnt[] = {{"&amp;", '&'}, {"&lt;", '<'}, {"&gt;", '>'}, {"&quot;", '"'}, {"&apos;", '\''}};
+    std::string o;
+    for (size_t k = 0; k < v.size();) {
+      bool hit = false;
+      if (v[k] == '&')
+        for (const auto &e : kEnt) {
+          const size_t n = std::strlen(e.ent);
+          if (v.compare(k, n, e.ent) == 0) { o.push_back(e.ch); k += n; hit = true; break; }
+        }
+      if (!hit) o.push_back(v[k++]);
+    }
+    return o;
+  }
   static bool name_char(char c) { return std::isalnum((unsigned char)c) || c == '_' || c == ':' || c == '-' || c == '.'; }
   bool parse_element(XmlNode &n)
   {
@@ -190,7 +208,7 @@ struct XmlParser {
       size_t vb = i;
       while (i < s.size() && s[i] != qc) ++i;
       if (i >= s.size()) { err = "unterminated attribute value"; return false; }
-      n.attr.emplace_back(key, s.substr(vb, i - vb));
+      n.attr.emplace_back(key, decode_entities(s.substr(vb, i - vb)));
       ++i;
     }
     // children until </tag>
@@ -278,43 +296,93 @@ bool parse_geometry(const XmlNode *g, Geometry &out, std::string *err)
 }
 }  // namespace
 
+// Follows urdfdom's parseURDF / Model::initTree / Model::initRoot (the parser behind urdf::Model::initString,
+// src/urdf_renderer.cpp:69-70) in what it accepts and rejects: robot and link names are required, link and joint
+// names unique, at least one link, joints need a known type, a parent and a child that exist (revolute and
+// prismatic ones a <limit>), and the links form a tree with exactly one root.
 bool UrdfModel::initString(const std::string &xml, std::string *error)
 {
-  links.clear(); joints.clear();
+  links.clear(); joints.clear(); name.clear(); root_link.clear();
+  auto fail = [&](const std::string &msg) { if (error) *error = msg; links.clear(); joints.clear(); return false; };
   XmlNode root;
   XmlParser p(xml);
-  if (!p.parse(root)) { if (error) *error = "XML: " + p.err; return false; }
-  if (root.tag != "robot") { if (error) *error = "no <robot> element"; return false; }
-  if (const std::string *n = root.get("name")) name = *n;
+  if (!p.parse(root)) return fail("XML: " + p.err);
+  if (root.tag != "robot") return fail("Could not find the 'robot' element in the xml file");
+  const std::string *rn = root.get("name");
+  if (!rn) return fail("No name given for the robot.");
+  name = *rn;
+  std::unordered_set<std::string> seen;
   for (const XmlNode &c : root.children) {
-    if (c.tag == "link") {
-      UrdfLink l;
-      const std::string *n = c.get("name");
-      if (!n) { if (error) *error = "link without name"; return false; }
-      l.name = *n;
-      for (const XmlNode &v : c.children) {
-        if (v.tag != "visual" && v.tag != "collision") continue;
-        Visual vis;
-        std::string e;
-        if (!parse_pose(v.child("origin"), vis.origin) || !parse_geometry(v.child("geometry"), vis.geometry, &e)) {
-          if (error) *error = "link " + l.name + ": " + (e.empty() ? "bad origin" : e);
-          return false;
-        }
-        (v.tag == "visual" ? l.visual_array : l.collision_array).push_back(vis);
-      }
-      links.push_back(std::move(l));
-    } else if (c.tag == "joint") {
-      UrdfJoint j;
-      if (const std::string *n = c.get("name")) j.name = *n;
-      if (const std::string *t = c.get("type")) j.type = *t;
-      if (const XmlNode *pn = c.child("parent")) if (const std::string *l = pn->get("link")) j.parent = *l;
-      if (const XmlNode *cn = c.child("child")) if (const std::string *l = cn->get("link")) j.child = *l;
-      if (!parse_pose(c.child("origin"), j.origin)) { if (error) *error = "joint " + j.name + ": bad origin"; return false; }
-      if (const XmlNode *a = c.child("axis")) if (const std::string *v = a->get("xyz")) parse_doubles(*v, j.axis, 3);
-      joints.push_back(std::move(j));
+    if (c.tag != "link") continue;
+    UrdfLink l;
+    const std::string *n = c.get("name");
+    if (!n) return fail("No name given for the link.");
+    l.name = *n;
+    if (!seen.insert(l.name).second) return fail("link '" + l.name + "' is not unique.");
+    for (const XmlNode &v : c.children) {
+      if (v.tag != "visual" && v.tag != "collision") continue;
+      Visual vis;
+      std::string e;
+      if (!parse_pose(v.child("origin"), vis.origin) || !parse_geometry(v.child("geometry"), vis.geometry, &e))
+        return fail("link " + l.name + ": " + (e.empty() ? "bad origin" : e));
+      (v.tag == "visual" ? l.visual_array : l.collision_array).push_back(vis);
     }
+    links.push_back(std::move(l));
   }
+  if (links.empty()) return fail("No link elements found in urdf file");
+  std::unordered_set<std::string> jseen, children;
+  for (const XmlNode &c : root.children) {
+    if (c.tag != "joint") continue;
+    UrdfJoint j;
+    const std::string *n = c.get("name");
+    if (!n) return fail("unnamed joint found");
+    j.name = *n;
+    if (!jseen.insert(j.name).second) return fail("joint '" + j.name + "' is not unique.");
+    const std::string *t = c.get("type");
+    if (!t) return fail("joint [" + j.name + "] has no type, check to see if it's a reference.");
+    j.type = *t;
+    static const char *kTypes[] = {"planar", "floating", "revolute", "continuous", "prismatic", "fixed"};
+    bool known = false;
+    for (const char *k : kTypes) known = known || j.type == k;
+    if (!known) return fail("Joint [" + j.name + "] has no known type [" + j.type + "]");
+    if ((j.type == "revolute" || j.type == "prismatic") && !c.child("limit"))
+      return fail("Joint [" + j.name + "] is of type " + (j.type == "revolute" ? "REVOLUTE" : "PRISMATIC") +
+                  " but it does not specify limits");
+    if (const XmlNode *pn = c.child("parent")) if (const std::string *l = pn->get("link")) j.parent = *l;
+    if (const XmlNode *cn = c.child("child")) if (const std::string *l = cn->get("link")) j.child = *l;
+    if (!parse_pose(c.child("origin"), j.origin)) return fail("joint " + j.name + ": bad origin");
+    if (const XmlNode *a = c.child("axis"))
+      if (const std::string *v = a->get("xyz"))
+        if (!parse_doubles(*v, j.axis, 3)) return fail("Malformed axis element for joint [" + j.name + "]");
+    joints.push_back(std::move(j));
+  }
+  // Model::initTree
+  for (const UrdfJoint &j : joints) {
+    if (j.parent.empty() || j.child.empty())
+      return fail("Joint [" + j.name + "] is missing a parent and/or child link specification.");
+    if (!seen.count(j.child)) return fail("child link [" + j.child + "] of joint [" + j.name + "] not found");
+    if (!seen.count(j.parent)) return fail("parent link [" + j.parent + "] of joint [" + j.name + "] not found");
+    children.insert(j.child);
+  }
+  // Model::initRoot
+  for (const UrdfLink &l : links) {
+    if (children.count(l.name)) continue;
+    if (!root_link.empty()) return fail("Two root links found: [" + root_link + "] and [" + l.name + "]");
+    root_link = l.name;
+  }
+  if (root_link.empty()) return fail("No root link found. The robot xml is not a valid tree.");
   return true;
+}
+
+// urdf::ModelInterface::getLinks walks links_, a std::map keyed by the link name: the renderables are created in
+// the byte-wise lexicographic order of the link names, not in document order.  The order is visible through the
+// "failed lookup re-uses the previous iteration's transform" quirk of update_link_transforms.
+std::vector<const UrdfLink *> UrdfModel::getLinks() const
+{
+  std::vector<const UrdfLink *> out;
+  for (const UrdfLink &l : links) out.push_back(&l);
+  std::sort(out.begin(), out.end(), [](const UrdfLink *a, const UrdfLink *b) { return a->name < b->name; });
+  return out;
 }
 
 // =================================================================================================
@@ -386,10 +454,11 @@ URDFRenderer::URDFRenderer(const std::string &model_description, const std::stri
   std::string err;
   if (!model.initString(model_description, &err)) {
     logf(LOG_ERROR, "URDF failed Model parse: %s", err.c_str());      // src/urdf_renderer.cpp:71-75
+    error_ = err;
     return;
   }
   logf(LOG_INFO, "URDF parsed OK");
-  for (const UrdfLink &l : model.links) process_link(l);              // :84-96
+  for (const UrdfLink *l : model.getLinks()) process_link(*l);        // :84-96 (std::map order)
   logf(LOG_INFO, "Loaded %zu renderables", num_renderables());
   ok_ = true;
 }

@@ -44,8 +44,12 @@ struct UrdfModel {
   std::string name;
   std::vector<UrdfLink> links;
   std::vector<UrdfJoint> joints;
-  // urdf::Model::initString: false on malformed XML / missing <robot>
+  std::string root_link;
+  // urdf::Model::initString: false on malformed XML and on what urdfdom rejects (missing robot / link names,
+  // duplicate names, no links, joints without a known type or with unknown links, not exactly one root link)
   bool initString(const std::string &xml, std::string *error = nullptr);
+  // links in the order urdf::ModelInterface::getLinks yields them (std::map: sorted by name)
+  std::vector<const UrdfLink *> getLinks() const;
 };
 
 // One draw call of the reference = one model matrix on the device ("part").
@@ -84,6 +88,7 @@ class URDFRenderer {
   const std::vector<uint32_t> &triangle_parts() const { return tri_part_; }
   size_t num_renderables() const { return renderable_name_.size(); }
   bool ok() const { return ok_; }
+  const std::string &error() const { return error_; }                  // why the description was rejected
 
  private:
   void process_link(const UrdfLink &link);
@@ -96,6 +101,7 @@ class URDFRenderer {
   std::vector<std::string> roots_;
   TransformListener &tf_;
   bool ok_ = false;
+  std::string error_;
   std::vector<RenderablePart> parts_;
   std::vector<float> tri_;
   std::vector<uint32_t> tri_part_;

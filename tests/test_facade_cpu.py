@@ -41,6 +41,7 @@ def test_primitives_origin_and_suffix():
       <link name="a"><visual><origin xyz="0.1 0.2 0.3" rpy="0.1 -0.2 0.3"/><geometry><cylinder radius="0.2" length="1.0"/></geometry></visual>
                      <visual><geometry><sphere radius="0.25"/></geometry></visual></link>
       <link name="b"/>
+      <joint name="ab" type="fixed"><parent link="a"/><child link="b"/></joint>
     </robot>"""
     tri, part, pm = facade.parse_urdf(xml, "visual")
     assert len(tri) == 220 + 180 and pm.shape == (2, 16)
@@ -63,6 +64,50 @@ def test_malformed_urdf_is_rejected():
                 '<robot><link name="a"><visual><geometry><cone/></geometry></visual></link></robot>']:
         with pytest.raises(ValueError):
             facade.parse_urdf(bad)
+
+
+def test_urdfdom_validation_rules():
+    """What urdf::Model::initString (urdfdom parseURDF / initTree / initRoot) rejects, the subset parser rejects
+    with the same reason; src/urdf_renderer.cpp:69-75 then logs and builds no renderables."""
+    link = lambda n: f'<link name="{n}"/>'
+    joint = lambda n, p, c, t="fixed", extra="": (f'<joint name="{n}" type="{t}"><parent link="{p}"/>'
+                                                  f'<child link="{c}"/>{extra}</joint>')
+    cases = {
+        "No name given for the robot": f'<robot>{link("a")}</robot>',
+        "No link elements found": '<robot name="r"/>',
+        "link 'a' is not unique": f'<robot name="r">{link("a")}{link("a")}</robot>',
+        "joint 'j' is not unique": f'<robot name="r">{link("a")}{link("b")}{link("c")}{joint("j", "a", "b")}{joint("j", "a", "c")}</robot>',
+        "has no known type [hinge]": f'<robot name="r">{link("a")}{link("b")}{joint("j", "a", "b", "hinge")}</robot>',
+        "does not specify limits": f'<robot name="r">{link("a")}{link("b")}{joint("j", "a", "b", "revolute")}</robot>',
+        "child link [zz] of joint [j] not found": f'<robot name="r">{link("a")}{joint("j", "a", "zz")}</robot>',
+        "parent link [zz] of joint [j] not found": f'<robot name="r">{link("a")}{joint("j", "zz", "a")}</robot>',
+        "Two root links found: [a] and [c]": f'<robot name="r">{link("a")}{link("b")}{link("c")}{joint("j", "a", "b")}</robot>',
+        "No root link found": f'<robot name="r">{link("a")}{link("b")}{joint("j", "a", "b")}{joint("k", "b", "a")}</robot>',
+        "missing a parent and/or child": f'<robot name="r">{link("a")}{link("b")}<joint name="j" type="fixed"><parent link="a"/></joint></robot>',
+    }
+    for reason, xml in cases.items():
+        with pytest.raises(ValueError, match=reason.replace("[", r"\[").replace("]", r"\]")):
+            facade.parse_urdf(xml)
+    # accepted: continuous needs no limit, revolute with one, entities in attribute values
+    ok = (f'<robot name="r &amp; d">{link("a")}{link("b")}{link("c")}{joint("j", "a", "b", "continuous")}'
+          f'{joint("k", "b", "c", "revolute", "<limit lower=\"0\" upper=\"1\" effort=\"1\" velocity=\"1\"/>")}</robot>')
+    tri, _, pm = facade.parse_urdf(ok)
+    assert len(tri) == 0 and pm.shape[0] == 0
+
+
+def test_renderables_follow_getLinks_order_not_document_order():
+    """urdf::ModelInterface::getLinks iterates a std::map keyed by link name (src/urdf_renderer.cpp:87-95): the
+    renderables come out sorted by link name whatever the document order is."""
+    def vis(size):
+        return f'<visual><geometry><sphere radius="{size}"/></geometry></visual>'
+    xml = (f'<robot name="o"><link name="zeta">{vis(0.3)}</link><link name="Alpha">{vis(0.1)}</link>'
+           f'<link name="beta">{vis(0.2)}</link>'
+           '<joint name="j1" type="fixed"><parent link="zeta"/><child link="Alpha"/></joint>'
+           '<joint name="j2" type="fixed"><parent link="zeta"/><child link="beta"/></joint></robot>')
+    tri, part, pm = facade.parse_urdf(xml, "visual")
+    assert pm.shape[0] == 3 and len(tri) == 3 * 180
+    radii = [float(np.abs(tri[part == k]).max()) for k in range(3)]
+    assert np.allclose(radii, [0.1, 0.2, 0.3])          # "Alpha" < "beta" < "zeta" (byte-wise: upper case first)
 
 
 def _write_binary_stl(path, tris, header=b"binary"):
