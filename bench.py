@@ -178,7 +178,9 @@ def run_reference(args, rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i64 (u16 I/O)",
         "data": "synthetic",
         "config": {"workload": "640x480 16UC1 stream, PR2-like synthetic model "
-                               f"({sc.n_parts} parts, {sc.n_tris} triangles), mask on", "frames_per_step": per_step},
+                               f"({sc.n_parts} parts, {sc.n_tris} triangles), mask on (BASELINE.json configs[1])",
+                   "frames_per_step": per_step, "threshold_m": float(sc.max_diff),
+                   "replace_value_m": float(sc.replace_value), "near_far_m": [0.1, 8.0]},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {per_step} frames, oracle/ruf_oracle.c -O3 -march=native, "
                                    f"OpenMP over {threads} threads (the reference's GL path needs libGL/X11: absent)"},
