@@ -42,6 +42,10 @@ def _sig(lib):
     lib.ruf_facade_get_double.restype = C.c_double
     lib.ruf_facade_parse_urdf.argtypes = [cp, cp, C.c_double, cp, cp, vp, vp, C.c_long, C.POINTER(C.c_long), vp]
     lib.ruf_facade_parse_urdf.restype = C.c_long
+    lib.ruf_facade_tracker_depth_to_buffer.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.ruf_facade_tracker_projection.argtypes = [C.c_int, C.c_int, vp]
+    lib.ruf_facade_tracker_masked_depth_to_mm.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.ruf_facade_last_parse_error.restype = cp
     return lib
 
 
@@ -61,6 +65,28 @@ def _d(a, n):
     return a, a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def tracker_depth_to_buffer(depth_mm: np.ndarray) -> np.ndarray:
+    """OpenNITrackerLoopback::runOnce input conversion (mirror in x, mm -> m), urdf_filtered_tracker.cpp:201-207."""
+    d = np.ascontiguousarray(depth_mm, np.uint16)
+    out = np.empty(d.shape, np.float32)
+    lib().ruf_facade_tracker_depth_to_buffer(C.c_void_p(d.ctypes.data), d.shape[1], d.shape[0], C.c_void_p(out.ctypes.data))
+    return out
+
+
+def tracker_projection(xres: int, yres: int) -> np.ndarray:
+    g = np.zeros(16)
+    lib().ruf_facade_tracker_projection(xres, yres, C.c_void_p(g.ctypes.data))
+    return g
+
+
+def tracker_masked_depth_to_mm(masked: np.ndarray) -> np.ndarray:
+    """...:243-249: truncating m -> mm of getMaskedDepth(), not mirrored back."""
+    m = np.ascontiguousarray(masked, np.float32)
+    out = np.empty(m.shape, np.uint16)
+    lib().ruf_facade_tracker_masked_depth_to_mm(C.c_void_p(m.ctypes.data), m.shape[1], m.shape[0], C.c_void_p(out.ctypes.data))
+    return out
+
+
 def parse_urdf(xml: str, geometry_type: str = "", scale: float = 1.0, ignore=(), resource_root: str = ""):
     """URDF text -> (tri[T,9], tri_part[T], part_models[P,16] with identity TF).  CPU only."""
     L = lib()
@@ -68,7 +94,6 @@ def parse_urdf(xml: str, geometry_type: str = "", scale: float = 1.0, ignore=(),
     n = L.ruf_facade_parse_urdf(xml.encode(), geometry_type.encode(), scale, ",".join(ignore).encode(),
                                 resource_root.encode(), None, None, 0, C.byref(n_parts), None)
     if n < 0:
-        L.ruf_facade_last_parse_error.restype = C.c_char_p
         raise ValueError("URDF failed to parse: " + L.ruf_facade_last_parse_error().decode())
     tri = np.zeros((n, 9), np.float32)
     part = np.zeros(n, np.uint32)

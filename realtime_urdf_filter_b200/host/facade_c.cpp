@@ -155,6 +155,16 @@ RUF_API double ruf_facade_get_double(void *h, const char *name)
   if (n == "height") return f->height_;
   return -1e300;
 }
+// the tracker caller's conversions (src/urdf_filtered_tracker.cpp:201-249)
+RUF_API void ruf_facade_tracker_depth_to_buffer(const uint16_t *mm, int xres, int yres, float *buffer)
+{
+  realtime_urdf_filter::tracker_depth_to_buffer(mm, xres, yres, buffer);
+}
+RUF_API void ruf_facade_tracker_projection(int xres, int yres, double *glTf) { realtime_urdf_filter::tracker_projection(xres, yres, glTf); }
+RUF_API void ruf_facade_tracker_masked_depth_to_mm(const float *masked, int xres, int yres, uint16_t *mm)
+{
+  realtime_urdf_filter::tracker_masked_depth_to_mm(masked, xres, yres, mm);
+}
 static thread_local std::string g_parse_error;
 RUF_API const char *ruf_facade_last_parse_error() { return g_parse_error.c_str(); }
 // URDF parsing alone (no GPU): number of parts / triangles a description would produce

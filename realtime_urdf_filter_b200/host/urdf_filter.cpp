@@ -232,4 +232,38 @@ void RealtimeURDFFilter::filter_callback(const ImageConstPtr &img, const CameraI
   }
 }
 
+void tracker_depth_to_buffer(const uint16_t *depth_mm, int xres, int yres, float *buffer)
+{
+  for (int y = 0; y < yres; ++y)
+    for (int x = 0; x < xres; ++x)
+      buffer[x + y * xres] = (float)(depth_mm[(xres - x - 1) + y * xres] * 0.001);                         // :201-207
+}
+
+void tracker_projection(int xres, int yres, double *glTf)
+{
+  float P[12];                                                                                             // :209-212
+  P[0] = 585.260f; P[1] = 0.0f;     P[2] = 317.387f; P[3] = 0.0f;
+  P[4] = 0.0f;     P[5] = 585.028f; P[6] = 239.264f; P[7] = 0.0f;
+  P[8] = 0.0f;     P[9] = 0.0f;     P[10] = 1.0f;    P[11] = 0.0f;
+  const double fx = P[0], fy = P[5], cx = P[2], cy = P[6];
+  const double far_plane = 8, near_plane = 0.1;                                                            // :218-219
+  for (int i = 0; i < 16; ++i) glTf[i] = 0.0;
+  glTf[0] = -2.0 * fx / xres;                                                                              // :227-236
+  glTf[5] = 2.0 * fy / yres;
+  glTf[8] = 2.0 * (0.5 - cx / xres);
+  glTf[9] = 2.0 * (cy / yres - 0.5);
+  glTf[10] = -(far_plane + near_plane) / (far_plane - near_plane);
+  glTf[14] = -2.0 * far_plane * near_plane / (far_plane - near_plane);
+  glTf[11] = -1;
+}
+
+void tracker_masked_depth_to_mm(const float *masked_depth, int xres, int yres, uint16_t *depth_mm)
+{
+  for (int y = 0; y < yres; ++y)
+    for (int x = 0; x < xres; ++x) {
+      const float v = masked_depth[x + y * xres] * 1000;                                                   // :247
+      depth_mm[x + y * xres] = !(v > 0.0f) ? (uint16_t)0 : (v >= 65535.0f ? (uint16_t)65535 : (uint16_t)v);
+    }
+}
+
 }  // namespace realtime_urdf_filter

@@ -6,6 +6,7 @@
 // Built against host/ros_shim.h here (no ROS in this image); with ROS present the shim types are
 // aliases of the real ones.
 #pragma once
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -91,5 +92,21 @@ class RealtimeURDFFilter {
   const unsigned char *staged_buffer_ = nullptr;
   size_t model_parts_ = 0;
 };
+
+// ---- the second caller of filter(): OpenNITrackerLoopback::runOnce (src/urdf_filtered_tracker.cpp:180-252) ----
+// The tracker is out of scope (OpenNI/NITE + a Kinect), but the conversions it wraps around
+// filter(buffer, glTf, XRes, YRes) + getMaskedDepth() are part of how the path is used, so they are kept here
+// for a maintainer who re-wires it:
+//   tracker_depth_to_buffer   :201-207  buffer[x + y*XRes] = depthMap(XRes - x - 1, y) * 0.001   (mirrored in x;
+//                                        the product is taken in double and rounded to float once)
+//   tracker_projection        :209-236  the hard-coded Kinect intrinsics 585.260 / 585.028 / 317.387 / 239.264
+//                                        (held as float P[12], like the reference) -> glTf[16]
+//   tracker_masked_depth_to_mm :243-249 depthMap_(x, y) = XnDepthPixel(masked_depth[..] * 1000): float product,
+//                                        TRUNCATED (not rounded like filter_callback's convertTo) and NOT mirrored
+//                                        back; values outside [0, 65535] and NaN are undefined in the reference,
+//                                        here NaN and negatives give 0 and larger values saturate
+void tracker_depth_to_buffer(const uint16_t *depth_mm, int xres, int yres, float *buffer);
+void tracker_projection(int xres, int yres, double *glTf);
+void tracker_masked_depth_to_mm(const float *masked_depth, int xres, int yres, uint16_t *depth_mm);
 
 }  // namespace realtime_urdf_filter

@@ -155,3 +155,32 @@ def test_constructor_reads_params_and_logs_fatal_on_missing():
     with facade.FilterNode({}, []) as n:          # missing required params: FATAL logs, construction continues
         log = n.log()
         assert log.count("FATAL") == 3 and n.get("filter_replace_value") == 0.0
+
+
+def test_tracker_caller_conversions():
+    """The second caller of filter() (src/urdf_filtered_tracker.cpp:201-249): mirrored mm -> m in double, the
+    hard-coded intrinsics held as float, and the truncating, un-mirrored m -> mm of the result."""
+    rng = np.random.default_rng(5)
+    mm = rng.integers(0, 65536, (7, 12)).astype(np.uint16)
+    mm[0, :4] = [0, 1, 65535, 739]
+    buf = facade.tracker_depth_to_buffer(mm)
+    want = (mm[:, ::-1].astype(np.float64) * 0.001).astype(np.float32)
+    assert np.array_equal(buf.view(np.uint32), want.view(np.uint32))
+    # not the same thing as filter_callback's float product for every value (cv::Mat::convertTo, :288)
+    all_mm = np.arange(65536, dtype=np.uint16).reshape(1, -1)
+    d = facade.tracker_depth_to_buffer(all_mm)[0, ::-1]
+    f = orc.u16_to_f32(all_mm.reshape(-1))
+    assert 0 < np.count_nonzero(d != f) < 65536
+    # projection: the KAT set of SURVEY.md 8(d), computed from float-held intrinsics
+    g = facade.tracker_projection(640, 480)
+    P = [float(np.float32(585.260)), 0, float(np.float32(317.387)), 0, 0, float(np.float32(585.028)),
+         float(np.float32(239.264)), 0, 0, 0, 1, 0]
+    assert np.array_equal(g, orc.projection_matrix(P, 640, 480)[0])
+    # output: truncation, no mirroring.  Through the tracker's own input conversion an untouched pixel loses
+    # 1 mm for 739 of the 65536 values (SURVEY.md 8f); filter_callback's float product would round-trip all
+    back = facade.tracker_masked_depth_to_mm(d.reshape(1, -1))[0]
+    assert np.array_equal(back, (d * np.float32(1000)).astype(np.uint16))
+    assert np.count_nonzero(back != np.arange(65536)) == 739
+    assert np.array_equal(facade.tracker_masked_depth_to_mm(f.reshape(1, -1))[0], np.arange(65536))
+    edge = np.array([[np.nan, -1.0, 1e9, 65.535, 5.0]], np.float32)
+    assert facade.tracker_masked_depth_to_mm(edge).tolist() == [[0, 0, 65535, 65535, 5000]]
