@@ -30,6 +30,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+{
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_fence_init()
 {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -756,10 +760,20 @@ __device__ __noinline__ uint32_t occlusion_filter(uint32_t cls, int x0, int y0, 
   return cls;
 }
 
+#if RUF_PERSISTENT
+// EXPERIMENT (off by default, not yet measured: profiles/r01_experiments.md "floor probe"): the body below becomes
+// the work of ONE (frame, tile) item of a persistent CTA, see ruf_raster_filter_kernel at the end of this section.
+template <int ENC>
+__device__ __forceinline__ void raster_tile(const Dims &d, const TriRec *__restrict__ big_all,
+                                            const TriRec *__restrict__ bins_all, const uint32_t *__restrict__ ctr_all,
+                                            uint32_t *status, const ShaderParams &sp, const FrameBuffers &fb,
+                                            const int frame, const int tile_bx, const int tile_by, const uint2 nfb_in)
+#else
 template <int ENC>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
                          const uint32_t *__restrict__ ctr_all, uint32_t *status, ShaderParams sp, FrameBuffers fb)
+#endif
 {
   // 8 warps rasterise and shade.  The tile's record list streams into a shared-memory ring by bulk async
   // copies (TMA): thread 0 starts the first kStages chunks, later refills are issued by whichever warp
@@ -779,14 +793,23 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ float s_bigz[kRasterThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if RUF_PERSISTENT
+  const int tile = tile_by * d.tiles_x + tile_bx;
+  const int tile_x0 = tile_bx * kTileW, tile_y0 = tile_by * kTileH;
+#else
   const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
   const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
+#endif
   const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
   // records binned to this tile (CTA-uniform): nf at the front of its list (triangles facing the camera, drawn
   // first), nb at the back (facing away: drawn last and depth-culled against what is already there).  Two
   // thirds of the tiles of a typical frame see only the background quad: they take the register-only path
   // below (no ring, no z tile, no CTA-wide barrier).
+#if RUF_PERSISTENT == 2
+  const uint2 nfb = nfb_in;                     // requested by the wrapper one item ahead
+#else
   const uint2 nfb = __ldg(reinterpret_cast<const uint2 *>(ctr + kCtrWords) + tile);
+#endif
   uint32_t nf = nfb.x, nb = nfb.y;
   const bool list_overflow = nf + nb > d.cap_tile;            // the two runs met: the host grows cap_tile and retries
   nf = min(nf, d.cap_tile);
@@ -1092,6 +1115,14 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
     }
     consumer_bar_sync();                      // every record of the tile has been rasterised
+#if RUF_PERSISTENT
+    // every wait and every arrive of this item is behind us: hand the barriers back so that the next item of this
+    // CTA can initialise them again
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < kStages; ++s) { mbar_inval(&full_bar[s]); mbar_inval(&empty_bar[s]); }
+    }
+#endif
   }
 
   // Every thread owns 8 consecutive pixels of kRowsPerThread tile rows (32 rows apart): fetch the rasterised
@@ -1272,6 +1303,36 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
   }
 }
+
+#if RUF_PERSISTENT
+// Persistent form: gridDim.x CTAs (a few per SM, coprime with the tile count so that every CTA sees every tile
+// position) walk the (frame, tile) items of the batch.  One CTA barrier separates two items: the classification
+// bytes, the z tile and the ring's barriers are shared-memory state of the item.
+template <int ENC>
+__global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
+ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
+                         const uint32_t *__restrict__ ctr_all, uint32_t *status, ShaderParams sp, FrameBuffers fb,
+                         int n_items)
+{
+  // RUF_PERSISTENT == 2: the (front, back) record counts of the NEXT item are requested before the current item
+  // is worked on, which takes one global round trip out of every item's dependency chain
+  auto counts_of = [&](int item) {
+    const int frame = item / d.ntiles, tile = item - frame * d.ntiles;
+    return __ldg(reinterpret_cast<const uint2 *>(ctr_all + (size_t)frame * d.ctr_stride + kCtrWords) + tile);
+  };
+  uint2 nfb = make_uint2(0u, 0u);
+  if (RUF_PERSISTENT == 2 && (int)blockIdx.x < n_items) nfb = counts_of(blockIdx.x);
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int frame = item / d.ntiles, tile = item - frame * d.ntiles;
+    const int by = tile / d.tiles_x;
+    uint2 nfb_next = make_uint2(0u, 0u);
+    if (RUF_PERSISTENT == 2 && item + (int)gridDim.x < n_items) nfb_next = counts_of(item + gridDim.x);
+    raster_tile<ENC>(d, big_all, bins_all, ctr_all, status, sp, fb, frame, tile - by * d.tiles_x, by, nfb);
+    __syncthreads();
+    nfb = nfb_next;
+  }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // host-side launcher for one batch
@@ -1505,11 +1566,30 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (ev) cudaEventRecord(ev[2], s);
   }
   {
+#if RUF_PERSISTENT
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long n_items = (long long)d.ntiles * n_frames;
+    long long g = (long long)sm_count * RUF_RASTER_MIN_BLOCKS;
+    if (g > n_items) g = n_items;
+    auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+    while (g > 1 && gcd(g, d.ntiles) != 1) --g;
+    dim3 grid((unsigned)g);
+    if (enc == 1)
+      ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb, (int)n_items);
+    else
+      ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb, (int)n_items);
+#else
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (enc == 1)
       ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
     else
       ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
+#endif
     ++launches;
     if ((err = check("ruf_raster_filter_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[3], s);
