@@ -183,9 +183,13 @@ struct XmlParser {
     return o;
   }
   static bool name_char(char c) { return std::isalnum((unsigned char)c) || c == '_' || c == ':' || c == '-' || c == '.'; }
+  int depth = 0;
+  struct DepthGuard { int &d; explicit DepthGuard(int &x) : d(x) { ++d; } ~DepthGuard() { --d; } };
   bool parse_element(XmlNode &n)
   {
     // s[i] == '<'
+    DepthGuard guard(depth);
+    if (depth > 256) { err = "elements nested deeper than 256"; return false; }   // recursion bound for hostile input
     ++i;
     size_t b = i;
     while (i < s.size() && name_char(s[i])) ++i;

@@ -184,3 +184,33 @@ def test_tracker_caller_conversions():
     assert np.array_equal(facade.tracker_masked_depth_to_mm(f.reshape(1, -1))[0], np.arange(65536))
     edge = np.array([[np.nan, -1.0, 1e9, 65.535, 5.0]], np.float32)
     assert facade.tracker_masked_depth_to_mm(edge).tolist() == [[0, 0, 65535, 65535, 5000]]
+
+
+def test_urdf_parser_survives_mutated_and_hostile_input():
+    """The hand-written XML subset reader must reject, never crash: seeded mutations of the example URDF,
+    truncations, and nesting far beyond what a robot description has."""
+    import random
+    base = synth.example_urdf_xml()
+    rnd = random.Random(11)
+    chars = '<>/="\' \n&;!-?abz019.'
+    outcomes = {"ok": 0, "rejected": 0}
+    for _ in range(400):
+        s = list(base if rnd.random() < 0.7 else base[:rnd.randrange(len(base))])
+        for _ in range(rnd.randrange(1, 6)):
+            i = rnd.randrange(len(s)) if s else 0
+            op = rnd.randrange(3)
+            if op == 0 and s:
+                del s[i:i + rnd.randrange(1, 20)]
+            elif op == 1:
+                s[i:i] = [rnd.choice(chars) for _ in range(rnd.randrange(1, 5))]
+            elif s:
+                s[i] = rnd.choice(chars)
+        try:
+            facade.parse_urdf("".join(s))
+            outcomes["ok"] += 1
+        except ValueError:
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 100 and outcomes["ok"] > 0
+    deep = "<robot name='d'>" + "<a>" * 100000 + "</a>" * 100000 + "</robot>"
+    with pytest.raises(ValueError, match="nested deeper"):
+        facade.parse_urdf(deep)
