@@ -62,16 +62,28 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    extra = os.environ.get("RUF_EXTRA_NVCC", "").split()
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(PKG_DIR, "..", "include"), "-o", LIB_PATH, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    # Several ranks of one torchrun job may arrive here together (a snapshot whose sources look newer than the
+    # library): one of them builds under an exclusive lock, into a temporary file that replaces the library
+    # atomically; the others wait and then find it up to date.
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB_PATH
+        tmp = f"{LIB_PATH}.tmp{os.getpid()}"
+        extra = os.environ.get("RUF_EXTRA_NVCC", "").split()
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(PKG_DIR, "..", "include"), "-o", tmp, *sources()]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        os.replace(tmp, LIB_PATH)
+        if verbose:
+            print(res.stderr)
     return LIB_PATH
 
 
