@@ -154,16 +154,17 @@ def lookat():
 
 def view_matrix(offset_q, offset_t, cam_q, cam_t, camera_tx=0.0, camera_ty=0.0):
     out = np.zeros(16)
-    load().ruf_view_matrix(_dp(_as_f64(offset_q, 4)), _dp(_as_f64(offset_t, 3)), _dp(_as_f64(cam_q, 4)),
-                           _dp(_as_f64(cam_t, 3)), float(camera_tx), float(camera_ty), _dp(out))
+    # every converted array is bound to a local: a temporary would be freed before the C call reads it
+    oq, ot, cq, ct = _as_f64(offset_q, 4), _as_f64(offset_t, 3), _as_f64(cam_q, 4), _as_f64(cam_t, 3)
+    load().ruf_view_matrix(_dp(oq), _dp(ot), _dp(cq), _dp(ct), float(camera_tx), float(camera_ty), _dp(out))
     return out
 
 
 def part_model(link_q, link_t, off_q=(0, 0, 0, 1), off_t=(0, 0, 0), suffix=None):
     out = np.zeros(16)
     sfx = None if suffix is None else _as_f64(suffix, 16)
-    load().ruf_part_model(_dp(_as_f64(link_q, 4)), _dp(_as_f64(link_t, 3)), _dp(_as_f64(off_q, 4)),
-                          _dp(_as_f64(off_t, 3)), None if sfx is None else _dp(sfx), _dp(out))
+    lq, lt, oq, ot = _as_f64(link_q, 4), _as_f64(link_t, 3), _as_f64(off_q, 4), _as_f64(off_t, 3)
+    load().ruf_part_model(_dp(lq), _dp(lt), _dp(oq), _dp(ot), None if sfx is None else _dp(sfx), _dp(out))
     return out
 
 
@@ -283,25 +284,42 @@ class Context:
         out = np.empty_like(d)
         mask = np.empty((self.height, self.width), np.uint8) if want_mask else None
         pm = _as_f64(part_models, 16 * self.n_parts)
-        self._check(self._lib.ruf_filter(self._h, d.ctypes.data, enc, _as_f64(proj, 16).ctypes.data,
-                                         _as_f64(view, 16).ctypes.data, pm.ctypes.data if pm.size else None,
+        pr, vw = _as_f64(proj, 16), _as_f64(view, 16)     # locals: the copies must outlive the call
+        self._check(self._lib.ruf_filter(self._h, d.ctypes.data, enc, pr.ctypes.data,
+                                         vw.ctypes.data, pm.ctypes.data if pm.size else None,
                                          max_diff, replace_value, out.ctypes.data,
                                          mask.ctypes.data if want_mask else None))
         return out, mask
 
+    def _frames(self, a, dtype, n, what):
+        """A caller-supplied (n, H, W) buffer: right dtype, C-contiguous, right shape -- never converted silently
+        (an output must be written in place)."""
+        if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.c_contiguous or \
+                a.shape != (n, self.height, self.width):
+            raise ValueError(f"{what} must be a C-contiguous {np.dtype(dtype).name} array of shape "
+                             f"({n}, {self.height}, {self.width})")
+        return a
+
     def filter_batch_host(self, depth, proj, views, part_models, max_diff, replace_value, out=None, mask=None,
                           want_mask=True):
         """n frames with host buffers (numpy arrays or raw pointers via .ctypes.data)."""
+        depth = np.asarray(depth)
         enc = ENC_U16_MM if depth.dtype == np.uint16 else ENC_F32_M
+        dt = self._enc_dtype(enc)
+        if depth.ndim != 3 or depth.shape[1:] != (self.height, self.width):
+            raise ValueError(f"depth must have shape (n, {self.height}, {self.width}), got {depth.shape}")
+        depth = np.ascontiguousarray(depth, dt)        # float64 / strided input is converted like Context.filter does
         n = depth.shape[0]
-        if out is None:
-            out = np.empty_like(depth)
+        out = np.empty_like(depth) if out is None else self._frames(out, dt, n, "out")
         if mask is None and want_mask:
             mask = np.empty(depth.shape, np.uint8)
+        elif mask is not None:
+            self._frames(mask, np.uint8, n, "mask")
         v = _as_f64(views, 16 * n)
         pm = _as_f64(part_models, 16 * n * self.n_parts)
+        pr = _as_f64(proj, 16)
         self._check(self._lib.ruf_filter_batch_host(self._h, n, depth.ctypes.data, enc,
-                                                    _as_f64(proj, 16).ctypes.data, v.ctypes.data,
+                                                    pr.ctypes.data, v.ctypes.data,
                                                     pm.ctypes.data if pm.size else None, max_diff, replace_value,
                                                     out.ctypes.data, mask.ctypes.data if mask is not None else None))
         return out, mask
@@ -323,9 +341,10 @@ class Context:
         axis = _as_f64(axis, 3 * n)
         pl = np.ascontiguousarray(part_link, np.int32)
         plocal = _as_f64(part_local, 16 * self.n_parts)
+        mount, pre = _as_f64(cam_mount, 16), _as_f64(view_pre, 16)
         self._check(self._lib.ruf_set_kinematics(self._h, n, parent.ctypes.data, jt.ctypes.data, origin.ctypes.data,
                                                  axis.ctypes.data, pl.ctypes.data, plocal.ctypes.data, int(cam_link),
-                                                 _as_f64(cam_mount, 16).ctypes.data, _as_f64(view_pre, 16).ctypes.data))
+                                                 mount.ctypes.data, pre.ctypes.data))
         self.n_links = n
 
     def fk_batch_device(self, n_frames, d_joint_q, tx, ty, d_part_model_out, d_view_out):

@@ -63,7 +63,8 @@ struct ruf_context {
   Kinematics kin{};
   void *kin_blob = nullptr;          // one device allocation holding all kinematics arrays
   double *fk_links = nullptr, *fk_pm = nullptr, *fk_view = nullptr;
-  int fk_frames = 0;
+  int fk_frames = 0;                 // what the FK buffers were sized for: frames x links, frames x parts
+  int fk_links_n = 0, fk_parts_n = 0;
 
   ruf_stats stats{};
   int last_frames = 0;
@@ -633,16 +634,21 @@ static int ensure_fk_buffers(ruf_context *c, int frames)
 {
   if (!c->kin_blob) return fail(c, RUF_ERR_INVALID, "no kinematics loaded (ruf_set_kinematics)");
   if (c->kin.n_parts != c->n_parts) return fail(c, RUF_ERR_INVALID, "kinematics were set for another model");
-  if (c->fk_frames >= frames) return RUF_OK;
+  // the buffers hold frames x links and frames x parts matrices: a new model or new kinematics with more of
+  // either needs larger ones even when the frame count did not grow
+  if (c->fk_frames >= frames && c->fk_links_n >= c->kin.n_links && c->fk_parts_n >= c->n_parts) return RUF_OK;
+  if (frames < c->fk_frames) frames = c->fk_frames;
   RUF_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaFree(c->fk_links); cudaFree(c->fk_pm); cudaFree(c->fk_view);
   c->fk_links = c->fk_pm = c->fk_view = nullptr;
-  c->fk_frames = 0;
+  c->fk_frames = 0; c->fk_links_n = 0; c->fk_parts_n = 0;
   const size_t f = (size_t)frames;
   RUF_CUDA(c, cudaMalloc(&c->fk_links, f * (c->kin.n_links > 0 ? c->kin.n_links : 1) * 128));
   RUF_CUDA(c, cudaMalloc(&c->fk_pm, f * (c->n_parts > 0 ? c->n_parts : 1) * 128));
   RUF_CUDA(c, cudaMalloc(&c->fk_view, f * 128));
   c->fk_frames = frames;
+  c->fk_links_n = c->kin.n_links;
+  c->fk_parts_n = c->n_parts;
   return RUF_OK;
 }
 

@@ -83,9 +83,6 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #ifndef RUF_MIN_BACK_BATCHES
 #define RUF_MIN_BACK_BATCHES 6u
 #endif
-#ifndef RUF_PERSISTENT
-#define RUF_PERSISTENT 0      // EXPERIMENT: raster kernel as persistent CTAs walking (frame, tile) items (unmeasured)
-#endif
 #ifndef RUF_OCCLUDE_MIN
 #define RUF_OCCLUDE_MIN 8
 #endif

@@ -30,10 +30,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_inval(uint64_t *bar)
-{
-  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_fence_init()
 {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -715,6 +711,48 @@ __device__ __forceinline__ uint32_t f32_to_u16(float x)
   return (uint32_t)min(max(r, 0), 65535);
 }
 
+// ---- fragment stage helpers -----------------------------------------------------------------------------
+// PRMT with the sign-replicate selector bit (nibble | 8: the byte becomes 0xff / 0x00 after the msb of the source byte)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// 16UC1 input: sensor = float(raw) * 0.001f (convertTo(CV_32F, 0.001), src/urdf_filter.cpp:288) is strictly increasing
+// in raw, so `sensor > thr` (frag:23) is `raw > R` with R = the largest raw whose sensor value is <= thr (-1: every
+// raw is filtered, 65535: none is; thr = NaN compares false for every raw, like the float compare).  floor(thr * 1000)
+// is within one step of R (two roundings of relative size 2^-24 on values below 65536); the two probes settle it with
+// the float expressions of the shader themselves.  tests/test_oracle_kat.py::test_u16_threshold_* checks every
+// boundary of all 65536 raw values against the float compare.
+__device__ __forceinline__ int u16_threshold(float thr)
+{
+  if (!(thr < 65.536f)) return 65535;                 // also NaN, +inf
+  if (thr < 0.0f) return -1;
+  int c = min(__float2int_rd(thr * 1000.0f), 65535);
+  if ((float)c * 0.001f > thr) --c;
+  else if (c < 65535 && !((float)(c + 1) * 0.001f > thr)) ++c;
+  return c;
+}
+// 8 pixels of one image row that share ONE virtual depth (all background, or a never-drawn run), 16UC1: per
+// 32-bit word two subtractions, one PRMT (sign -> 0xffff / 0 per pixel) and one LOP3 instead of the per-pixel
+// int->float conversions and float compares.  R < 0x7fff0000 so that R - raw cannot wrap.
+__device__ __forceinline__ void shade_row_u16_uniform(const uint4 sens, int R, uint32_t repl2, uint4 &o, uint2 &mq)
+{
+  const uint32_t w[4] = {sens.x, sens.y, sens.z, sens.w};
+  uint32_t M[4], ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t dlo = (uint32_t)(R - (int)(w[j] & 0xffffu));     // negative <=> raw > R <=> filtered
+    const uint32_t dhi = (uint32_t)(R - (int)(w[j] >> 16));
+    M[j] = prmt(dlo, dhi, 0xffbbu);                                  // 0xffff per filtered pixel
+    ow[j] = (w[j] & ~M[j]) | (repl2 & M[j]);                         // unfiltered: the input bits (round trip = identity)
+  }
+  o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  mq.x = prmt(M[0], M[1], 0x6420u);                                  // one 0 / 255 byte per pixel
+  mq.y = prmt(M[2], M[3], 0x6420u);
+}
+
 struct FragOut { float depth; uint32_t mask; };
 // include/shaders/urdf_filter.frag:19-35 for the fragment that survived GL_LESS.
 __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const ShaderParams &sp)
@@ -760,20 +798,10 @@ __device__ __noinline__ uint32_t occlusion_filter(uint32_t cls, int x0, int y0, 
   return cls;
 }
 
-#if RUF_PERSISTENT
-// EXPERIMENT (off by default, not yet measured: profiles/r01_experiments.md "floor probe"): the body below becomes
-// the work of ONE (frame, tile) item of a persistent CTA, see ruf_raster_filter_kernel at the end of this section.
-template <int ENC>
-__device__ __forceinline__ void raster_tile(const Dims &d, const TriRec *__restrict__ big_all,
-                                            const TriRec *__restrict__ bins_all, const uint32_t *__restrict__ ctr_all,
-                                            uint32_t *status, const ShaderParams &sp, const FrameBuffers &fb,
-                                            const int frame, const int tile_bx, const int tile_by, const uint2 nfb_in)
-#else
 template <int ENC>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
                          const uint32_t *__restrict__ ctr_all, uint32_t *status, ShaderParams sp, FrameBuffers fb)
-#endif
 {
   // 8 warps rasterise and shade.  The tile's record list streams into a shared-memory ring by bulk async
   // copies (TMA): thread 0 starts the first kStages chunks, later refills are issued by whichever warp
@@ -793,23 +821,14 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ float s_bigz[kRasterThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#if RUF_PERSISTENT
-  const int tile = tile_by * d.tiles_x + tile_bx;
-  const int tile_x0 = tile_bx * kTileW, tile_y0 = tile_by * kTileH;
-#else
   const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
   const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
-#endif
   const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
   // records binned to this tile (CTA-uniform): nf at the front of its list (triangles facing the camera, drawn
   // first), nb at the back (facing away: drawn last and depth-culled against what is already there).  Two
   // thirds of the tiles of a typical frame see only the background quad: they take the register-only path
   // below (no ring, no z tile, no CTA-wide barrier).
-#if RUF_PERSISTENT == 2
-  const uint2 nfb = nfb_in;                     // requested by the wrapper one item ahead
-#else
   const uint2 nfb = __ldg(reinterpret_cast<const uint2 *>(ctr + kCtrWords) + tile);
-#endif
   uint32_t nf = nfb.x, nb = nfb.y;
   const bool list_overflow = nf + nb > d.cap_tile;            // the two runs met: the host grows cap_tile and retries
   nf = min(nf, d.cap_tile);
@@ -899,9 +918,15 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
     if (occlude) cls = occlusion_filter(cls, ox0, oy0, oz0, ogx, ogy, tpx, tpy, tid, &s_zcut, &s_zown);
     s_bigcls[tid] = (uint8_t)cls;
+    return cls;
   };
-  classify(0);
-  __syncthreads();          // the classification, the cleared z tile and the ring's barriers are visible
+  const uint32_t cls0 = classify(0);
+  // the classification, the cleared z tile and the ring's barriers are visible after this barrier; it also says whether
+  // any big-list record needs per-pixel work in this tile (class 1 / 2: a wall, a clipped triangle)
+  const bool big_per_pixel = __syncthreads_or(cls0 == 1u || cls0 == 2u) != 0;
+  // FLAT tile (CTA-uniform; two thirds of the tiles of a typical frame): no binned record and only constant-depth
+  // covering records in the big list (the background quad) -> one virtual depth for all 4096 pixels
+  const bool flat = cnt == 0 && !big_per_pixel && nbig <= (uint32_t)kRasterThreads;
 
   if (cnt) {
     {
@@ -1115,20 +1140,21 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
     }
     consumer_bar_sync();                      // every record of the tile has been rasterised
-#if RUF_PERSISTENT
-    // every wait and every arrive of this item is behind us: hand the barriers back so that the next item of this
-    // CTA can initialise them again
-    if (tid == 0) {
-#pragma unroll
-      for (int s = 0; s < kStages; ++s) { mbar_inval(&full_bar[s]); mbar_inval(&empty_bar[s]); }
-    }
-#endif
   }
 
   // Every thread owns 8 consecutive pixels of kRowsPerThread tile rows (32 rows apart): fetch the rasterised
   // depths, merge the per-frame big list on registers (one walk over the classified records for all rows),
   // then run the fragment stage row by row.
   float zall[kRowsPerThread][8];
+  if (flat) {
+    float zt = 1.0f;                                           // glClear depth
+    for (uint32_t b = 0; b < nbig; ++b)
+      if (s_bigcls[b] == 3) zt = fminf(zt, s_bigz[b]);
+#pragma unroll
+    for (int half = 0; half < kRowsPerThread; ++half)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) zall[half][i] = zt;
+  } else {
 #pragma unroll
   for (int half = 0; half < kRowsPerThread; ++half) {
     if (cnt) {
@@ -1201,94 +1227,96 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
   }
 
+  }   // !flat
+
+  // ---- fused fragment stage (include/shaders/urdf_filter.frag:19-35): 8 pixels per thread and row, vector loads/stores ----
+  const uint32_t repl_u16 = f32_to_u16(sp.replace_value);     // convertTo(CV_16U, 1000) of the replaced pixels, :311
+  const uint32_t repl2 = repl_u16 | (repl_u16 << 16);
+  const float kInf = __int_as_float(0x7f800000);
 #pragma unroll
   for (int half = 0; half < kRowsPerThread; ++half) {
     const int trow = prow + 32 * half;
     const int gy = tile_y0 + trow, gx = tile_x0 + pcol;
-    const size_t pix = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
-    const bool full = fb.vec_ok && gy < d.H && (gx + 8 <= d.W);
-    uint4 sens0 = make_uint4(0u, 0u, 0u, 0u), sens1 = make_uint4(0u, 0u, 0u, 0u);
-    auto load_sensor = [&]() {
-      if (full) {
-        if (ENC == 1) {
-          sens0 = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + pix));
-        } else {
-          const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + pix);
-          sens0 = __ldg(p); sens1 = __ldg(p + 1);
-        }
-      }
-    };
-    const float (&zr)[8] = zall[half];
-
-    // ---- fused fragment stage: 8 pixels per thread, vector loads/stores ----
     if (gy >= d.H || gx >= d.W) continue;
-    const size_t base = pix;
-    const float (&zw)[8] = zr;
-    if (full) {
-      load_sensor();
-      // to_linear_depth (frag:14-17,22) and the threshold (frag:23) once per distinct z of this thread's run:
-      // background pixels share one window z, so most threads divide once instead of eight times.  Never-drawn
+    const size_t base = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
+    const float (&zw)[8] = zall[half];
+    if (fb.vec_ok && gx + 8 <= d.W) {
+      // One virtual depth for the whole run (background, or never drawn)?  z values are clamped to +0 / come out of
+      // fminf, so equal floats have equal bits.
+      uint32_t zdiff = 0;
+#pragma unroll
+      for (int i = 1; i < 8; ++i) zdiff |= __float_as_uint(zw[i]) ^ __float_as_uint(zw[0]);
+      // to_linear_depth (frag:14-17,22) and the threshold (frag:23) once per distinct z of the run.  Never-drawn
       // pixels (z = 1: clear colour, :566) get +inf, so that `sensor > thr` is false for them.
       float thr[8];
-      {
-        float zprev = 1.0f, tprev = __int_as_float(0x7f800000);
-  #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+      thr[0] = (zw[0] == 1.0f) ? kInf : (sp.k1 / (zw[0] - sp.k2)) - sp.max_diff;
+      if (zdiff) {
+        float zprev = zw[0], tprev = thr[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
           if (zw[i] != zprev) {
-            tprev = (zw[i] == 1.0f) ? __int_as_float(0x7f800000) : (sp.k1 / (zw[i] - sp.k2)) - sp.max_diff;
+            tprev = (zw[i] == 1.0f) ? kInf : (sp.k1 / (zw[i] - sp.k2)) - sp.max_diff;
             zprev = zw[i];
           }
           thr[i] = tprev;
         }
       }
-      uint32_t om[8];
+      uint2 mq;
       if (ENC == 1) {
-        const uint32_t w[4] = {sens0.x, sens0.y, sens0.z, sens0.w};
-        const uint32_t repl = f32_to_u16(sp.replace_value);       // convertTo(CV_16U, 1000) of the replaced pixels, :311
-        uint32_t u[8];
-  #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t raw = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
-          const float sensor = (float)raw * 0.001f;               // convertTo(CV_32F, 0.001), :288
-          const bool drawn = zw[i] != 1.0f;                       // else clear colour: depth 0, mask 0 (:566)
-          const bool sflt = sensor > thr[i];                      // frag:23
-          // an unfiltered pixel is sat_u16(rint((u * 0.001f) * 1000.f)), which is u itself for every
-          // 16-bit u (exhaustively checked: tests/test_oracle_encodings.py::test_u16_roundtrip_identity_all_65536)
-          u[i] = drawn ? (sflt ? repl : raw) : 0u;
-          om[i] = sflt ? 255u : 0u;
-        }
+        const uint4 sens = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + base));
         uint4 o;
-        o.x = u[0] | (u[1] << 16); o.y = u[2] | (u[3] << 16); o.z = u[4] | (u[5] << 16); o.w = u[6] | (u[7] << 16);
+        if (!zdiff) {
+          if (zw[0] == 1.0f) { o = make_uint4(0u, 0u, 0u, 0u); mq = make_uint2(0u, 0u); }   // clear colour: depth 0, mask 0
+          else shade_row_u16_uniform(sens, u16_threshold(thr[0]), repl2, o, mq);
+        } else {
+          const uint32_t w[4] = {sens.x, sens.y, sens.z, sens.w};
+          uint32_t u[8], om[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t raw = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+            const float sensor = (float)raw * 0.001f;               // convertTo(CV_32F, 0.001), :288
+            const bool drawn = zw[i] != 1.0f;                       // else clear colour: depth 0, mask 0 (:566)
+            const bool sflt = sensor > thr[i];                      // frag:23
+            // an unfiltered pixel is sat_u16(rint((u * 0.001f) * 1000.f)), which is u itself for every
+            // 16-bit u (exhaustively checked: tests/test_oracle_encodings.py::test_u16_roundtrip_identity_all_65536)
+            u[i] = drawn ? (sflt ? repl_u16 : raw) : 0u;
+            om[i] = sflt ? 255u : 0u;
+          }
+          o.x = u[0] | (u[1] << 16); o.y = u[2] | (u[3] << 16); o.z = u[4] | (u[5] << 16); o.w = u[6] | (u[7] << 16);
+          mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
+          mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
+        }
         *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
       } else {
+        const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + base);
+        const uint4 sens0 = __ldg(p), sens1 = __ldg(p + 1);
         const float sensor[8] = {__uint_as_float(sens0.x), __uint_as_float(sens0.y), __uint_as_float(sens0.z),
                                  __uint_as_float(sens0.w), __uint_as_float(sens1.x), __uint_as_float(sens1.y),
                                  __uint_as_float(sens1.z), __uint_as_float(sens1.w)};
         float od[8];
-  #pragma unroll
+        uint32_t om[8];
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const bool drawn = zw[i] != 1.0f;
-          const bool sflt = sensor[i] > thr[i];
+          const float t = zdiff ? thr[i] : thr[0];
+          const bool drawn = zdiff ? (zw[i] != 1.0f) : (zw[0] != 1.0f);
+          const bool sflt = sensor[i] > t;
           od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
           om[i] = sflt ? 255u : 0u;
         }
         float4 *po = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
         po[0] = make_float4(od[0], od[1], od[2], od[3]);
         po[1] = make_float4(od[4], od[5], od[6], od[7]);
-      }
-      if (fb.mask_out) {
-        uint2 mq;
         mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
         mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
-        *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
       }
+      if (fb.mask_out) *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
       if (fb.zbuf_out) {
         float4 *p = reinterpret_cast<float4 *>(fb.zbuf_out + base);
         p[0] = make_float4(zw[0], zw[1], zw[2], zw[3]);
         p[1] = make_float4(zw[4], zw[5], zw[6], zw[7]);
       }
     } else {
-  #pragma unroll
+#pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (gx + i >= d.W) break;
         float sensor;
@@ -1303,36 +1331,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
   }
 }
-
-#if RUF_PERSISTENT
-// Persistent form: gridDim.x CTAs (a few per SM, coprime with the tile count so that every CTA sees every tile
-// position) walk the (frame, tile) items of the batch.  One CTA barrier separates two items: the classification
-// bytes, the z tile and the ring's barriers are shared-memory state of the item.
-template <int ENC>
-__global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
-ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
-                         const uint32_t *__restrict__ ctr_all, uint32_t *status, ShaderParams sp, FrameBuffers fb,
-                         int n_items)
-{
-  // RUF_PERSISTENT == 2: the (front, back) record counts of the NEXT item are requested before the current item
-  // is worked on, which takes one global round trip out of every item's dependency chain
-  auto counts_of = [&](int item) {
-    const int frame = item / d.ntiles, tile = item - frame * d.ntiles;
-    return __ldg(reinterpret_cast<const uint2 *>(ctr_all + (size_t)frame * d.ctr_stride + kCtrWords) + tile);
-  };
-  uint2 nfb = make_uint2(0u, 0u);
-  if (RUF_PERSISTENT == 2 && (int)blockIdx.x < n_items) nfb = counts_of(blockIdx.x);
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int frame = item / d.ntiles, tile = item - frame * d.ntiles;
-    const int by = tile / d.tiles_x;
-    uint2 nfb_next = make_uint2(0u, 0u);
-    if (RUF_PERSISTENT == 2 && item + (int)gridDim.x < n_items) nfb_next = counts_of(item + gridDim.x);
-    raster_tile<ENC>(d, big_all, bins_all, ctr_all, status, sp, fb, frame, tile - by * d.tiles_x, by, nfb);
-    __syncthreads();
-    nfb = nfb_next;
-  }
-}
-#endif
 
 // ------------------------------------------------------------------------------------------
 // host-side launcher for one batch
@@ -1566,30 +1564,11 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (ev) cudaEventRecord(ev[2], s);
   }
   {
-#if RUF_PERSISTENT
-    static int sm_count = 0;
-    if (!sm_count) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    const long long n_items = (long long)d.ntiles * n_frames;
-    long long g = (long long)sm_count * RUF_RASTER_MIN_BLOCKS;
-    if (g > n_items) g = n_items;
-    auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
-    while (g > 1 && gcd(g, d.ntiles) != 1) --g;
-    dim3 grid((unsigned)g);
-    if (enc == 1)
-      ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb, (int)n_items);
-    else
-      ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb, (int)n_items);
-#else
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (enc == 1)
       ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
     else
       ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
-#endif
     ++launches;
     if ((err = check("ruf_raster_filter_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[3], s);

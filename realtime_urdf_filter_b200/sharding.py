@@ -33,21 +33,27 @@ def broadcast_arrays(arrays: dict | None, src: int, device, rank: int | None = N
     (names are fixed by the caller's order; shapes/dtypes travel in an int64 tensor), then one
     broadcast per buffer.  On `src`, `arrays` holds the data; elsewhere it may be None."""
     rank = dist.get_rank() if rank is None and dist.is_initialized() else (rank or 0)
-    dtypes = [np.float32, np.float64, np.int16, np.int32, np.int64, np.uint8]
+    # uint16 (16UC1 depth) and uint32 (tri_part of ruf_set_model) travel as their signed twins: torch has no
+    # arithmetic on them, and the payload is moved as raw bytes anyway
+    dtypes = [np.float32, np.float64, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32]
+    as_torch = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32}
     MAXN, MAXD = 16, 6
-    hdr = torch.zeros((MAXN, MAXD + 2), dtype=torch.int64, device=device)
+    # row MAXN carries the entry count explicitly (a 0-d array is a legal entry: ndim alone cannot say "absent")
+    hdr = torch.zeros((MAXN + 1, MAXD + 2), dtype=torch.int64, device=device)
     names = None
     if rank == src:
         names = list(arrays.keys())
         assert len(names) <= MAXN
         for i, k in enumerate(names):
-            a = arrays[k]
+            a = arrays[k] = np.asarray(arrays[k])
+            assert a.ndim <= MAXD, f"{k}: more than {MAXD} dimensions"
             hdr[i, 0] = a.ndim
             hdr[i, 1] = [np.dtype(d) for d in dtypes].index(a.dtype)
             for j, s in enumerate(a.shape):
                 hdr[i, 2 + j] = s
+        hdr[MAXN, 0] = len(names)
     _bcast(hdr, src)
-    n = int((hdr[:, 0] > 0).sum())
+    n = int(hdr[MAXN, 0])
     obj = [names]
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast_object_list(obj, src, device=torch.device(device) if not isinstance(device, torch.device) else device)
@@ -55,14 +61,19 @@ def broadcast_arrays(arrays: dict | None, src: int, device, rank: int | None = N
     out = {}
     h = hdr.cpu().numpy()
     for i in range(n):
-        nd, dt = int(h[i, 0]), dtypes[int(h[i, 1])]
+        nd, dt = int(h[i, 0]), np.dtype(dtypes[int(h[i, 1])])
+        dt = np.dtype(as_torch.get(dt, dt))
         shape = tuple(int(v) for v in h[i, 2:2 + nd])
         if rank == src:
-            t = torch.from_numpy(np.ascontiguousarray(arrays[names[i]])).to(device)
+            a = arrays[names[i]]
+            a = a if a.ndim == 0 else np.ascontiguousarray(a)      # ascontiguousarray would make a 0-d array 1-d
+            t = torch.from_numpy(np.array(a).view(dt)).to(device)
         else:
             t = torch.empty(shape, dtype=torch.from_numpy(np.zeros(1, dt)).dtype, device=device)
         # transport as raw bytes: every backend (nccl, gloo) moves uint8, not every one moves int16
-        _bcast(t.view(torch.uint8) if t.numel() else t, src)
+        # (a 0-d tensor cannot be viewed as bytes: it goes through a 1-element view)
+        flat = t.reshape(-1) if t.dim() == 0 else t
+        _bcast(flat.view(torch.uint8) if flat.numel() else flat, src)
         out[names[i]] = t
     return out
 

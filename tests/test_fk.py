@@ -96,3 +96,47 @@ def test_kinematics_argument_checks():
             ctx.set_kinematics(**{k_: bad[k_] for k_ in ("parent", "joint_type", "origin", "axis", "part_link",
                                                         "part_local", "cam_link", "cam_mount", "view_pre")})
         assert e.value.code == ruf.RUF_ERR_INVALID
+
+
+@pytest.mark.gpu
+def test_fk_buffers_follow_a_larger_model():
+    """the library's internal FK buffers are frames x links / frames x parts; a second model with more
+    links and parts (same frame count) must get larger buffers, not write past the old ones."""
+    import torch
+    dev = torch.device("cuda:0")
+    KEYS = ("parent", "joint_type", "origin", "axis", "part_link", "part_local", "cam_link", "cam_mount", "view_pre")
+    small, large = helpers.scene("example"), helpers.scene("pr2_small")
+    assert large.n_parts > small.n_parts
+    ks = [1, 5, 8]
+    # a context per resolution is avoided on purpose: both scenes are 640x480, ONE context sees both models
+    assert (small.width, small.height) == (large.width, large.height)
+    with ruf.Context(large.width, large.height) as ctx:
+        for sc in (small, large):
+            kin = sc.kinematics()
+            proj, tx, ty = sc.proj()
+            kin["tx"], kin["ty"] = tx, ty
+            q = np.stack([sc.joint_q(k) for k in ks])
+            want = [orc.fk(kin, q[i]) for i in range(len(ks))]
+            frames = []
+            from realtime_urdf_filter_b200 import synth
+            for i, k in enumerate(ks):
+                fr = dict(view=want[i][2], pm=want[i][1])
+                z = orc.render(sc.tri, sc.tri_part, helpers.oracle_mvp(sc, fr["view"], fr["pm"]), sc.width, sc.height,
+                               helpers.BG_Z, nthreads=4)
+                fr["depth"] = synth.synth_depth(synth.linear_depth(z), k, "u16")
+                frames.append(fr)
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            d_q, d_proj = t(q), t(proj)
+            d_in = t(np.stack([f["depth"] for f in frames]).view(np.int16))
+            d_out = torch.empty_like(d_in)
+            d_mask = torch.empty(d_in.shape, dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+            ctx.set_kinematics(**{k_: kin[k_] for k_ in KEYS})
+            ctx.filter_batch_device_fk(len(ks), d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_q.data_ptr(), tx, ty,
+                                       sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
+            ctx.sync()
+            for i, fr in enumerate(frames):
+                want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+                assert np.array_equal(d_out[i].cpu().numpy().view(np.uint16), want_d)
+                assert np.array_equal(d_mask[i].cpu().numpy(), want_m)

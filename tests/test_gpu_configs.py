@@ -386,3 +386,37 @@ def test_million_frames_stay_identical():
                 assert torch.equal(d_out, first_d) and torch.equal(d_mask, first_m), f"differs after {it + 1} launches"
         ctx.sync()
     assert torch.equal(d_out, first_d) and torch.equal(d_mask, first_m)
+
+
+@pytest.mark.parametrize("enc", ["u16", "f32"])
+def test_sensor_values_straddling_the_threshold(enc):
+    """Every pixel's sensor depth sits within a few units of its own `virtual - threshold`: the compare of
+    urdf_filter.frag:23 (and the raster kernel's integer form of it for 16UC1 runs that share one virtual depth)
+    must flip at exactly the oracle's value, for robot, background and never-drawn pixels alike."""
+    for sc, k in ((helpers.scene("pr2_small"), 4), (helpers.scene("example"), 0)):
+        proj, _, _ = sc.proj()
+        view, pm = sc.frame(k)
+        z = orc.render(sc.tri, sc.tri_part, helpers.oracle_mvp(sc, view, pm), sc.width, sc.height, helpers.BG_Z, nthreads=8)
+        virt = synth.linear_depth(z).astype(np.float32)
+        rng = np.random.default_rng(77)
+        for md in (0.05, 0.0, -0.013, 2.5):
+            thr = virt - np.float32(md)
+            if enc == "u16":
+                depth = np.clip(np.floor(thr.astype(np.float64) * 1000.0) + rng.integers(-2, 4, thr.shape), 0, 65535)
+                depth = depth.astype(np.uint16)
+                depth[::7, ::5] = rng.integers(0, 65536, depth[::7, ::5].shape).astype(np.uint16)
+            else:
+                steps = rng.integers(-2, 3, thr.shape)
+                depth = thr.copy()
+                for s in range(2):
+                    depth = np.where(steps > s, np.nextafter(depth, np.float32(np.inf)), depth)
+                    depth = np.where(steps < -s, np.nextafter(depth, np.float32(-np.inf)), depth)
+                depth[::9, ::4] = np.nan
+            fr = dict(view=view, pm=pm, depth=depth)
+            want_d, want_m, _ = helpers.oracle_filter(sc, fr, nthreads=8, max_diff=md)
+            with ruf.Context(sc.width, sc.height) as ctx:
+                ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+                got_d, got_m = ctx.filter(depth, proj, view, pm, md, sc.replace_value)
+            assert np.array_equal(got_m, want_m), f"mask differs at {np.count_nonzero(got_m != want_m)} px (md={md})"
+            assert np.array_equal(got_d.view(np.uint8), want_d.view(np.uint8))
+            assert 0.02 < (want_m == 255).mean() < 0.98

@@ -67,3 +67,23 @@ def test_synth_scenes_shape():
     assert view.shape == (16,) and pm.shape == (sc.n_parts, 16)
     ex = synth.example_scene()
     assert ex.n_tris == 48 and ex.n_parts == 4
+
+
+def test_binding_keeps_converted_arguments_alive():
+    """lists, float32 and transposed (non-contiguous) matrices are copied by the binding; the copies
+    must outlive the C call (numpy's small-block cache hands a freed temporary's address to the next one)."""
+    import realtime_urdf_filter_b200 as ruf
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        q1, q2 = rng.normal(size=4), rng.normal(size=4)
+        t1, t2 = rng.normal(size=3), rng.normal(size=3)
+        want = ruf.view_matrix(q1, t1, q2, t2, 0.1, -0.2)
+        got = ruf.view_matrix(list(q1), t1.astype(np.float64)[::-1][::-1].tolist(), tuple(q2), list(t2), 0.1, -0.2)
+        assert np.array_equal(want, got)
+        # float32 / strided inputs take the copying branch for every argument at once
+        q1f, q2f = q1.astype(np.float32), q2.astype(np.float32)
+        t1s, t2s = np.stack([t1, t1], 1)[:, 0], np.stack([t2, t2], 1)[:, 0]
+        want32 = ruf.view_matrix(q1f.astype(np.float64), t1, q2f.astype(np.float64), t2)
+        assert np.array_equal(want32, ruf.view_matrix(q1f, t1s, q2f, t2s))
+        want_pm = ruf.part_model(q1, t1, q2, t2)
+        assert np.array_equal(want_pm, ruf.part_model(list(q1), list(t1), list(q2), list(t2)))

@@ -162,3 +162,39 @@ def test_render_is_order_and_thread_independent():
     perm = np.random.default_rng(0).permutation(sc.n_tris)
     zp = orc.render(sc.tri[perm], sc.tri_part[perm], mvp, 640, 480, helpers.BG_Z, nthreads=3)
     assert np.array_equal(z1, z8) and np.array_equal(z1, zp)
+
+
+# ---- the raster kernel's integer form of the shader compare for 16UC1 frames (csrc/ruf_kernels.cu: u16_threshold) ----
+def _u16_threshold_np(thr):
+    """numpy float32 transcription of u16_threshold(): largest raw with float32(raw) * 0.001f <= thr."""
+    thr = np.asarray(thr, np.float32)
+    k = np.float32(0.001)
+    with np.errstate(invalid="ignore", over="ignore"):
+        c = np.minimum(np.floor(thr * np.float32(1000.0)), np.float32(65535.0))
+        c = np.where(np.isfinite(c), c, 0).astype(np.int64)
+        c = np.clip(c, 0, 65535)
+        down = (c.astype(np.float32) * k) > thr
+        up = ~down & (c < 65535) & ~(((c + 1).astype(np.float32) * k) > thr)
+        c = c - down + up
+        c = np.where(thr < np.float32(0.0), -1, c)
+        c = np.where(~(thr < np.float32(65.536)), 65535, c)
+    return c
+
+
+def test_u16_threshold_matches_float_compare_on_every_boundary():
+    """`float(raw) * 0.001f > thr` (urdf_filter.frag:23 after convertTo(CV_32F, 0.001), src/urdf_filter.cpp:288) must
+    equal `raw > R(thr)` for every raw: check thr = the sensor value of every raw and its float neighbours."""
+    raw = np.arange(65536, dtype=np.int64)
+    g = raw.astype(np.float32) * np.float32(0.001)
+    assert np.all(np.diff(g) > 0)                       # strictly increasing: the integer form exists
+    cands = [g, np.nextafter(g, np.float32(-np.inf)), np.nextafter(g, np.float32(np.inf)),
+             ((g[:-1].astype(np.float64) + g[1:]) / 2).astype(np.float32)]
+    rng = np.random.default_rng(3)
+    cands.append(rng.uniform(-1, 70, 400000).astype(np.float32))
+    cands.append(np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 65.535, 65.536, 1e-30, -1e-30, 7.87, 3e38], np.float32))
+    for thr in cands:
+        R = _u16_threshold_np(thr)
+        # reference: count of raw values that are NOT filtered = first index with g > thr
+        with np.errstate(invalid="ignore"):
+            want = np.where(np.isnan(thr), 65535, np.searchsorted(g, thr, side="right") - 1)
+        assert np.array_equal(R, want)

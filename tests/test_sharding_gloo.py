@@ -30,8 +30,16 @@ def _worker(rank, world, port, q):
             arrays = {"tri": rng.normal(size=(1000, 9)).astype(np.float32),
                       "tri_part": rng.integers(0, 7, 1000).astype(np.int32),
                       "views": rng.normal(size=(6, 16)),
-                      "depth": rng.integers(0, 8000, (6, 12, 16)).astype(np.int16)}
+                      "depth": rng.integers(0, 8000, (6, 12, 16)).astype(np.int16),
+                      # the library's own buffer types (16UC1 depth, uint32 tri_part) and a 0-d entry in the middle
+                      "depth_u16": np.arange(40000, 40096, dtype=np.uint16).reshape(2, 6, 8),
+                      "scalar": np.float64(2.5),
+                      "part_u32": np.array([0, 3, 0xfffffff0], np.uint32)}
         got = sharding.broadcast_arrays(arrays, 0, "cpu")
+        assert list(got) == ["tri", "tri_part", "views", "depth", "depth_u16", "scalar", "part_u32"]
+        assert np.array_equal(got["depth_u16"].numpy().view(np.uint16), np.arange(40000, 40096, dtype=np.uint16).reshape(2, 6, 8))
+        assert got["scalar"].shape == () and float(got["scalar"]) == 2.5
+        assert got["part_u32"].numpy().view(np.uint32).tolist() == [0, 3, 0xfffffff0]
         ref = np.random.default_rng(5)
         assert np.array_equal(got["tri"].numpy(), ref.normal(size=(1000, 9)).astype(np.float32))
         assert got["tri_part"].dtype == torch.int32 and got["views"].dtype == torch.float64
