@@ -14,6 +14,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER_LINES = {}      # (header file, line) -> id; the line table holds -id for instructions inlined from CUDA headers
 
 
 def line_table(lib, kernel):
@@ -31,9 +32,15 @@ def line_table(lib, kernel):
                     continue
                 if not inside:
                     continue
-                m = re.search(r'//## File ".*?", line (\d+)', l)
+                m = re.search(r'//## File "(.*?)", line (\d+)', l)
                 if m:
-                    cur = int(m.group(1))
+                    # lines of inlined CUDA headers (shuffles, min/max, ...) must not alias lines of the kernel file:
+                    # they are reported as negative numbers keyed by HEADER_LINES
+                    if m.group(1).endswith("ruf_kernels.cu"):
+                        cur = int(m.group(2))
+                    else:
+                        key = (os.path.basename(m.group(1)), int(m.group(2)))
+                        cur = -HEADER_LINES.setdefault(key, len(HEADER_LINES) + 1)
                 elif re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
                     lines.append(cur)
             if inside and lines:
@@ -84,6 +91,8 @@ def main(rep, kernel, top=45, lib=None, mangled=None):
         stalls = sorted(((a[n], n[6:]) for n in stall_cols), reverse=True)[:3]
         st = " ".join(f"{n}:{v / s * 100:.0f}%" for v, n in stalls if v > 0)
         text = src[ln - 1].strip()[:100] if 0 < ln <= len(src) else ""
+        if ln < 0:
+            text = "[%s:%d]" % next(k for k, v in HEADER_LINES.items() if v == -ln)
         print(f"{ln:5d} {s / tot_s * 100:5.1f}% smp {a['inst'] / tot_i * 100:5.1f}% inst  [{st}]  {text}")
 
 

@@ -100,7 +100,8 @@ static int fail(ruf_context *c, int code, const char *fmt, ...)
 
 static void free_workspace(ruf_context *c)
 {
-  cudaFree(c->ws.mvp); cudaFree(c->ws.vis); cudaFree(c->ws.ctr); cudaFree(c->ws.big); cudaFree(c->ws.bins);
+  cudaFree(c->ws.mvp); cudaFree(c->ws.vis); cudaFree(c->ws.ctr); cudaFree(c->ws.big); cudaFree(c->ws.bins); cudaFree(c->ws.tinfo);
+  c->ws.tinfo = nullptr;
   c->ws.mvp = nullptr; c->ws.vis = nullptr; c->ws.ctr = nullptr; c->ws.big = nullptr; c->ws.bins = nullptr;
   c->max_batch = 0;
 }
@@ -146,6 +147,7 @@ static int ensure_workspace(ruf_context *c, int frames)
   RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * c->dims.ctr_stride * sizeof(uint32_t)));
   RUF_CUDA(c, cudaMalloc(&c->ws.big, f * cap_big * sizeof(TriRec)));
   RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * c->dims.ntiles * cap_tile * sizeof(TriRec)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.tinfo, f * c->dims.ntiles * sizeof(uint4)));
   c->max_batch = frames;
   return RUF_OK;
 }
@@ -229,6 +231,7 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
       ws.ctr += (size_t)f0 * c->dims.ctr_stride;
       ws.big += (size_t)f0 * c->dims.cap_big;
       ws.bins += (size_t)f0 * c->dims.ntiles * c->dims.cap_tile;
+      ws.tinfo += (size_t)f0 * c->dims.ntiles;
       FrameBuffers fs = fb;
       fs.depth_in = (const char *)d_in + f0 * img * es;
       fs.depth_out = (char *)d_out + f0 * img * es;

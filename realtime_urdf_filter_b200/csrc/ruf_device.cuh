@@ -108,6 +108,10 @@ constexpr int kZPad = 72;                       // zero words after the z tile (
 constexpr int kNumStages = 3;                   // pose, setup+bin, raster+filter
 constexpr uint32_t kFlagBigOverflow = 1u;
 constexpr uint32_t kFlagBinOverflow = 2u;
+// per (frame, tile) word written by ruf_tile_info_kernel: x = flags, y = integer threshold (16UC1) or bits of the float
+// threshold (32FC1), z = bits of the tile's single window z
+constexpr uint32_t kTileFlat = 1u, kTileUndrawn = 2u;
+constexpr int kFlatMaxBig = 8;                  // big-list records a tile-info thread is willing to classify
 
 // One window-space triangle after setup: 48 bytes = 3 x 16 B (bulk-copy granularity).
 // Vertices are snapped (1/256 px) and ordered so that the doubled area is positive.
@@ -164,6 +168,7 @@ struct Workspace {
   TriRec *big;           // [frame][cap_big]
   TriRec *bins;          // [frame][tile][cap_tile] one record list per tile
   uint32_t *status;      // sticky OR of all frame flags
+  uint4 *tinfo;          // [frame][tile] ruf_tile_info_kernel -> ruf_raster_filter_kernel
 };
 
 struct Model {

@@ -766,6 +766,33 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
   return o;
 }
 
+// Class of one big-list record against one tile: 0 = no sample of the tile can be covered, 1 = every sample is
+// covered, 2 = mixed, 3 = every sample is covered with ONE depth (*zconst).  Edge values are linear over the tile's
+// sample grid, so their min / max sit on its corners.  Shared by the tile-info kernel and the raster kernel.
+__device__ __forceinline__ uint32_t classify_big_record(const TriRec &r, int tile_x0, int tile_y0, float *zconst)
+{
+  const int bi0 = (int)(r.bx & 0xffffu), bi1 = (int)(r.bx >> 16);
+  const int bj0 = (int)(r.by & 0xffffu), bj1 = (int)(r.by >> 16);
+  if (bi1 < tile_x0 || bi0 >= tile_x0 + kTileW || bj1 < tile_y0 || bj0 >= tile_y0 + kTileH) return 0u;
+  const int tpx = tile_x0 * kSubpix + kSubpixHalf, tpy = tile_y0 * kSubpix + kSubpixHalf;
+  const Edges e = make_edges(r);
+  const long long spanx = (long long)(kTileW - 1) * kSubpix, spany = (long long)(kTileH - 1) * kSubpix;
+  const long long t0 = (long long)e.A0 * (tpx - r.x0) + (long long)e.B0 * (tpy - r.y0) + e.bias0;
+  const long long t1 = (long long)e.A1 * (tpx - r.x1) + (long long)e.B1 * (tpy - r.y1) + e.bias1;
+  const long long t2 = (long long)e.A2 * (tpx - r.x2) + (long long)e.B2 * (tpy - r.y2) + e.bias2;
+  const long long a0 = e.A0 * spanx, c0 = e.B0 * spany, a1 = e.A1 * spanx, c1 = e.B1 * spany,
+                  a2 = e.A2 * spanx, c2 = e.B2 * spany;
+  const long long mx0 = t0 + max(a0, 0LL) + max(c0, 0LL), mn0 = t0 + min(a0, 0LL) + min(c0, 0LL);
+  const long long mx1 = t1 + max(a1, 0LL) + max(c1, 0LL), mn1 = t1 + min(a1, 0LL) + min(c1, 0LL);
+  const long long mx2 = t2 + max(a2, 0LL) + max(c2, 0LL), mn2 = t2 + min(a2, 0LL) + min(c2, 0LL);
+  if ((mx0 | mx1 | mx2) < 0) return 0u;
+  if ((mn0 | mn1 | mn2) < 0) return 2u;
+  // a covering record with a constant depth plane (the background quad: every vertex has the same window z, so both
+  // gradients are exactly 0 and z(P) = fma(0, ., fma(0, ., z0)) = z0): the value stands in for the record
+  if (r.gx == 0.0f && r.gy == 0.0f) { *zconst = clamp_z(r.z0); return 3u; }
+  return 1u;
+}
+
 // Occlusion among the big-list records of one tile (result-neutral; every thread of the CTA calls it with its own
 // record, cls = 0 for none).  A record that covers every sample of the tile and is drawn everywhere (cls 1 / 3,
 // farthest corner in front of the far plane) hides every record whose NEAREST corner is not in front of its FARTHEST
@@ -798,10 +825,59 @@ __device__ __noinline__ uint32_t occlusion_filter(uint32_t cls, int x0, int y0, 
   return cls;
 }
 
+// ------------------------------------------------------------------------------------------
+// K1b: one thread per (frame, tile), between the setup and the raster kernel.
+//  * folds the frame's overflow flags into the context's sticky status word;
+//  * recognises FLAT tiles: no binned record and at most kFlatMaxBig big-list records, none of which needs per-pixel
+//    work (class 0 or 3).  Their single virtual depth goes through the shader's scalar part here, once per tile
+//    instead of once per thread: to_linear_depth (frag:14-17,22), the threshold (frag:23) and -- 16UC1 -- its
+//    integer form (u16_threshold).  tinfo = { flags, R or bits(thr), bits(z), 0 }.
+// ------------------------------------------------------------------------------------------
+template <int ENC>
+__global__ void __launch_bounds__(128)
+ruf_tile_info_kernel(Dims d, int n_frames, const TriRec *__restrict__ big_all, const uint32_t *__restrict__ ctr_all,
+                     uint32_t *status, ShaderParams sp, uint4 *__restrict__ tinfo)
+{
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n_frames * d.ntiles) return;
+  const int frame = (int)(gid / d.ntiles), tile = (int)(gid - (long long)frame * d.ntiles);
+  const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
+  const uint2 nfb = __ldg(reinterpret_cast<const uint2 *>(ctr + kCtrWords) + tile);
+  uint32_t flags = (nfb.x + nfb.y > d.cap_tile) ? kFlagBinOverflow : 0u;     // the two runs met: the host grows cap_tile and retries
+  if (tile == 0) flags |= __ldg(ctr + kCtrFlags);
+  if (flags) atomicOr(status, flags);
+  uint4 ti = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t nbig = min(__ldg(ctr + kCtrBig), d.cap_big);
+  if (nfb.x + nfb.y == 0 && nbig <= (uint32_t)kFlatMaxBig) {
+    const int tile_by = tile / d.tiles_x, tile_bx = tile - tile_by * d.tiles_x;
+    const TriRec *big = big_all + (size_t)frame * d.cap_big;
+    float zt = 1.0f;                                           // glClear depth
+    bool flat = true;
+    for (uint32_t b = 0; b < nbig; ++b) {
+      const TriRec r = load_rec_global(big + b);
+      float zc = 0.0f;
+      const uint32_t cls = classify_big_record(r, tile_bx * kTileW, tile_by * kTileH, &zc);
+      if (cls == 1u || cls == 2u) flat = false;
+      if (cls == 3u) zt = fminf(zt, zc);
+    }
+    if (flat) {
+      ti.x = kTileFlat;
+      ti.z = __float_as_uint(zt);
+      if (zt == 1.0f) {
+        ti.x |= kTileUndrawn;                                  // clear colour: depth 0, mask 0 (:566)
+      } else {
+        const float thr = (sp.k1 / (zt - sp.k2)) - sp.max_diff;
+        ti.y = (ENC == 1) ? (uint32_t)u16_threshold(thr) : __float_as_uint(thr);
+      }
+    }
+  }
+  tinfo[gid] = ti;
+}
+
 template <int ENC>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
-                         const uint32_t *__restrict__ ctr_all, uint32_t *status, ShaderParams sp, FrameBuffers fb)
+                         const uint32_t *__restrict__ ctr_all, const uint4 *__restrict__ tinfo, ShaderParams sp, FrameBuffers fb)
 {
   // 8 warps rasterise and shade.  The tile's record list streams into a shared-memory ring by bulk async
   // copies (TMA): thread 0 starts the first kStages chunks, later refills are issued by whichever warp
@@ -823,23 +899,84 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
   const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
+  const int prow = tid >> 3, pcol = (tid & 7) * 8;
+  // FLAT tiles (two thirds of the tiles of a typical frame: no binned record, only constant-depth covering records in
+  // the big list = the background quad) were recognised by ruf_tile_info_kernel, which also took the virtual depth
+  // through to_linear_depth and the threshold: what is left is a streaming pass (5 B/px for 16UC1) that never touches
+  // shared memory, the record lists or a barrier.
+  {
+    const uint4 ti = __ldg(tinfo + (size_t)frame * d.ntiles + tile);
+    if (ti.x & kTileFlat) {
+      const bool drawn = !(ti.x & kTileUndrawn);
+      const uint32_t repl_u16 = f32_to_u16(sp.replace_value);
+      const uint32_t repl2 = repl_u16 | (repl_u16 << 16);
+      const float zt = __uint_as_float(ti.z);
+#pragma unroll
+      for (int half = 0; half < kRowsPerThread; ++half) {
+        const int gy = tile_y0 + prow + 32 * half, gx = tile_x0 + pcol;
+        if (gy >= d.H || gx >= d.W) continue;
+        const size_t base = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
+        if (fb.vec_ok && gx + 8 <= d.W) {
+          uint2 mq = make_uint2(0u, 0u);
+          if (ENC == 1) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);                       // never drawn: clear colour (:566)
+            if (drawn) {
+              const uint4 sens = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + base));
+              shade_row_u16_uniform(sens, (int)ti.y, repl2, o, mq);
+            }
+            *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
+          } else {
+            float od[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (drawn) {
+              const float thr = __uint_as_float(ti.y);
+              const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + base);
+              const uint4 s0 = __ldg(p), s1 = __ldg(p + 1);
+              const float sensor[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
+                                       __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
+              uint32_t om[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const bool sflt = sensor[i] > thr;                      // frag:23
+                od[i] = sflt ? sp.replace_value : sensor[i];            // frag:29
+                om[i] = sflt ? 255u : 0u;
+              }
+              mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
+              mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
+            }
+            float4 *po = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
+            po[0] = make_float4(od[0], od[1], od[2], od[3]);
+            po[1] = make_float4(od[4], od[5], od[6], od[7]);
+          }
+          if (fb.mask_out) *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
+          if (fb.zbuf_out) {
+            float4 *p = reinterpret_cast<float4 *>(fb.zbuf_out + base);
+            p[0] = make_float4(zt, zt, zt, zt);
+            p[1] = make_float4(zt, zt, zt, zt);
+          }
+        } else {
+          for (int i = 0; i < 8 && gx + i < d.W; ++i) {
+            float sensor;
+            if (ENC == 1) sensor = (float)static_cast<const uint16_t *>(fb.depth_in)[base + i] * 0.001f;
+            else sensor = static_cast<const float *>(fb.depth_in)[base + i];
+            const FragOut o = fragment(sensor, zt, sp);
+            if (ENC == 1) static_cast<uint16_t *>(fb.depth_out)[base + i] = (uint16_t)f32_to_u16(o.depth);
+            else static_cast<float *>(fb.depth_out)[base + i] = o.depth;
+            if (fb.mask_out) fb.mask_out[base + i] = (uint8_t)o.mask;
+            if (fb.zbuf_out) fb.zbuf_out[base + i] = zt;
+          }
+        }
+      }
+      return;
+    }
+  }
   const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
   // records binned to this tile (CTA-uniform): nf at the front of its list (triangles facing the camera, drawn
-  // first), nb at the back (facing away: drawn last and depth-culled against what is already there).  Two
-  // thirds of the tiles of a typical frame see only the background quad: they take the register-only path
-  // below (no ring, no z tile, no CTA-wide barrier).
+  // first), nb at the back (facing away: drawn last and depth-culled against what is already there)
   const uint2 nfb = __ldg(reinterpret_cast<const uint2 *>(ctr + kCtrWords) + tile);
   uint32_t nf = nfb.x, nb = nfb.y;
-  const bool list_overflow = nf + nb > d.cap_tile;            // the two runs met: the host grows cap_tile and retries
-  nf = min(nf, d.cap_tile);
+  nf = min(nf, d.cap_tile);                  // an overflow (the two runs met) was flagged by ruf_tile_info_kernel
   nb = min(nb, d.cap_tile - nf);
   const uint32_t cnt = nf + nb;
-  // fold this frame's overflow flags into the context's sticky status word
-  if (threadIdx.x == 0) {
-    uint32_t flags = list_overflow ? kFlagBinOverflow : 0u;
-    if (tile == 0) flags |= ctr[kCtrFlags];
-    if (flags) atomicOr(status, flags);
-  }
   const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
   const TriRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
   // chunk c of the virtual list "front run, then back run": at most two bulk copies into one ring stage
@@ -853,7 +990,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(TriRec),
                &full_bar[stage]);
   };
-  const int prow = tid >> 3, pcol = (tid & 7) * 8;
   if (cnt) {
     if (tid == 0) {
 #pragma unroll
@@ -895,38 +1031,20 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     const bool occlude = nbig - b0 > (uint32_t)kOccludeMin;     // CTA-uniform; a typical frame holds just the background quad
     if (b0 + tid < nbig) {
       const TriRec r = load_rec_global(big + b0 + tid);
-      const int bi0 = (int)(r.bx & 0xffffu), bi1 = (int)(r.bx >> 16);
-      const int bj0 = (int)(r.by & 0xffffu), bj1 = (int)(r.by >> 16);
-      if (!(bi1 < tile_x0 || bi0 >= tile_x0 + kTileW || bj1 < tile_y0 || bj0 >= tile_y0 + kTileH)) {
-        const Edges e = make_edges(r);
-        const long long spanx = (long long)(kTileW - 1) * kSubpix, spany = (long long)(kTileH - 1) * kSubpix;
-        const long long t0 = (long long)e.A0 * (tpx - r.x0) + (long long)e.B0 * (tpy - r.y0) + e.bias0;
-        const long long t1 = (long long)e.A1 * (tpx - r.x1) + (long long)e.B1 * (tpy - r.y1) + e.bias1;
-        const long long t2 = (long long)e.A2 * (tpx - r.x2) + (long long)e.B2 * (tpy - r.y2) + e.bias2;
-        const long long a0 = e.A0 * spanx, c0 = e.B0 * spany, a1 = e.A1 * spanx, c1 = e.B1 * spany,
-                        a2 = e.A2 * spanx, c2 = e.B2 * spany;
-        const long long mx0 = t0 + max(a0, 0LL) + max(c0, 0LL), mn0 = t0 + min(a0, 0LL) + min(c0, 0LL);
-        const long long mx1 = t1 + max(a1, 0LL) + max(c1, 0LL), mn1 = t1 + min(a1, 0LL) + min(c1, 0LL);
-        const long long mx2 = t2 + max(a2, 0LL) + max(c2, 0LL), mn2 = t2 + min(a2, 0LL) + min(c2, 0LL);
-        if ((mx0 | mx1 | mx2) >= 0) cls = ((mn0 | mn1 | mn2) >= 0) ? 1u : 2u;
-        // a covering record with a constant depth plane (the background quad: every vertex has the same
-        // window z, so both gradients are exactly 0 and z(P) = fma(0, ., fma(0, ., z0)) = z0): hand the
-        // value over instead of the record
-        if (cls == 1u && r.gx == 0.0f && r.gy == 0.0f) { cls = 3u; s_bigz[tid] = clamp_z(r.z0); }
-        if (occlude) { ox0 = r.x0; oy0 = r.y0; oz0 = r.z0; ogx = r.gx; ogy = r.gy; }
-      }
+      float zc = 0.0f;
+      cls = classify_big_record(r, tile_x0, tile_y0, &zc);
+      if (cls == 3u) s_bigz[tid] = zc;
+      if (cls && occlude) { ox0 = r.x0; oy0 = r.y0; oz0 = r.z0; ogx = r.gx; ogy = r.gy; }
     }
     if (occlude) cls = occlusion_filter(cls, ox0, oy0, oz0, ogx, ogy, tpx, tpy, tid, &s_zcut, &s_zown);
     s_bigcls[tid] = (uint8_t)cls;
-    return cls;
   };
-  const uint32_t cls0 = classify(0);
-  // the classification, the cleared z tile and the ring's barriers are visible after this barrier; it also says whether
-  // any big-list record needs per-pixel work in this tile (class 1 / 2: a wall, a clipped triangle)
-  const bool big_per_pixel = __syncthreads_or(cls0 == 1u || cls0 == 2u) != 0;
-  // FLAT tile (CTA-uniform; two thirds of the tiles of a typical frame): no binned record and only constant-depth
-  // covering records in the big list (the background quad) -> one virtual depth for all 4096 pixels
-  const bool flat = cnt == 0 && !big_per_pixel && nbig <= (uint32_t)kRasterThreads;
+  // The cleared z tile and the ring's barriers are visible after this barrier.  The classification comes AFTER it: its
+  // results are only read behind the end-of-raster barrier, so the other warps start on the tile's records while warp 0
+  // still waits for its big-list records (two dependent global loads and ~150 instructions of 64-bit arithmetic).
+  __syncthreads();
+  classify(0);
+  if (!cnt) __syncthreads();       // no raster phase (and no end-of-raster barrier) on this path
 
   if (cnt) {
     {
@@ -1146,15 +1264,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   // depths, merge the per-frame big list on registers (one walk over the classified records for all rows),
   // then run the fragment stage row by row.
   float zall[kRowsPerThread][8];
-  if (flat) {
-    float zt = 1.0f;                                           // glClear depth
-    for (uint32_t b = 0; b < nbig; ++b)
-      if (s_bigcls[b] == 3) zt = fminf(zt, s_bigz[b]);
-#pragma unroll
-    for (int half = 0; half < kRowsPerThread; ++half)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) zall[half][i] = zt;
-  } else {
 #pragma unroll
   for (int half = 0; half < kRowsPerThread; ++half) {
     if (cnt) {
@@ -1227,8 +1336,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
   }
 
-  }   // !flat
-
   // ---- fused fragment stage (include/shaders/urdf_filter.frag:19-35): 8 pixels per thread and row, vector loads/stores ----
   const uint32_t repl_u16 = f32_to_u16(sp.replace_value);     // convertTo(CV_16U, 1000) of the replaced pixels, :311
   const uint32_t repl2 = repl_u16 | (repl_u16 << 16);
@@ -1241,16 +1348,11 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     const size_t base = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
     const float (&zw)[8] = zall[half];
     if (fb.vec_ok && gx + 8 <= d.W) {
-      // One virtual depth for the whole run (background, or never drawn)?  z values are clamped to +0 / come out of
-      // fminf, so equal floats have equal bits.
-      uint32_t zdiff = 0;
-#pragma unroll
-      for (int i = 1; i < 8; ++i) zdiff |= __float_as_uint(zw[i]) ^ __float_as_uint(zw[0]);
       // to_linear_depth (frag:14-17,22) and the threshold (frag:23) once per distinct z of the run.  Never-drawn
       // pixels (z = 1: clear colour, :566) get +inf, so that `sensor > thr` is false for them.
       float thr[8];
       thr[0] = (zw[0] == 1.0f) ? kInf : (sp.k1 / (zw[0] - sp.k2)) - sp.max_diff;
-      if (zdiff) {
+      {
         float zprev = zw[0], tprev = thr[0];
 #pragma unroll
         for (int i = 1; i < 8; ++i) {
@@ -1265,10 +1367,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       if (ENC == 1) {
         const uint4 sens = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(fb.depth_in) + base));
         uint4 o;
-        if (!zdiff) {
-          if (zw[0] == 1.0f) { o = make_uint4(0u, 0u, 0u, 0u); mq = make_uint2(0u, 0u); }   // clear colour: depth 0, mask 0
-          else shade_row_u16_uniform(sens, u16_threshold(thr[0]), repl2, o, mq);
-        } else {
+        {
           const uint32_t w[4] = {sens.x, sens.y, sens.z, sens.w};
           uint32_t u[8], om[8];
 #pragma unroll
@@ -1297,9 +1396,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         uint32_t om[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float t = zdiff ? thr[i] : thr[0];
-          const bool drawn = zdiff ? (zw[i] != 1.0f) : (zw[0] != 1.0f);
-          const bool sflt = sensor[i] > t;
+          const bool drawn = zw[i] != 1.0f;
+          const bool sflt = sensor[i] > thr[i];
           od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
           om[i] = sflt ? 255u : 0u;
         }
@@ -1561,14 +1659,20 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     ruf_setup_bin_kernel<<<grid, kSetupThreads, 0, s>>>(m, ws.mvp, ws.vis, d, n_frames, fpc, ws.big, ws.bins, ws.ctr);
     ++launches;
     if ((err = check("ruf_setup_bin_kernel")) != cudaSuccess) return err;
+    const long long n_items = (long long)n_frames * d.ntiles;
+    const unsigned tblocks = (unsigned)((n_items + 127) / 128);
+    if (enc == 1) ruf_tile_info_kernel<1><<<tblocks, 128, 0, s>>>(d, n_frames, ws.big, ws.ctr, ws.status, sp, ws.tinfo);
+    else ruf_tile_info_kernel<0><<<tblocks, 128, 0, s>>>(d, n_frames, ws.big, ws.ctr, ws.status, sp, ws.tinfo);
+    ++launches;
+    if ((err = check("ruf_tile_info_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[2], s);
   }
   {
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (enc == 1)
-      ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
+      ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
     else
-      ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.status, sp, fb);
+      ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
     ++launches;
     if ((err = check("ruf_raster_filter_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[3], s);

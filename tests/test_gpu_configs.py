@@ -313,7 +313,7 @@ def test_sliced_two_stream_launch_matches_single_launch(monkeypatch):
             ctx.sync()
             launches = ctx.stats()["kernel_launches"]
         outs.append((d_out.cpu().numpy().view(np.uint16), d_mask.cpu().numpy(), launches))
-    assert outs[0][2] == 9 and outs[1][2] == 3          # 3 slices x 3 kernels vs one launch sequence
+    assert outs[0][2] == 12 and outs[1][2] == 4         # 3 slices x 4 kernels vs one launch sequence
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     # and a few frames against the oracle
     for k in (0, 255, 256, 529):
