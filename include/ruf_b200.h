@@ -169,6 +169,13 @@ RUF_API int ruf_filter_batch_device_fk(ruf_context *ctx, int n_frames, const voi
                                        double camera_ty, float max_diff, float replace_value,
                                        void *d_depth_out, uint8_t *d_mask_out, float *d_zbuf_out);
 
+/* Measurement aid: the chunked host pipeline of ruf_filter_batch_host with the same staging slots, streams, chunk
+ * sizes and copies (H2D of depth + matrices, D2H of depth + mask) but WITHOUT the kernels: the PCIe / host-memory
+ * ceiling of the end-to-end number on this box (bench.py `e2e.copy_ceiling`).  The output buffers receive whatever
+ * the staging slots hold. */
+RUF_API int ruf_host_copy_ceiling(ruf_context *ctx, int n_frames, const void *depth_in, int enc, const double *proj,
+                                  const double *view, const double *part_model, void *depth_out, uint8_t *mask_out);
+
 RUF_API int ruf_host_alloc(void **ptr, size_t bytes);   /* cudaHostAlloc (pinned) */
 RUF_API int ruf_host_free(void *ptr);
 

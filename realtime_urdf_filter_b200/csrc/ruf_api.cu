@@ -116,13 +116,12 @@ static void free_staging(ruf_context *c)
   c->stage_frames = 0;
 }
 
-static int ensure_workspace(ruf_context *c, int frames)
+// The record lists are sized for the worst tile of every frame (fixed capacity per (frame, tile)), so the workspace
+// grows with the batch: 35 MB per frame at 640x480 / 90k triangles, 193 MB per frame at 1080p / 500k.  It is capped
+// at a byte budget (RUF_WORKSPACE_GB, default 48 of the 180 GB); a device batch with more frames than fit runs as
+// equal sub-batches, one after the other on the same stream, through the same workspace.
+static long long default_cap_tile(const ruf_context *c)
 {
-  if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
-  if (frames < c->want_batch) frames = c->want_batch;
-  // capacities: every tile of every frame owns a record list of cap_tile entries (a robot seen from its own
-  // head concentrates its triangles in a third of the tiles: the default is 8x the mean, at least 2048), plus
-  // the per-frame big list; both grow by doubling after an overflow (check_status)
   long long cap_tile = c->want_bin;
   if (cap_tile <= 0) {
     cap_tile = 8 * (c->n_tris + 2) / c->dims.ntiles;
@@ -130,6 +129,28 @@ static int ensure_workspace(ruf_context *c, int frames)
     if (cap_tile > c->n_tris + 2) cap_tile = c->n_tris + 2;
     cap_tile = (cap_tile + 63) & ~63LL;
   }
+  return cap_tile;
+}
+static int max_frames_in_budget(const ruf_context *c)
+{
+  static const double gb = [] { const char *e = getenv("RUF_WORKSPACE_GB"); const double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 48.0; }();
+  const long long cap_big = c->want_big > 0 ? c->want_big : 1024;
+  const double per_frame = (double)sizeof(TriRec) * ((double)c->dims.ntiles * (double)default_cap_tile(c) + (double)cap_big) +
+                           (double)(c->n_parts + 1) * 65.0 + (double)c->dims.ntiles * 24.0 + 16.0;
+  const double n = gb * 1e9 / per_frame;
+  return n < 1.0 ? 1 : (n > 65535.0 ? 65535 : (int)n);
+}
+
+static int ensure_workspace(ruf_context *c, int frames)
+{
+  if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  if (frames < c->want_batch) frames = c->want_batch;
+  const int fit = max_frames_in_budget(c);
+  if (frames > fit) frames = fit;
+  // capacities: every tile of every frame owns a record list of cap_tile entries (a robot seen from its own
+  // head concentrates its triangles in a third of the tiles: the default is 8x the mean, at least 2048), plus
+  // the per-frame big list; both grow by doubling after an overflow (check_status)
+  const long long cap_tile = default_cap_tile(c);
   long long cap_big = c->want_big > 0 ? c->want_big : 1024;
   if (cap_big > 0x7fffffffLL || cap_tile > 0x7fffffffLL) return fail(c, RUF_ERR_INVALID, "capacity too large");
   if (c->max_batch >= frames && c->dims.cap_big == (uint32_t)cap_big && c->dims.cap_tile == (uint32_t)cap_tile)
@@ -474,16 +495,27 @@ int ruf_filter_batch_device(ruf_context *c, int n_frames, const void *d_depth_in
   if (rc != RUF_OK) return rc;
   c->stats = ruf_stats{};
   c->stats.frames = n_frames;
-  c->last_frames = n_frames;
-  return launch(c, n_frames, d_depth_in, enc, d_proj, d_view, d_part_model, max_diff, replace_value, d_depth_out,
-                d_mask_out, d_zbuf_out, c->stream);
+  // more frames than the workspace budget holds: equal sub-batches, stream-ordered through the same workspace
+  const int n_sub = (n_frames + c->max_batch - 1) / c->max_batch;
+  const int per = (n_frames + n_sub - 1) / n_sub;
+  const size_t es = elem_size(enc), img = (size_t)c->W * c->H;
+  for (int f0 = 0; f0 < n_frames; f0 += per) {
+    const int nf = (n_frames - f0 < per) ? (n_frames - f0) : per;
+    c->last_frames = nf;
+    rc = launch(c, nf, (const char *)d_depth_in + f0 * img * es, enc, d_proj, d_view + 16 * (size_t)f0,
+                d_part_model ? d_part_model + 16 * (size_t)f0 * c->n_parts : nullptr, max_diff, replace_value,
+                (char *)d_depth_out + f0 * img * es, d_mask_out ? d_mask_out + f0 * img : nullptr,
+                d_zbuf_out ? d_zbuf_out + f0 * img : nullptr, c->stream);
+    if (rc != RUF_OK) return rc;
+  }
+  return RUF_OK;
 }
 
 // One pass of the chunked host pipeline.  Chunk k: H2D on s_in (slot k&1) -> kernels on the
 // context stream -> D2H on s_out.  Slots are recycled under event dependencies.
 static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int enc, const double *proj,
                          const double *view, const double *part_model, float max_diff, float replace_value,
-                         void *depth_out, uint8_t *mask_out, int chunk)
+                         void *depth_out, uint8_t *mask_out, int chunk, bool copy_only = false)
 {
   const size_t es = elem_size(enc);
   const size_t img = (size_t)c->W * c->H;
@@ -519,8 +551,9 @@ static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int
     RUF_CUDA(c, cudaStreamWaitEvent(sk, c->ev_in[slot], 0));
     if (k >= 2) RUF_CUDA(c, cudaStreamWaitEvent(sk, c->ev_out[slot], 0));   // output slot drained
     double *dm = c->d_mats[slot];
-    int rc = launch(c, nf, c->d_in[slot], enc, dm, dm + 16, dm + 16 + 16 * (size_t)nf, max_diff, replace_value,
-                    c->d_out[slot], mask_out ? c->d_mask[slot] : nullptr, nullptr, sk);
+    int rc = copy_only ? RUF_OK
+                       : launch(c, nf, c->d_in[slot], enc, dm, dm + 16, dm + 16 + 16 * (size_t)nf, max_diff, replace_value,
+                                c->d_out[slot], mask_out ? c->d_mask[slot] : nullptr, nullptr, sk);
     if (rc != RUF_OK) return rc;
     c->last_frames = nf;                       // ruf_get_stats reads the counters of the last launch sequence
     RUF_CUDA(c, cudaEventRecord(c->ev_k[slot], sk));
@@ -539,6 +572,17 @@ static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int
   return check_status(c, sk);
 }
 
+// frames per pipeline chunk: large enough for efficient copies/launches, small enough to overlap (measured)
+static int host_chunk(int n_frames)
+{
+  int chunk = n_frames >= 512 ? 64 : (n_frames >= 128 ? 32 : (n_frames >= 64 ? 16 : (n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1))));
+  if (const char *e = getenv("RUF_HOST_CHUNK")) {      // tuning aid
+    const int v = atoi(e);
+    if (v >= 1 && v <= 4096) chunk = v < n_frames ? v : n_frames;
+  }
+  return chunk;
+}
+
 int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, int enc, const double *proj,
                           const double *view, const double *part_model, float max_diff, float replace_value,
                           void *depth_out, uint8_t *mask_out)
@@ -549,12 +593,7 @@ int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, in
     return fail(c, RUF_ERR_INVALID, "bad arguments");
   if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
   RUF_CUDA(c, cudaSetDevice(c->device));
-  // frames per pipeline chunk: large enough for efficient copies/launches, small enough to overlap (measured)
-  int chunk = n_frames >= 512 ? 64 : (n_frames >= 128 ? 32 : (n_frames >= 64 ? 16 : (n_frames >= 32 ? 8 : (n_frames >= 8 ? 4 : 1))));
-  if (const char *e = getenv("RUF_HOST_CHUNK")) {      // tuning aid
-    const int v = atoi(e);
-    if (v >= 1 && v <= 4096) chunk = v < n_frames ? v : n_frames;
-  }
+  const int chunk = host_chunk(n_frames);
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_workspace(c, chunk);
     if (rc != RUF_OK) return rc;
@@ -568,6 +607,25 @@ int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, in
     if (rc != RUF_ERR_OVERFLOW) return rc;   // overflow: capacities were doubled, run again
   }
   return fail(c, RUF_ERR_OVERFLOW, "internal buffers still too small after 8 attempts");
+}
+
+int ruf_host_copy_ceiling(ruf_context *c, int n_frames, const void *depth_in, int enc, const double *proj,
+                          const double *view, const double *part_model, void *depth_out, uint8_t *mask_out)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (n_frames < 1 || !depth_in || !depth_out || !proj || !view || (c->n_parts > 0 && !part_model) ||
+      (enc != RUF_ENC_F32_M && enc != RUF_ENC_U16_MM))
+    return fail(c, RUF_ERR_INVALID, "bad arguments");
+  if (!c->have_model) return fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_set_model)");
+  RUF_CUDA(c, cudaSetDevice(c->device));
+  const int chunk = host_chunk(n_frames);
+  int rc = ensure_workspace(c, chunk);
+  if (rc != RUF_OK) return rc;
+  rc = ensure_staging(c, chunk);
+  if (rc != RUF_OK) return rc;
+  c->stats = ruf_stats{};
+  c->stats.frames = n_frames;
+  return host_pipeline(c, n_frames, depth_in, enc, proj, view, part_model, 0.0f, 0.0f, depth_out, mask_out, chunk, true);
 }
 
 int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj, const double *view,

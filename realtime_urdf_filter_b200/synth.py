@@ -19,6 +19,17 @@ import numpy as np
 
 from . import _lib
 
+# Host-math provider: the matrices and primitive tessellations come from libruf_b200.so's host functions by default.
+# bench.py's reference arm swaps in the CPU oracle's bit-identical twins (tests/test_host_math.py) with use_math(), so
+# that the CPU arm never loads the product library.
+_math = _lib
+
+
+def use_math(provider):
+    """provider: object with projection_matrix, view_matrix, part_model, box/cube/sphere/cylinder_triangles."""
+    global _math
+    _math = provider
+
 Z_NEAR, Z_FAR = 0.1, 8.0
 
 
@@ -136,7 +147,7 @@ class Scene:
         return int(self.tri.shape[0])
 
     def proj(self):
-        return _lib.projection_matrix(self.P, self.width, self.height, Z_NEAR, Z_FAR)
+        return _math.projection_matrix(self.P, self.width, self.height, Z_NEAR, Z_FAR)
 
     def link_poses(self, k: int):
         """Forward kinematics at frame k -> list of 4x4 link_to_fixed."""
@@ -159,7 +170,7 @@ class Scene:
         _, tx, ty = self.proj()
         Tc = (np.eye(4) if self.cam_link < 0 else Ts[self.cam_link]) @ make_T(self.cam_R, self.cam_xyz)
         Tinv = np.linalg.inv(Tc)              # lookupTransform(cam_frame, fixed_frame)
-        view = _lib.view_matrix(self.offset_q, self.offset_t, quat_from_matrix(Tinv[:3, :3]), Tinv[:3, 3], tx, ty)
+        view = _math.view_matrix(self.offset_q, self.offset_t, quat_from_matrix(Tinv[:3, :3]), Tinv[:3, 3], tx, ty)
         pm = np.zeros((self.n_parts, 16))
         cache = {}
         for i, p in enumerate(self.parts):
@@ -167,7 +178,7 @@ class Scene:
                 T = Ts[p.link]
                 cache[p.link] = (quat_from_matrix(T[:3, :3]), T[:3, 3].copy())
             q, t = cache[p.link]
-            pm[i] = _lib.part_model(q, t, p.off_q, p.off_t, p.suffix)
+            pm[i] = _math.part_model(q, t, p.off_q, p.off_t, p.suffix)
         return view, pm
 
     # ---- device-side forward kinematics inputs (ruf_set_kinematics / ruf_fk_batch_device) ----
@@ -186,13 +197,13 @@ class Scene:
             axis[i] = np.asarray(ln.axis, float) / np.linalg.norm(ln.axis)
         part_local = np.zeros((self.n_parts, 16))
         for i, p in enumerate(self.parts):
-            part_local[i] = _lib.part_model((0, 0, 0, 1), (0, 0, 0), p.off_q, p.off_t, p.suffix)
+            part_local[i] = _math.part_model((0, 0, 0, 1), (0, 0, 0), p.off_q, p.off_t, p.suffix)
         return dict(parent=np.array([ln.parent for ln in self.links], np.int32),
                     joint_type=np.array([jt[ln.jtype] for ln in self.links], np.int32),
                     origin=origin, axis=axis, part_link=np.array([p.link for p in self.parts], np.int32),
                     part_local=part_local, cam_link=self.cam_link,
                     cam_mount=make_T(self.cam_R, self.cam_xyz).T.reshape(-1),
-                    view_pre=_lib.view_matrix(self.offset_q, self.offset_t, (0, 0, 0, 1), (0, 0, 0), 0.0, 0.0))
+                    view_pre=_math.view_matrix(self.offset_q, self.offset_t, (0, 0, 0, 1), (0, 0, 0), 0.0, 0.0))
 
     def frames(self, ks):
         views = np.zeros((len(ks), 16))
@@ -225,20 +236,20 @@ def add_box(parts, tris, pidx, link, dims, off_q=(0, 0, 0, 1), off_t=(0, 0, 0)):
     glScalef(dx,dy,dz); glutSolidCube(dx)  -- two draw calls, two model matrices (F4)."""
     dx, dy, dz = (float(np.float32(v)) for v in dims)
     parts.append(Part(link, off_q, off_t, None))
-    _add(tris, pidx, _lib.box_triangles(dx, dy, dz), len(parts) - 1)
+    _add(tris, pidx, _math.box_triangles(dx, dy, dz), len(parts) - 1)
     parts.append(Part(link, off_q, off_t, scale_suffix(np.float32(dx), np.float32(dy), np.float32(dz))))
-    _add(tris, pidx, _lib.cube_triangles(dx), len(parts) - 1)
+    _add(tris, pidx, _math.cube_triangles(dx), len(parts) - 1)
 
 
 def add_sphere(parts, tris, pidx, link, radius, off_q=(0, 0, 0, 1), off_t=(0, 0, 0)):
     parts.append(Part(link, off_q, off_t, None))
-    _add(tris, pidx, _lib.sphere_triangles(float(np.float32(radius)), 10, 10), len(parts) - 1)
+    _add(tris, pidx, _math.sphere_triangles(float(np.float32(radius)), 10, 10), len(parts) - 1)
 
 
 def add_cylinder(parts, tris, pidx, link, radius, length, off_q=(0, 0, 0, 1), off_t=(0, 0, 0)):
     r, l = float(np.float32(radius)), float(np.float32(length))
     parts.append(Part(link, off_q, off_t, translate_suffix(0, 0, -np.float32(l) / np.float32(2))))
-    _add(tris, pidx, _lib.cylinder_triangles(r, l, 10, 10), len(parts) - 1)
+    _add(tris, pidx, _math.cylinder_triangles(r, l, 10, 10), len(parts) - 1)
 
 
 def add_mesh(parts, tris, pidx, link, tri, scale=(1.0, 1.0, 1.0), off_q=(0, 0, 0, 1), off_t=(0, 0, 0)):
@@ -407,7 +418,7 @@ def pr2_like_scene(width=640, height=480, n_tris=90000, seed=7, name="pr2_like",
         # C3: two static wall meshes (Automatica-style cell walls): box-shaped RenderableMesh parts, 2.6 m ahead
         w1 = len(links); links.append(Link("wall1", -1, (2.6, 0.9, 1.0), (0, 0, math.pi / 2 + 0.5)))
         w2 = len(links); links.append(Link("wall2", -1, (2.6, -0.9, 1.0), (0, 0, math.pi / 2 - 0.5)))
-        slab = _lib.box_triangles(3.0, 0.2, 2.5)
+        slab = _math.box_triangles(3.0, 0.2, 2.5)
         add_mesh(parts, tris, pidx, w1, slab)
         add_mesh(parts, tris, pidx, w2, slab)
         wall_tris = 24

@@ -87,3 +87,24 @@ def test_binding_keeps_converted_arguments_alive():
         assert np.array_equal(want32, ruf.view_matrix(q1f, t1s, q2f, t2s))
         want_pm = ruf.part_model(q1, t1, q2, t2)
         assert np.array_equal(want_pm, ruf.part_model(list(q1), list(t1), list(q2), list(t2)))
+
+
+def test_scenes_do_not_depend_on_the_math_provider():
+    """bench.py's reference arm builds its scene with the oracle's host math (so that the CPU arm never loads the
+    product library): same triangles, same matrices, bit for bit."""
+    import bench
+    from realtime_urdf_filter_b200 import synth
+    a = synth.pr2_like_scene(n_tris=5000, name="prov_a")
+    va, pa = a.frame(7)
+    try:
+        synth.use_math(bench.OracleMath(orc))
+        b = synth.pr2_like_scene(n_tris=5000, name="prov_b")
+        vb, pb = b.frame(7)
+        ex = synth.example_scene()
+        pj = b.proj()
+    finally:
+        synth.use_math(synth._lib)
+    assert np.array_equal(a.tri.view(np.uint32), b.tri.view(np.uint32)) and np.array_equal(a.tri_part, b.tri_part)
+    assert np.array_equal(va.view(np.uint64), vb.view(np.uint64)) and np.array_equal(pa.view(np.uint64), pb.view(np.uint64))
+    assert np.array_equal(ex.tri.view(np.uint32), synth.example_scene().tri.view(np.uint32))
+    assert np.array_equal(np.asarray(pj[0]).view(np.uint64), np.asarray(a.proj()[0]).view(np.uint64))
