@@ -1319,10 +1319,23 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
 #pragma unroll
         for (int half = 0; half < kRowsPerThread; ++half) {
           const int py = py0 + 32 * half * kSubpix;
-          const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
           long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
           long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
           long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
+          // The edge values are linear along the run of 8 samples: non-negative at both ends = all 8 covered;
+          // one edge negative at both ends = none covered.  A wall or a doubled box cuts few runs of a tile, so
+          // most runs take one of the two shortcuts instead of eight 64-bit edge tests.
+          const long long f0 = e0 + 7 * s0, f1 = e1 + 7 * s1, f2 = e2 + 7 * s2;
+          if (((e0 & f0) | (e1 & f1) | (e2 & f2)) < 0) continue;
+          const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
+          if ((e0 | e1 | e2 | f0 | f1 | f2) >= 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
+              if (z < 1.0f) zall[half][i] = fminf(zall[half][i], z);
+            }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if ((e0 | e1 | e2) >= 0) {
