@@ -148,4 +148,5 @@ def test_sphere_cylinder_box_and_scaled_mesh_links_through_the_facade(tmp_path, 
         keep = part != p
         _, m2, _ = orc.filter_frame(depth, tri[keep], part[keep], mvp, np.float32(0.1), np.float32(8.0), np.float32(0.05),
                                     np.float32(5.0), want_mask=True, nthreads=8)
-        assert p == 0 or not np.array_equal(m2, want_m), f"part {p} is invisible in this test scene"
+        # (part 1 is the box's doubled cube: glScalef(dx,dy,dz); glutSolidCube(dx) = dx^2 x dx*dy x dx*dz, inside the box for dx < 1)
+        assert p == 1 or not np.array_equal(m2, want_m), f"part {p} is invisible in this test scene"
