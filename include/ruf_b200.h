@@ -176,6 +176,32 @@ RUF_API int ruf_filter_batch_device_fk(ruf_context *ctx, int n_frames, const voi
 RUF_API int ruf_host_copy_ceiling(ruf_context *ctx, int n_frames, const void *depth_in, int enc, const double *proj,
                                   const double *view, const double *part_model, void *depth_out, uint8_t *mask_out);
 
+/* ------------------------------------------------------------------------------------ */
+/* Multi-GPU group: one host process, N devices, frames sharded, no per-frame   */
+/* collective.  The reference is single-GPU and single-context (function-local statics,       */
+/* src/urdf_filter.cpp:210,388,549); this is what lets ONE node feed 8 GPUs.                  */
+/* ------------------------------------------------------------------------------------ */
+typedef struct ruf_group ruf_group;
+/* One context per device (devices == NULL: 0..n-1) and, for n > 1, one NCCL communicator per device
+ * (ncclCommInitAll; libnccl.so.2 is loaded at run time). */
+RUF_API int ruf_group_create(ruf_group **grp, int n_devices, const int *devices, int width, int height,
+                             double z_near, double z_far);
+RUF_API int ruf_group_destroy(ruf_group *grp);
+RUF_API int ruf_group_size(const ruf_group *grp);
+/* The context of member i: its own stream, usable with every ruf_* call (one camera stream per GPU, BASELINE configs[3]). */
+RUF_API ruf_context *ruf_group_context(ruf_group *grp, int i);
+RUF_API const char *ruf_group_last_error(const ruf_group *grp);
+/* ruf_set_model for every member: the model is prepared once on the host, uploaded to device 0 and sent to the other
+ * devices with one ncclBroadcast per static buffer (over NVLink / NVSwitch). */
+RUF_API int ruf_group_set_model(ruf_group *grp, const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts);
+RUF_API int64_t ruf_group_broadcast_bytes(const ruf_group *grp);   /* bytes each non-root device received */
+/* ruf_filter_batch_host over all members: chunk j of frames_per_chunk frames (0 = automatic) runs on device j mod N
+ * (frames_per_chunk = 1: frame k -> GPU k mod N, BASELINE configs[4]); one host thread per device; results are written
+ * at their frame's position, i.e. in sequence order. */
+RUF_API int ruf_group_filter_batch_host(ruf_group *grp, int n_frames, const void *depth_in, int enc, const double *proj,
+                                        const double *view, const double *part_model, float max_diff,
+                                        float replace_value, void *depth_out, uint8_t *mask_out, int frames_per_chunk);
+
 RUF_API int ruf_host_alloc(void **ptr, size_t bytes);   /* cudaHostAlloc (pinned) */
 RUF_API int ruf_host_free(void *ptr);
 

@@ -58,6 +58,15 @@ SIGNATURES = {
                                         C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "ruf_host_copy_ceiling": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "ruf_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "ruf_group_destroy": (C.c_int, [C.c_void_p]),
+    "ruf_group_size": (C.c_int, [C.c_void_p]),
+    "ruf_group_context": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "ruf_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "ruf_group_set_model": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "ruf_group_broadcast_bytes": (C.c_int64, [C.c_void_p]),
+    "ruf_group_filter_batch_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int]),
     "ruf_set_kinematics": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ruf_fk_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
@@ -375,6 +384,58 @@ class Context:
         s = RufStats()
         self._check(self._lib.ruf_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in RufStats._fields_}
+
+
+class Group:
+    """ruf_group: N devices in one process (one context + one host thread per device, NCCL broadcast of the model)."""
+
+    def __init__(self, width: int, height: int, devices=None, n_devices: int | None = None, z_near=0.1, z_far=8.0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        devs = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        n = int(n_devices if devs is None else devs.size)
+        rc = self._lib.ruf_group_create(C.byref(self._h), n, None if devs is None else devs.ctypes.data, width, height,
+                                        z_near, z_far)
+        if rc != RUF_OK:
+            raise RufError(rc, self._lib.ruf_group_last_error(None).decode())
+        self.width, self.height, self.size, self.n_parts = width, height, n, 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ruf_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != RUF_OK:
+            raise RufError(rc, self._lib.ruf_group_last_error(self._h).decode())
+
+    def set_model(self, tri_xyz, tri_part, n_parts: int):
+        tri = np.ascontiguousarray(tri_xyz, np.float32).reshape(-1, 9)
+        part = np.ascontiguousarray(tri_part, np.uint32).reshape(-1)
+        self._check(self._lib.ruf_group_set_model(self._h, tri.ctypes.data, part.ctypes.data, tri.shape[0], int(n_parts)))
+        self.n_parts = int(n_parts)
+        return int(self._lib.ruf_group_broadcast_bytes(self._h))
+
+    def filter_batch_host(self, depth, proj, views, part_models, max_diff, replace_value, out=None, mask=None,
+                          frames_per_chunk=0):
+        depth = np.asarray(depth)
+        enc = ENC_U16_MM if depth.dtype == np.uint16 else ENC_F32_M
+        if depth.ndim != 3 or depth.shape[1:] != (self.height, self.width) or not depth.flags.c_contiguous:
+            raise ValueError("depth must be a C-contiguous (n, H, W) array")
+        n = depth.shape[0]
+        out = np.empty_like(depth) if out is None else out
+        mask = np.empty(depth.shape, np.uint8) if mask is None else mask
+        v, pm, pr = _as_f64(views, 16 * n), _as_f64(part_models, 16 * n * self.n_parts), _as_f64(proj, 16)
+        self._check(self._lib.ruf_group_filter_batch_host(self._h, n, depth.ctypes.data, enc, pr.ctypes.data, v.ctypes.data,
+                                                          pm.ctypes.data if pm.size else None, max_diff, replace_value,
+                                                          out.ctypes.data, mask.ctypes.data, int(frames_per_chunk)))
+        return out, mask
 
 
 def host_alloc(nbytes: int) -> int:

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ruf_b200.h"
@@ -409,12 +410,9 @@ int ruf_sync(ruf_context *c)
   return check_status(c, c->stream);
 }
 
-// Model ingest (set-up time): the soup is cut into meshlets on the host (ruf_meshlet.cpp) and uploaded.
-static int build_model(ruf_context *c, const float *h_xyz, const uint32_t *h_part, int64_t n_tris, int n_parts)
+// Device buffers for a meshlet model of the given sizes (contents come from upload_model or from an ncclBroadcast)
+static int alloc_model(ruf_context *c, const MeshletModel &mm, int64_t n_tris, int n_parts)
 {
-  MeshletModel mm;
-  // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
-  build_meshlets(h_xyz, h_part, n_tris, n_parts, (float)(c->z_far * 0.99), kMeshVerts, kMeshTris, kMeshParts, mm);
   if (mm.verts.size() / 4 > 0xffffffffull || mm.tris.size() > 0xffffffffull || mm.n_meshlets() > 0x7fffffffull)
     return fail(c, RUF_ERR_INVALID, "model too large");
   RUF_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -425,10 +423,6 @@ static int build_model(ruf_context *c, const float *h_xyz, const uint32_t *h_par
   RUF_CUDA(c, cudaMalloc(&c->mverts, mm.verts.size() * sizeof(float)));
   RUF_CUDA(c, cudaMalloc(&c->mtris, mm.tris.size() * sizeof(uint32_t)));
   RUF_CUDA(c, cudaMalloc(&c->part_aabb, mm.part_aabb.size() * sizeof(float)));
-  RUF_CUDA(c, cudaMemcpy(c->meshlets, mm.hdr.data(), mm.hdr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  RUF_CUDA(c, cudaMemcpy(c->mverts, mm.verts.data(), mm.verts.size() * sizeof(float), cudaMemcpyHostToDevice));
-  RUF_CUDA(c, cudaMemcpy(c->mtris, mm.tris.data(), mm.tris.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  RUF_CUDA(c, cudaMemcpy(c->part_aabb, mm.part_aabb.data(), mm.part_aabb.size() * sizeof(float), cudaMemcpyHostToDevice));
   c->n_meshlets = (int)mm.n_meshlets();
   c->n_tris = n_tris; c->n_parts = n_parts;
   c->dims.n_tris = n_tris; c->dims.n_parts = n_parts;
@@ -439,6 +433,23 @@ static int build_model(ruf_context *c, const float *h_xyz, const uint32_t *h_par
   cudaFree(c->kin_blob);       // kinematics belong to the previous model
   c->kin_blob = nullptr;
   return RUF_OK;
+}
+static int upload_model(ruf_context *c, const MeshletModel &mm)
+{
+  RUF_CUDA(c, cudaMemcpy(c->meshlets, mm.hdr.data(), mm.hdr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  RUF_CUDA(c, cudaMemcpy(c->mverts, mm.verts.data(), mm.verts.size() * sizeof(float), cudaMemcpyHostToDevice));
+  RUF_CUDA(c, cudaMemcpy(c->mtris, mm.tris.data(), mm.tris.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  RUF_CUDA(c, cudaMemcpy(c->part_aabb, mm.part_aabb.data(), mm.part_aabb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return RUF_OK;
+}
+// Model ingest (set-up time): the soup is cut into meshlets on the host (ruf_meshlet.cpp) and uploaded.
+static int build_model(ruf_context *c, const float *h_xyz, const uint32_t *h_part, int64_t n_tris, int n_parts)
+{
+  MeshletModel mm;
+  // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
+  build_meshlets(h_xyz, h_part, n_tris, n_parts, (float)(c->z_far * 0.99), kMeshVerts, kMeshTris, kMeshParts, mm);
+  const int rc = alloc_model(c, mm, n_tris, n_parts);
+  return rc != RUF_OK ? rc : upload_model(c, mm);
 }
 
 int ruf_set_model(ruf_context *c, const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts)
@@ -515,23 +526,17 @@ int ruf_filter_batch_device(ruf_context *c, int n_frames, const void *d_depth_in
 // context stream -> D2H on s_out.  Slots are recycled under event dependencies.
 static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int enc, const double *proj,
                          const double *view, const double *part_model, float max_diff, float replace_value,
-                         void *depth_out, uint8_t *mask_out, int chunk, bool copy_only = false)
+                         void *depth_out, uint8_t *mask_out, const std::vector<std::pair<int, int>> &segs,
+                         bool copy_only = false)
 {
+  (void)n_frames;
   const size_t es = elem_size(enc);
   const size_t img = (size_t)c->W * c->H;
   const int P = c->n_parts;
   cudaStream_t sk = c->stream;
-  // The D2H copies are the bottleneck (2+1 bytes out vs 2 bytes in per pixel) and run back to back once they have
-  // started, so what the chunking can still save is the time until the first one starts: the first chunks are
-  // small (chunk/8, chunk/8, chunk/4, chunk/2), then full size.
-  int f0 = 0, nf = 0;
-  for (int k = 0; f0 + nf < n_frames; ++k) {
-    f0 += nf;
+  for (int k = 0; k < (int)segs.size(); ++k) {
+    const int f0 = segs[k].first, nf = segs[k].second;
     const int slot = k & 1;
-    int want = chunk;
-    if (k < 2) want = chunk / 8; else if (k == 2) want = chunk / 4; else if (k == 3) want = chunk / 2;
-    if (want < 1) want = 1;
-    nf = (n_frames - f0 < want) ? (n_frames - f0) : want;
     if (k >= 2) {
       // slot reuse: input slot free once chunk k-2's kernels ran; pinned matrices likewise
       RUF_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_k[slot], 0));
@@ -583,6 +588,24 @@ static int host_chunk(int n_frames)
   return chunk;
 }
 
+// The frames of one host call as pipeline segments (first frame, count).  The D2H copies are the bottleneck (2+1 bytes
+// out vs 2 bytes in per pixel) and run back to back once they have started, so what the chunking can still save is the
+// time until the first one starts: the first segments are small (chunk/8, chunk/8, chunk/4, chunk/2), then full size.
+static std::vector<std::pair<int, int>> ramp_segments(int n_frames, int chunk)
+{
+  std::vector<std::pair<int, int>> segs;
+  int f0 = 0;
+  for (int k = 0; f0 < n_frames; ++k) {
+    int want = chunk;
+    if (k < 2) want = chunk / 8; else if (k == 2) want = chunk / 4; else if (k == 3) want = chunk / 2;
+    if (want < 1) want = 1;
+    const int nf = (n_frames - f0 < want) ? (n_frames - f0) : want;
+    segs.emplace_back(f0, nf);
+    f0 += nf;
+  }
+  return segs;
+}
+
 int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, int enc, const double *proj,
                           const double *view, const double *part_model, float max_diff, float replace_value,
                           void *depth_out, uint8_t *mask_out)
@@ -603,7 +626,7 @@ int ruf_filter_batch_host(ruf_context *c, int n_frames, const void *depth_in, in
     c->stats.frames = n_frames;
     c->last_frames = (n_frames % chunk) ? (n_frames % chunk) : chunk;
     rc = host_pipeline(c, n_frames, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
-                       mask_out, chunk);
+                       mask_out, ramp_segments(n_frames, chunk));
     if (rc != RUF_ERR_OVERFLOW) return rc;   // overflow: capacities were doubled, run again
   }
   return fail(c, RUF_ERR_OVERFLOW, "internal buffers still too small after 8 attempts");
@@ -625,7 +648,8 @@ int ruf_host_copy_ceiling(ruf_context *c, int n_frames, const void *depth_in, in
   if (rc != RUF_OK) return rc;
   c->stats = ruf_stats{};
   c->stats.frames = n_frames;
-  return host_pipeline(c, n_frames, depth_in, enc, proj, view, part_model, 0.0f, 0.0f, depth_out, mask_out, chunk, true);
+  return host_pipeline(c, n_frames, depth_in, enc, proj, view, part_model, 0.0f, 0.0f, depth_out, mask_out,
+                       ramp_segments(n_frames, chunk), true);
 }
 
 int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj, const double *view,
@@ -809,6 +833,195 @@ int ruf_get_stats(ruf_context *c, ruf_stats *out)
     }
   }
   *out = s;
+  return RUF_OK;
+}
+
+}  // extern "C"
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU group: ONE host process, one context + one host thread per device, frames sharded with
+ * no per-frame collective.  The only communication is the set-up broadcast of the static model buffers from
+ * device 0 to the others over NVLink / NVSwitch (ncclCommInitAll + one ncclBroadcast per buffer).  NCCL is loaded at
+ * run time (libnccl.so.2): a single-GPU host never needs it.
+ * ------------------------------------------------------------------------------------------------ */
+#include <dlfcn.h>
+#include <thread>
+
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int /*ncclDataType_t*/, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string &err)
+  {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+    CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    Broadcast = (decltype(Broadcast))dlsym(lib, "ncclBroadcast");
+    GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!CommInitAll || !CommDestroy || !Broadcast || !GroupStart || !GroupEnd || !GetErrorString) {
+      err = "libnccl lacks an expected symbol";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclChar = 0;     // ncclInt8 / ncclChar
+}  // namespace
+
+struct ruf_group {
+  std::vector<ruf_context *> ctx;
+  std::vector<ncclComm_t> comm;
+  std::string err;
+  int64_t bcast_bytes = 0;       // bytes every non-root device received in the last ruf_group_set_model
+};
+
+static int gfail(ruf_group *g, int code, const std::string &msg)
+{
+  if (g) g->err = msg; else g_create_error = msg;
+  return code;
+}
+
+extern "C" {
+
+int ruf_group_create(ruf_group **out, int n_devices, const int *devices, int width, int height, double z_near, double z_far)
+{
+  if (!out || n_devices < 1 || n_devices > 64) return gfail(nullptr, RUF_ERR_INVALID, "bad group arguments");
+  *out = nullptr;
+  ruf_group *g = new (std::nothrow) ruf_group;
+  if (!g) return gfail(nullptr, RUF_ERR_NOMEM, "out of host memory");
+  std::vector<int> devs(n_devices);
+  for (int i = 0; i < n_devices; ++i) devs[i] = devices ? devices[i] : i;
+  for (int i = 0; i < n_devices; ++i) {
+    ruf_context *c = nullptr;
+    const int rc = ruf_create(&c, devs[i], width, height, z_near, z_far);
+    if (rc != RUF_OK) { ruf_group_destroy(g); return rc; }          // g_create_error holds the text
+    g->ctx.push_back(c);
+  }
+  if (n_devices > 1) {
+    std::string err;
+    if (!g_nccl.load(err)) { ruf_group_destroy(g); return gfail(nullptr, RUF_ERR_CUDA, err); }
+    g->comm.assign(n_devices, nullptr);
+    const int rc = g_nccl.CommInitAll(g->comm.data(), n_devices, devs.data());
+    if (rc != 0) {
+      g->comm.clear();
+      ruf_group_destroy(g);
+      return gfail(nullptr, RUF_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(rc));
+    }
+  }
+  *out = g;
+  return RUF_OK;
+}
+
+int ruf_group_destroy(ruf_group *g)
+{
+  if (!g) return RUF_OK;
+  for (size_t i = 0; i < g->comm.size(); ++i)
+    if (g->comm[i]) { cudaSetDevice(g->ctx[i]->device); g_nccl.CommDestroy(g->comm[i]); }
+  for (ruf_context *c : g->ctx) ruf_destroy(c);
+  delete g;
+  return RUF_OK;
+}
+
+int ruf_group_size(const ruf_group *g) { return g ? (int)g->ctx.size() : 0; }
+ruf_context *ruf_group_context(ruf_group *g, int i) { return (g && i >= 0 && i < (int)g->ctx.size()) ? g->ctx[i] : nullptr; }
+const char *ruf_group_last_error(const ruf_group *g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+int64_t ruf_group_broadcast_bytes(const ruf_group *g) { return g ? g->bcast_bytes : 0; }
+
+int ruf_group_set_model(ruf_group *g, const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts)
+{
+  if (!g) return RUF_ERR_INVALID;
+  if (n_tris < 0 || n_parts < 0 || n_parts > (1 << 20) || (n_tris > 0 && (!tri_xyz || !tri_part)) || n_tris > (1LL << 30))
+    return gfail(g, RUF_ERR_INVALID, "bad model arguments");
+  for (int64_t t = 0; t < n_tris; ++t)
+    if (tri_part[t] >= (uint32_t)n_parts) return gfail(g, RUF_ERR_INVALID, "tri_part out of range");
+  ruf_context *c0 = g->ctx[0];
+  MeshletModel mm;                 // built once on the host, uploaded once (device 0), broadcast to the rest
+  build_meshlets(tri_xyz, tri_part, n_tris, n_parts, (float)(c0->z_far * 0.99), kMeshVerts, kMeshTris, kMeshParts, mm);
+  for (ruf_context *c : g->ctx) {
+    if (cudaSetDevice(c->device) != cudaSuccess) return gfail(g, RUF_ERR_CUDA, "cudaSetDevice failed");
+    const int rc = alloc_model(c, mm, n_tris, n_parts);
+    if (rc != RUF_OK) return gfail(g, rc, c->err);
+  }
+  cudaSetDevice(c0->device);
+  int rc = upload_model(c0, mm);
+  if (rc != RUF_OK) return gfail(g, rc, c0->err);
+  g->bcast_bytes = 0;
+  if (g->ctx.size() > 1) {
+    const size_t bytes[4] = {mm.hdr.size() * sizeof(uint32_t), mm.verts.size() * sizeof(float), mm.tris.size() * sizeof(uint32_t),
+                             mm.part_aabb.size() * sizeof(float)};
+    for (int b = 0; b < 4; ++b) {                    // one broadcast per static buffer, root = device 0
+      if (!bytes[b]) continue;
+      int nrc = g_nccl.GroupStart();
+      for (size_t i = 0; i < g->ctx.size() && nrc == 0; ++i) {
+        ruf_context *c = g->ctx[i];
+        void *buf = b == 0 ? (void *)c->meshlets : b == 1 ? (void *)c->mverts : b == 2 ? (void *)c->mtris : (void *)c->part_aabb;
+        nrc = g_nccl.Broadcast(buf, buf, bytes[b], kNcclChar, 0, g->comm[i], c->stream);
+      }
+      const int erc = g_nccl.GroupEnd();
+      if (nrc == 0) nrc = erc;
+      if (nrc != 0) return gfail(g, RUF_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(nrc));
+      g->bcast_bytes += (int64_t)bytes[b];
+    }
+    for (ruf_context *c : g->ctx) {
+      cudaSetDevice(c->device);
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) return gfail(g, RUF_ERR_CUDA, "broadcast did not complete");
+    }
+  }
+  return RUF_OK;
+}
+
+/* n frames with host buffers: the frames are cut into chunks, chunk j goes to device j mod N (chunk = 1 is "frame k ->
+ * GPU k mod N"), every device runs its chunks through its own staging pipeline on its own host thread, and every
+ * result lands at its frame's position in the caller's arrays: the output is in sequence order by construction. */
+int ruf_group_filter_batch_host(ruf_group *g, int n_frames, const void *depth_in, int enc, const double *proj,
+                                const double *view, const double *part_model, float max_diff, float replace_value,
+                                void *depth_out, uint8_t *mask_out, int frames_per_chunk)
+{
+  if (!g) return RUF_ERR_INVALID;
+  const int N = (int)g->ctx.size();
+  if (n_frames < 1 || !depth_in || !depth_out || !proj || !view || (enc != RUF_ENC_F32_M && enc != RUF_ENC_U16_MM))
+    return gfail(g, RUF_ERR_INVALID, "bad arguments");
+  int chunk = frames_per_chunk > 0 ? frames_per_chunk : host_chunk((n_frames + N - 1) / N);
+  std::vector<std::vector<std::pair<int, int>>> segs(N);
+  int j = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, ++j)
+    segs[j % N].emplace_back(f0, (n_frames - f0 < chunk) ? (n_frames - f0) : chunk);
+  std::vector<int> rcs(N, RUF_OK);
+  auto work = [&](int i) {
+    ruf_context *c = g->ctx[i];
+    if (segs[i].empty()) return;
+    if (!c->have_model) { rcs[i] = fail(c, RUF_ERR_NO_MODEL, "no model loaded (ruf_group_set_model)"); return; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { rcs[i] = fail(c, RUF_ERR_CUDA, "cudaSetDevice failed"); return; }
+    for (int attempt = 0; attempt < 8; ++attempt) {
+      int rc = ensure_workspace(c, chunk);
+      if (rc == RUF_OK) rc = ensure_staging(c, chunk);
+      if (rc != RUF_OK) { rcs[i] = rc; return; }
+      c->stats = ruf_stats{};
+      for (auto &sg : segs[i]) c->stats.frames += sg.second;
+      rc = host_pipeline(c, n_frames, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
+                         mask_out, segs[i]);
+      rcs[i] = rc;
+      if (rc != RUF_ERR_OVERFLOW) return;       // overflow: this device's capacities were doubled, run its share again
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int i = 1; i < N; ++i) threads.emplace_back(work, i);
+  work(0);
+  for (std::thread &t : threads) t.join();
+  for (int i = 0; i < N; ++i)
+    if (rcs[i] != RUF_OK) return gfail(g, rcs[i], "device " + std::to_string(g->ctx[i]->device) + ": " + g->ctx[i]->err);
   return RUF_OK;
 }
 
