@@ -101,6 +101,7 @@ constexpr int kMeshParts = 32;
 constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   // triangles per thread
 constexpr int kSetupFrames = RUF_SETUP_FRAMES;  // frames a setup CTA loops over with its meshlet in registers
 static_assert(kMeshVerts <= 1024 && kMeshTris <= 1023, "meshlet indices are packed in 10 bits");
+constexpr int kWideCap = 16;                    // wide records a raster CTA parks for its cooperative final phase
 constexpr int kMaxTiles = 4096;
 constexpr int kPartStride = 8;                  // floats per part in Model::part_aabb
 constexpr int kZPad = 72;                       // zero words after the z tile (the depth-cull reads may run past its end)

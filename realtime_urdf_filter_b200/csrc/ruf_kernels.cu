@@ -650,12 +650,12 @@ __device__ __forceinline__ uint32_t smem_add(uint32_t saddr, uint32_t v)
 // edge functions is below 2^14, so 32-bit arithmetic is exact; WIDE = true: 64-bit.
 template <bool WIDE>
 __device__ __forceinline__ void raster_warp(const TriRec &r, int i0, int i1, int j0, int j1, int tile_x0,
-                                            int tile_y0, uint32_t *sz, int lane)
+                                            int tile_y0, uint32_t *sz, int lane, int row_off = 0, int row_step = 4)
 {
   typedef typename std::conditional<WIDE, long long, int>::type acc_t;
   const Edges e = make_edges(r);
   const int lx = lane & 7, ly = lane >> 3;
-  for (int jb = j0; jb <= j1; jb += 4) {
+  for (int jb = j0 + row_off; jb <= j1; jb += row_step) {
     const int j = jb + ly;
     const int py = j * kSubpix + kSubpixHalf;
     const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
@@ -764,6 +764,26 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
   o.depth = s ? sp.replace_value : sensor;                        // frag:29, mix() with a in {0,1}
   o.mask = s ? 255u : 0u;                                         // frag:35 read back as UNSIGNED_BYTE
   return o;
+}
+
+// Scalar tail of the fragment stage: up to 8 pixels of one row when the vector path does not apply (image width not a
+// multiple of 8, unaligned caller buffers).  Cold and out of line: inlined and unrolled it was 40 % of the kernel's code.
+template <int ENC>
+__device__ __noinline__ void shade_scalar(const FrameBuffers &fb, const ShaderParams &sp, size_t base, int n, const float *zw,
+                                          int zstride)
+{
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float z = zw[i * zstride];
+    float sensor;
+    if (ENC == 1) sensor = (float)static_cast<const uint16_t *>(fb.depth_in)[base + i] * 0.001f;
+    else sensor = static_cast<const float *>(fb.depth_in)[base + i];
+    const FragOut o = fragment(sensor, z, sp);
+    if (ENC == 1) static_cast<uint16_t *>(fb.depth_out)[base + i] = (uint16_t)f32_to_u16(o.depth);
+    else static_cast<float *>(fb.depth_out)[base + i] = o.depth;
+    if (fb.mask_out) fb.mask_out[base + i] = (uint8_t)o.mask;
+    if (fb.zbuf_out) fb.zbuf_out[base + i] = z;
+  }
 }
 
 // Class of one big-list record against one tile: 0 = no sample of the tile can be covered, 1 = every sample is
@@ -893,6 +913,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ int s_issued[kStages];              // latest chunk whose bulk copies were issued into each ring stage
   __shared__ uint32_t s_zblk[(kTileH / 4) * 16]; // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
+  __shared__ uint8_t s_biglist[kRasterThreads];  // the records of this round with a class other than 0, in any order
+  __shared__ uint32_t s_nlist, s_nwide;
+  __shared__ __align__(16) TriRec s_wide[kWideCap];   // wide records of this tile, rasterised by the whole CTA at the end
   __shared__ uint32_t s_zcut, s_zown;            // big-list occlusion: smallest farthest-corner z of a covering record, its index
   __shared__ float s_bigz[kRasterThreads];
 
@@ -954,16 +977,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
             p[1] = make_float4(zt, zt, zt, zt);
           }
         } else {
-          for (int i = 0; i < 8 && gx + i < d.W; ++i) {
-            float sensor;
-            if (ENC == 1) sensor = (float)static_cast<const uint16_t *>(fb.depth_in)[base + i] * 0.001f;
-            else sensor = static_cast<const float *>(fb.depth_in)[base + i];
-            const FragOut o = fragment(sensor, zt, sp);
-            if (ENC == 1) static_cast<uint16_t *>(fb.depth_out)[base + i] = (uint16_t)f32_to_u16(o.depth);
-            else static_cast<float *>(fb.depth_out)[base + i] = o.depth;
-            if (fb.mask_out) fb.mask_out[base + i] = (uint8_t)o.mask;
-            if (fb.zbuf_out) fb.zbuf_out[base + i] = zt;
-          }
+          const float ztmp = zt;
+          shade_scalar<ENC>(fb, sp, base, min(8, d.W - gx), &ztmp, 0);
         }
       }
       return;
@@ -990,6 +1005,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(TriRec),
                &full_bar[stage]);
   };
+  if (tid == 0) s_nlist = 0;
   if (cnt) {
     if (tid == 0) {
 #pragma unroll
@@ -999,6 +1015,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
       mbar_fence_init();
       s_next[0] = 0; s_next[1] = 0;
+      s_nwide = 0;
 #pragma unroll
       for (int c = 0; c < kStages; ++c) {
         s_issued[c] = -1;
@@ -1038,6 +1055,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
     if (occlude) cls = occlusion_filter(cls, ox0, oy0, oz0, ogx, ogy, tpx, tpy, tid, &s_zcut, &s_zown);
     s_bigcls[tid] = (uint8_t)cls;
+    if (cls) s_biglist[atomicAdd(&s_nlist, 1u)] = (uint8_t)tid;
   };
   // The cleared z tile and the ring's barriers are visible after this barrier.  The classification comes AFTER it: its
   // results are only read behind the end-of-raster barrier, so the other warps start on the tile's records while warp 0
@@ -1163,8 +1181,20 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           }
         }
 
-        // big or wide records first (the full record dies after this, which keeps the unit loop's register
-        // footprint small): the whole warp covers one triangle at a time
+        // Wide records (more than kMaxUnits units, or 64-bit edge arithmetic: pieces of walls, doubled boxes) are parked
+        // in shared memory and rasterised by the WHOLE CTA after the last batch; one warp walking 128 footprints while
+        // seven wait at the barrier was the long pole of example.urdf (C1) and of the wall tiles of C3.  Only when the
+        // parking lot is full does the claiming warp cover them itself, one triangle at a time.
+        if (kind >= 2) {
+          const uint32_t pos = atomicAdd(&s_nwide, 1u);
+          if (pos < (uint32_t)kWideCap) {
+            uint4 *dst = reinterpret_cast<uint4 *>(&s_wide[pos]);
+            dst[0] = make_uint4((uint32_t)r.x0, (uint32_t)r.y0, (uint32_t)r.x1, (uint32_t)r.y1);
+            dst[1] = make_uint4((uint32_t)r.x2, (uint32_t)r.y2, __float_as_uint(r.z0), __float_as_uint(r.gx));
+            dst[2] = make_uint4(__float_as_uint(r.gy), r.bx, r.by, (uint32_t)kind);
+            kind = 0;
+          }
+        }
         unsigned wide = __ballot_sync(0xffffffffu, kind >= 2);
         while (wide) {
           const int src = __ffs(wide) - 1;
@@ -1172,8 +1202,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           const TriRec q = shfl_rec(r, src);
           const int qi0 = __shfl_sync(0xffffffffu, i0, src), qi1 = __shfl_sync(0xffffffffu, i1, src);
           const int qj0 = __shfl_sync(0xffffffffu, j0, src), qj1 = __shfl_sync(0xffffffffu, j1, src);
-          if (__shfl_sync(0xffffffffu, kind, src) == 2) raster_warp<false>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz, lane);
-          else raster_warp<true>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz, lane);
+          raster_warp<true>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz, lane);     // 64-bit edges are exact for every record
         }
 
         // ---- phase 2: the units (kUW x kUH samples) of the 32 records are dealt out to the lanes
@@ -1257,7 +1286,18 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
       }
     }
-    consumer_bar_sync();                      // every record of the tile has been rasterised
+    consumer_bar_sync();                      // every record of the tile has been rasterised or parked
+    const uint32_t nwide = min(s_nwide, (uint32_t)kWideCap);      // CTA-uniform
+    if (nwide) {
+      for (uint32_t w = 0; w < nwide; ++w) {
+        const TriRec q = load_rec_smem(&s_wide[w]);
+        const int qi0 = max((int)(q.bx & 0xffffu), tile_x0), qi1 = min((int)(q.bx >> 16), tile_x0 + kTileW - 1);
+        const int qj0 = max((int)(q.by & 0xffffu), tile_y0), qj1 = min((int)(q.by >> 16), tile_y0 + kTileH - 1);
+        // warp w takes the footprint rows 4 w, 4 w + 32, ... of the clipped bbox
+        raster_warp<true>(q, qi0, qi1, qj0, qj1, tile_x0, tile_y0, sz, lane, 4 * warp, 4 * (kRasterThreads / 32));
+      }
+      __syncthreads();
+    }
   }
 
   // Every thread owns 8 consecutive pixels of kRowsPerThread tile rows (32 rows apart): fetch the rasterised
@@ -1284,13 +1324,15 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
       if (b0) {                                   // more than 256 records (clipping-heavy views): classify the next round
         __syncthreads();
+        if (tid == 0) s_nlist = 0;
+        __syncthreads();
         classify(b0);
         __syncthreads();
       }
-      const uint32_t nb = min(nbig - b0, (uint32_t)kRasterThreads);
-      for (uint32_t b = 0; b < nb; ++b) {
+      const uint32_t nl = s_nlist;                // records of this round that touch the tile (a few of 45 for example.urdf)
+      for (uint32_t k = 0; k < nl; ++k) {
+        const uint32_t b = s_biglist[k];
         const uint32_t c = s_bigcls[b];
-        if (c == 0) continue;
         if (c == 3) {
           const float z = s_bigz[b];
           if (z < 1.0f) {
@@ -1427,18 +1469,10 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         p[1] = make_float4(zw[4], zw[5], zw[6], zw[7]);
       }
     } else {
+      float ztmp[8];                 // a copy for the out-of-line call: the register array itself must not become addressable
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (gx + i >= d.W) break;
-        float sensor;
-        if (ENC == 1) sensor = (float)static_cast<const uint16_t *>(fb.depth_in)[base + i] * 0.001f;
-        else sensor = static_cast<const float *>(fb.depth_in)[base + i];
-        const FragOut o = fragment(sensor, zw[i], sp);
-        if (ENC == 1) static_cast<uint16_t *>(fb.depth_out)[base + i] = (uint16_t)f32_to_u16(o.depth);
-        else static_cast<float *>(fb.depth_out)[base + i] = o.depth;
-        if (fb.mask_out) fb.mask_out[base + i] = (uint8_t)o.mask;
-        if (fb.zbuf_out) fb.zbuf_out[base + i] = zw[i];
-      }
+      for (int i = 0; i < 8; ++i) ztmp[i] = zw[i];
+      shade_scalar<ENC>(fb, sp, base, min(8, d.W - gx), ztmp, 1);
     }
   }
 }
