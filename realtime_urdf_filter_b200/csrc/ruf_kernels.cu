@@ -767,9 +767,10 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
 }
 
 // Scalar tail of the fragment stage: up to 8 pixels of one row when the vector path does not apply (image width not a
-// multiple of 8, unaligned caller buffers).  Cold and out of line: inlined and unrolled it was 40 % of the kernel's code.
+// multiple of 8, unaligned caller buffers).  Cold: a rolled loop (unrolled it was 40 % of the kernel's code), but inlined --
+// as an out-of-line call it gave the kernel a stack frame and cost the hot record loop 6 % (profiles/r02_experiments.md).
 template <int ENC>
-__device__ __noinline__ void shade_scalar(const FrameBuffers &fb, const ShaderParams &sp, size_t base, int n, const float *zw,
+__device__ __forceinline__ void shade_scalar(const FrameBuffers &fb, const ShaderParams &sp, size_t base, int n, const float *zw,
                                           int zstride)
 {
 #pragma unroll 1
@@ -913,8 +914,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ int s_issued[kStages];              // latest chunk whose bulk copies were issued into each ring stage
   __shared__ uint32_t s_zblk[(kTileH / 4) * 16]; // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
-  __shared__ uint8_t s_biglist[kRasterThreads];  // the records of this round with a class other than 0, in any order
-  __shared__ uint32_t s_nlist, s_nwide;
+  __shared__ uint32_t s_nwide;
   __shared__ __align__(16) TriRec s_wide[kWideCap];   // wide records of this tile, rasterised by the whole CTA at the end
   __shared__ uint32_t s_zcut, s_zown;            // big-list occlusion: smallest farthest-corner z of a covering record, its index
   __shared__ float s_bigz[kRasterThreads];
@@ -1005,7 +1005,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(TriRec),
                &full_bar[stage]);
   };
-  if (tid == 0) s_nlist = 0;
   if (cnt) {
     if (tid == 0) {
 #pragma unroll
@@ -1055,7 +1054,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     }
     if (occlude) cls = occlusion_filter(cls, ox0, oy0, oz0, ogx, ogy, tpx, tpy, tid, &s_zcut, &s_zown);
     s_bigcls[tid] = (uint8_t)cls;
-    if (cls) s_biglist[atomicAdd(&s_nlist, 1u)] = (uint8_t)tid;
   };
   // The cleared z tile and the ring's barriers are visible after this barrier.  The classification comes AFTER it: its
   // results are only read behind the end-of-raster barrier, so the other warps start on the tile's records while warp 0
@@ -1324,15 +1322,13 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
     for (uint32_t b0 = 0; b0 < nbig; b0 += kRasterThreads) {
       if (b0) {                                   // more than 256 records (clipping-heavy views): classify the next round
         __syncthreads();
-        if (tid == 0) s_nlist = 0;
-        __syncthreads();
         classify(b0);
         __syncthreads();
       }
-      const uint32_t nl = s_nlist;                // records of this round that touch the tile (a few of 45 for example.urdf)
-      for (uint32_t k = 0; k < nl; ++k) {
-        const uint32_t b = s_biglist[k];
+      const uint32_t nl = min(nbig - b0, (uint32_t)kRasterThreads);
+      for (uint32_t b = 0; b < nl; ++b) {
         const uint32_t c = s_bigcls[b];
+        if (c == 0) continue;
         if (c == 3) {
           const float z = s_bigz[b];
           if (z < 1.0f) {
@@ -1364,20 +1360,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           long long e0 = (long long)e.A0 * (px0 - r.x0) + (long long)e.B0 * (py - r.y0) + e.bias0;
           long long e1 = (long long)e.A1 * (px0 - r.x1) + (long long)e.B1 * (py - r.y1) + e.bias1;
           long long e2 = (long long)e.A2 * (px0 - r.x2) + (long long)e.B2 * (py - r.y2) + e.bias2;
-          // The edge values are linear along the run of 8 samples: non-negative at both ends = all 8 covered;
-          // one edge negative at both ends = none covered.  A wall or a doubled box cuts few runs of a tile, so
-          // most runs take one of the two shortcuts instead of eight 64-bit edge tests.
-          const long long f0 = e0 + 7 * s0, f1 = e1 + 7 * s1, f2 = e2 + 7 * s2;
-          if (((e0 & f0) | (e1 & f1) | (e2 & f2)) < 0) continue;
           const float rowz = fmaf(r.gy, (float)(py - r.y0), r.z0);
-          if ((e0 | e1 | e2 | f0 | f1 | f2) >= 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float z = clamp_z(fmaf(r.gx, (float)(px0 + i * kSubpix - r.x0), rowz));
-              if (z < 1.0f) zall[half][i] = fminf(zall[half][i], z);
-            }
-            continue;
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if ((e0 | e1 | e2) >= 0) {
