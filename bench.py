@@ -402,12 +402,14 @@ def run_b200(args, rank, world, local_rank):
     # ---- strong scaling: ordered gather over NCCL, checked against rank 0 running the whole stream itself ----
     gather_ok = None
     if strong:
-        parts = [torch.empty_like(ring_out[0]) for _ in range(world)] if rank == 0 else None
-        dist.gather(ring_out[0].contiguous(), parts, dst=0)
+        # raw bytes on the wire: NCCL has no 16-bit integer type
+        mine_bytes = ring_out[0].contiguous().view(torch.uint8)
+        parts = [torch.empty_like(mine_bytes) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine_bytes, parts, dst=0)
         if rank == 0:
             whole = torch.empty((B_total, H_IMG, W_IMG), dtype=torch.int16, device=dev)
             for r_, p_ in enumerate(parts):
-                whole[torch.tensor(sharding.frames_for_rank(B_total, r_, world), device=dev)] = p_   # sequence order
+                whole[torch.tensor(sharding.frames_for_rank(B_total, r_, world), device=dev)] = p_.view(torch.int16)   # sequence order
             ref_out = torch.empty_like(whole)
             chunk = max(1, B)
             for f0 in range(0, B_total, chunk):

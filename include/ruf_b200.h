@@ -169,6 +169,16 @@ RUF_API int ruf_filter_batch_device_fk(ruf_context *ctx, int n_frames, const voi
                                        double camera_ty, float max_diff, float replace_value,
                                        void *d_depth_out, uint8_t *d_mask_out, float *d_zbuf_out);
 
+/* Mask output format of every later call on this context.  RUF_MASK_BYTES (default): one byte per pixel, 0 / 255, the
+ * MONO8 image the reference publishes (glGetTexImage(GL_RED, GL_UNSIGNED_BYTE) of attachment 3, src/urdf_filter.cpp:731-735,
+ * :321-329).  RUF_MASK_BITS (opt-in): one BIT per pixel, bit i of byte k = pixel 8 k + i of the row-major image (numpy
+ * unpackbits(bitorder="little")); mask buffers are then width*height/8 bytes per frame and the device -> host traffic of a
+ * 16UC1 frame drops from 3 to 2.125 bytes per pixel.  Needs width % 8 == 0.  The C++ facade expands the bits to MONO8
+ * where it publishes (host/urdf_filter.cpp), so subscribers see the reference's image either way. */
+#define RUF_MASK_BYTES 0
+#define RUF_MASK_BITS 1
+RUF_API int ruf_set_mask_format(ruf_context *ctx, int format);
+
 /* Measurement aid: the chunked host pipeline of ruf_filter_batch_host with the same staging slots, streams, chunk
  * sizes and copies (H2D of depth + matrices, D2H of depth + mask) but WITHOUT the kernels: the PCIe / host-memory
  * ceiling of the end-to-end number on this box (bench.py `e2e.copy_ceiling`).  The output buffers receive whatever

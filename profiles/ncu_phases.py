@@ -33,7 +33,7 @@ def main(rep, which, lib=None):
                  ("pass control, block maxima", find("const uint32_t nbatches", k)), ("claim + wait for chunk", find("for (;;) {", k)),
                  ("phase 1: record -> tile bbox", find("---- phase 1: one lane per record", k)), ("depth cull", find("if (pass) {", find("---- phase 1", k))),
                  ("phase 1: edge set-up", find("if (kind == 1) {", k)), ("arrive / refill", find("if (lane == 0) {", find("if (kind == 1) {", k))),
-                 ("wide records", find("big or wide records first", k)), ("unit table", find("---- phase 2: the units", k)),
+                 ("wide records", find("Wide records (more than kMaxUnits units", k)), ("unit table", find("---- phase 2: the units", k)),
                  ("unit loop", find("for (int base = 0; base < items; base += 32) {", k)), ("last barrier, z reload", find("every record of the tile has been rasterised", k) - 4),
                  ("big list: apply", find("per-frame big list, part 2", k)), ("fragment stage", find("---- fused fragment stage", k)),
                  ("(after)", find("Forward kinematics on the device", k))]

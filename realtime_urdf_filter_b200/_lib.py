@@ -22,6 +22,8 @@ RUF_ERR_NOMEM = -5
 
 ENC_F32_M = 0
 ENC_U16_MM = 1
+MASK_BYTES = 0
+MASK_BITS = 1
 
 _c_double_p = C.POINTER(C.c_double)
 _c_float_p = C.POINTER(C.c_float)
@@ -56,6 +58,7 @@ SIGNATURES = {
                                           C.c_void_p]),
     "ruf_filter_batch_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "ruf_set_mask_format": (C.c_int, [C.c_void_p, C.c_int]),
     "ruf_host_copy_ceiling": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
     "ruf_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
@@ -268,6 +271,15 @@ class Context:
     def sync(self):
         self._check(self._lib.ruf_sync(self._h))
 
+    def set_mask_format(self, fmt: int):
+        """MASK_BYTES (0 / 255 per pixel, default) or MASK_BITS (1 bit per pixel, little bit order; width % 8 == 0)."""
+        self._check(self._lib.ruf_set_mask_format(self._h, int(fmt)))
+        self.mask_format = int(fmt)
+
+    def _mask_shape(self, n=None):
+        w = self.width // 8 if getattr(self, "mask_format", MASK_BYTES) == MASK_BITS else self.width
+        return (self.height, w) if n is None else (n, self.height, w)
+
     def set_model(self, tri_xyz: np.ndarray, tri_part: np.ndarray, n_parts: int):
         tri = np.ascontiguousarray(tri_xyz, np.float32).reshape(-1, 9)
         part = np.ascontiguousarray(tri_part, np.uint32).reshape(-1)
@@ -293,7 +305,7 @@ class Context:
         enc = ENC_U16_MM if depth.dtype == np.uint16 else ENC_F32_M
         d = np.ascontiguousarray(depth, self._enc_dtype(enc)).reshape(self.height, self.width)
         out = np.empty_like(d)
-        mask = np.empty((self.height, self.width), np.uint8) if want_mask else None
+        mask = np.empty(self._mask_shape(), np.uint8) if want_mask else None
         pm = _as_f64(part_models, 16 * self.n_parts)
         pr, vw = _as_f64(proj, 16), _as_f64(view, 16)     # locals: the copies must outlive the call
         self._check(self._lib.ruf_filter(self._h, d.ctypes.data, enc, pr.ctypes.data,
@@ -323,9 +335,9 @@ class Context:
         n = depth.shape[0]
         out = np.empty_like(depth) if out is None else self._frames(out, dt, n, "out")
         if mask is None and want_mask:
-            mask = np.empty(depth.shape, np.uint8)
-        elif mask is not None:
-            self._frames(mask, np.uint8, n, "mask")
+            mask = np.empty(self._mask_shape(n), np.uint8)
+        elif mask is not None and (mask.dtype != np.uint8 or not mask.flags.c_contiguous or mask.shape != self._mask_shape(n)):
+            raise ValueError(f"mask must be a C-contiguous uint8 array of shape {self._mask_shape(n)}")
         v = _as_f64(views, 16 * n)
         pm = _as_f64(part_models, 16 * n * self.n_parts)
         pr = _as_f64(proj, 16)

@@ -67,6 +67,8 @@ struct ruf_context {
   int fk_frames = 0;                 // what the FK buffers were sized for: frames x links, frames x parts
   int fk_links_n = 0, fk_parts_n = 0;
 
+  int mask_format = RUF_MASK_BYTES;  // ruf_set_mask_format
+
   ruf_stats stats{};
   int last_frames = 0;
 
@@ -175,6 +177,8 @@ static int ensure_workspace(ruf_context *c, int frames)
 }
 
 static size_t elem_size(int enc) { return enc == RUF_ENC_U16_MM ? 2 : 4; }
+// bytes of one frame's mask in the context's mask format
+static size_t mask_bytes(const ruf_context *c) { const size_t px = (size_t)c->W * c->H; return c->mask_format == RUF_MASK_BITS ? px / 8 : px; }
 
 static int ensure_staging(ruf_context *c, int frames)
 {
@@ -214,7 +218,10 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
   FrameBuffers fb;
   fb.depth_in = d_in; fb.depth_out = d_out; fb.mask_out = d_mask; fb.zbuf_out = d_zbuf;
   const uintptr_t al = (uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_zbuf;
-  fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (((uintptr_t)d_mask & 7) == 0);
+  fb.mask_bits = c->mask_format == RUF_MASK_BITS;
+  fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (fb.mask_bits || ((uintptr_t)d_mask & 7) == 0);
+  if (fb.mask_bits && d_mask && !fb.vec_ok)
+    return fail(c, RUF_ERR_INVALID, "RUF_MASK_BITS needs an image width that is a multiple of 8 and 16-byte aligned depth buffers");
   const ShaderParams sp = shader_params(c, max_diff, replace_value);
   Model m{c->meshlets, c->mverts, c->mtris, c->part_aabb};
   int launches = 0;
@@ -257,7 +264,7 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
       FrameBuffers fs = fb;
       fs.depth_in = (const char *)d_in + f0 * img * es;
       fs.depth_out = (char *)d_out + f0 * img * es;
-      fs.mask_out = d_mask ? d_mask + f0 * img : nullptr;
+      fs.mask_out = d_mask ? d_mask + f0 * mask_bytes(c) : nullptr;
       fs.zbuf_out = d_zbuf ? d_zbuf + f0 * img : nullptr;
       int l = 0;
       cudaError_t e = launch_frames(c->dims, m, ws, nf, d_proj, d_view + 16 * (size_t)f0, d_model + 16 * (size_t)f0 * P,
@@ -515,7 +522,7 @@ int ruf_filter_batch_device(ruf_context *c, int n_frames, const void *d_depth_in
     c->last_frames = nf;
     rc = launch(c, nf, (const char *)d_depth_in + f0 * img * es, enc, d_proj, d_view + 16 * (size_t)f0,
                 d_part_model ? d_part_model + 16 * (size_t)f0 * c->n_parts : nullptr, max_diff, replace_value,
-                (char *)d_depth_out + f0 * img * es, d_mask_out ? d_mask_out + f0 * img : nullptr,
+                (char *)d_depth_out + f0 * img * es, d_mask_out ? d_mask_out + f0 * mask_bytes(c) : nullptr,
                 d_zbuf_out ? d_zbuf_out + f0 * img : nullptr, c->stream);
     if (rc != RUF_OK) return rc;
   }
@@ -568,8 +575,9 @@ static int host_pipeline(ruf_context *c, int n_frames, const void *depth_in, int
                                 cudaMemcpyDeviceToHost, c->s_out));
     c->stats.d2h_bytes += (int64_t)(nf * img * es);
     if (mask_out) {
-      RUF_CUDA(c, cudaMemcpyAsync(mask_out + f0 * img, c->d_mask[slot], nf * img, cudaMemcpyDeviceToHost, c->s_out));
-      c->stats.d2h_bytes += (int64_t)(nf * img);
+      const size_t mb = mask_bytes(c);
+      RUF_CUDA(c, cudaMemcpyAsync(mask_out + f0 * mb, c->d_mask[slot], nf * mb, cudaMemcpyDeviceToHost, c->s_out));
+      c->stats.d2h_bytes += (int64_t)(nf * mb);
     }
     RUF_CUDA(c, cudaEventRecord(c->ev_out[slot], c->s_out));
   }
@@ -766,6 +774,16 @@ int ruf_filter_batch_device_fk(ruf_context *c, int n_frames, const void *d_depth
                                d_depth_out, d_mask_out, d_zbuf_out);
   if (rc == RUF_OK) c->stats.kernel_launches += 2;
   return rc;
+}
+
+int ruf_set_mask_format(ruf_context *c, int format)
+{
+  if (!c) return RUF_ERR_INVALID;
+  if (format != RUF_MASK_BYTES && format != RUF_MASK_BITS) return fail(c, RUF_ERR_INVALID, "unknown mask format %d", format);
+  if (format == RUF_MASK_BITS && c->W % 8 != 0)
+    return fail(c, RUF_ERR_INVALID, "RUF_MASK_BITS needs an image width that is a multiple of 8 (width is %d)", c->W);
+  c->mask_format = format;
+  return RUF_OK;
 }
 
 int ruf_set_profiling(ruf_context *c, int enable)

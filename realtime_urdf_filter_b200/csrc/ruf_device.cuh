@@ -159,6 +159,7 @@ struct FrameBuffers {
   uint8_t *mask_out;     // may be null
   float *zbuf_out;       // may be null
   int vec_ok;            // rows are 16-byte aligned for 8-pixel vectors
+  int mask_bits;         // mask_out holds 1 bit per pixel (W % 8 == 0 required) instead of one 0 / 255 byte
 };
 
 struct Workspace {

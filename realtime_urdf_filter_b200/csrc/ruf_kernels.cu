@@ -753,6 +753,18 @@ __device__ __forceinline__ void shade_row_u16_uniform(const uint4 sens, int R, u
   mq.y = prmt(M[2], M[3], 0x6420u);
 }
 
+// 8 mask bytes (0 / 255) -> one byte, bit i = pixel i (RUF_MASK_BITS).  The multiplication gathers bit 0 of the four bytes
+// of a word in its top nibble: no two partial products meet, so there are no carries.
+__device__ __forceinline__ uint32_t mask_bits(const uint2 mq)
+{
+  return (((mq.x & 0x01010101u) * 0x10204080u) >> 28) | ((((mq.y & 0x01010101u) * 0x10204080u) >> 28) << 4);
+}
+__device__ __forceinline__ void store_mask(const FrameBuffers &fb, size_t base, const uint2 mq)
+{
+  if (fb.mask_bits) fb.mask_out[base >> 3] = (uint8_t)mask_bits(mq);       // base is a multiple of 8 on the vector path
+  else *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
+}
+
 struct FragOut { float depth; uint32_t mask; };
 // include/shaders/urdf_filter.frag:19-35 for the fragment that survived GL_LESS.
 __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const ShaderParams &sp)
@@ -970,7 +982,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
             po[0] = make_float4(od[0], od[1], od[2], od[3]);
             po[1] = make_float4(od[4], od[5], od[6], od[7]);
           }
-          if (fb.mask_out) *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
+          if (fb.mask_out) store_mask(fb, base, mq);
           if (fb.zbuf_out) {
             float4 *p = reinterpret_cast<float4 *>(fb.zbuf_out + base);
             p[0] = make_float4(zt, zt, zt, zt);
@@ -1445,7 +1457,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
         mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
       }
-      if (fb.mask_out) *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
+      if (fb.mask_out) store_mask(fb, base, mq);
       if (fb.zbuf_out) {
         float4 *p = reinterpret_cast<float4 *>(fb.zbuf_out + base);
         p[0] = make_float4(zw[0], zw[1], zw[2], zw[3]);

@@ -30,6 +30,9 @@ RealtimeURDFFilter::RealtimeURDFFilter(NodeHandle &nh, int argc, char **argv)
     logf(LOG_FATAL, "need a depth_distance_threshold paramter!");
   logf(LOG_INFO, "using depth distance threshold %f", depth_distance_threshold_);
   if (!nh_.getParam("show_gui", show_gui_)) show_gui_ = false;                                             // :106
+  // not a parameter of the reference: read the mask back as 1 bit per pixel and expand it to MONO8 here (saves 0.875
+  // byte per pixel of device -> host traffic; subscribers see the same 0 / 255 image)
+  if (!nh_.getParam("packed_mask_readback", packed_mask_)) packed_mask_ = false;
   if (!nh_.getParam("filter_replace_value", filter_replace_value_)) filter_replace_value_ = 0;             // :110
   logf(LOG_INFO, "using filter replace value %f", filter_replace_value_);
 }
@@ -97,6 +100,11 @@ void RealtimeURDFFilter::initGL()
   if (const char *e = std::getenv("RUF_DEVICE")) dev = std::atoi(e);
   if (ruf_create(&ctx_, dev, width_, height_, near_plane_, far_plane_) != RUF_OK)
     throw std::runtime_error(std::string("Could not initialise the CUDA path: ") + ruf_last_error(nullptr));   // ~ :413-416
+  if (packed_mask_ && width_ % 8 == 0) {
+    if (ruf_set_mask_format(ctx_, RUF_MASK_BITS) != RUF_OK) packed_mask_ = false;
+  } else {
+    packed_mask_ = false;
+  }
   initFrameBufferObject();
   loadModels();                                                                                            // :423
   if (renderers_.empty()) throw std::runtime_error("Could not load any models for filtering!");           // :426-427
@@ -138,8 +146,21 @@ int RealtimeURDFFilter::run_device(const void *depth_in, int enc, const double *
     r->update_link_transforms(stamp);
     r->append_part_models(models);
   }
+  unsigned char *mask_dst = mask_out;
+  if (packed_mask_ && mask_out) {
+    mask_bits_.resize((size_t)width_ * height_ / 8);
+    mask_dst = mask_bits_.data();
+  }
   int rc = ruf_filter(ctx_, depth_in, enc, P, view, models.data(), (float)depth_distance_threshold_,
-                      (float)filter_replace_value_, depth_out, mask_out);                                  // :625-631, :729-735
+                      (float)filter_replace_value_, depth_out, mask_dst);                                  // :625-631, :729-735
+  if (rc == RUF_OK && packed_mask_ && mask_out) {
+    // bit i of byte k = pixel 8 k + i -> the MONO8 bytes the reference reads back (GL_UNSIGNED_BYTE, :731-735)
+    const size_t n = mask_bits_.size();
+    for (size_t k = 0; k < n; ++k) {
+      const unsigned b = mask_bits_[k];
+      for (int i = 0; i < 8; ++i) mask_out[8 * k + i] = (b >> i) & 1u ? 255 : 0;
+    }
+  }
   if (rc != RUF_OK) {
     last_error_ = ruf_last_error(ctx_);
     logf(LOG_ERROR, "CUDA path failed: %s", last_error_.c_str());

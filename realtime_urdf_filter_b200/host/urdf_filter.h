@@ -63,6 +63,8 @@ class RealtimeURDFFilter {
   std::string cam_frame_;
   std::string fixed_frame_;
   bool show_gui_ = false;
+  bool packed_mask_ = false;            // `packed_mask_readback`: RUF_MASK_BITS on the wire, expanded to MONO8 on the host
+  std::vector<unsigned char> mask_bits_;
   bool need_mask_ = false;
 
   int width_ = 0;

@@ -420,3 +420,34 @@ def test_sensor_values_straddling_the_threshold(enc):
             assert np.array_equal(got_m, want_m), f"mask differs at {np.count_nonzero(got_m != want_m)} px (md={md})"
             assert np.array_equal(got_d.view(np.uint8), want_d.view(np.uint8))
             assert 0.02 < (want_m == 255).mean() < 0.98
+
+
+@pytest.mark.parametrize("enc", ["u16", "f32"])
+def test_bit_packed_mask_equals_the_byte_mask(enc):
+    """RUF_MASK_BITS (opt-in, 1 bit per pixel on the wire): unpacked it is the 0 / 255 image of the default format, on
+    flat tiles, busy tiles and through the batched host call; widths that are not a multiple of 8 are refused."""
+    sc = helpers.scene("pr2_small")
+    proj, _, _ = sc.proj()
+    frs = [helpers.make_frame(sc, k, enc) for k in (2, 9, 30)]
+    depth = np.stack([f["depth"] for f in frs])
+    views, pms = np.stack([f["view"] for f in frs]), np.stack([f["pm"] for f in frs])
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        want_d, want_m = ctx.filter_batch_host(depth, proj, views, pms, sc.max_diff, sc.replace_value)
+        ctx.set_mask_format(ruf.MASK_BITS)
+        got_d, bits = ctx.filter_batch_host(depth, proj, views, pms, sc.max_diff, sc.replace_value)
+        assert bits.shape == (3, sc.height, sc.width // 8)
+        one_d, one_bits = ctx.filter(depth[1], proj, views[1], pms[1], sc.max_diff, sc.replace_value)
+        ctx.set_mask_format(ruf.MASK_BYTES)
+        again_d, again_m = ctx.filter_batch_host(depth, proj, views, pms, sc.max_diff, sc.replace_value)
+    unpacked = np.unpackbits(bits, axis=-1, bitorder="little") * np.uint8(255)
+    assert np.array_equal(unpacked, want_m) and np.array_equal(got_d.view(np.uint8), want_d.view(np.uint8))
+    assert np.array_equal(np.unpackbits(one_bits, axis=-1, bitorder="little") * np.uint8(255), want_m[1])
+    assert np.array_equal(again_m, want_m)
+    for i, f in enumerate(frs):
+        _, om, _ = helpers.oracle_filter(sc, f)
+        assert np.array_equal(unpacked[i], om)
+    with ruf.Context(100, 75) as ctx:
+        with pytest.raises(ruf.RufError) as e:
+            ctx.set_mask_format(ruf.MASK_BITS)
+        assert e.value.code == ruf.RUF_ERR_INVALID

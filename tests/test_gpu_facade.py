@@ -108,3 +108,20 @@ def test_image_size_change_reinitialises():
         assert "image size has changed" in n.log()
         got_d, _ = n.last_image(0, (240, 320), np.uint16)
         assert np.array_equal(got_d, want_d)
+
+
+def test_packed_mask_readback_publishes_the_same_mono8_mask():
+    sc = helpers.scene("example")
+    fr = helpers.make_frame(sc, 0, "u16")
+    _, want_m, _ = helpers.oracle_filter(sc, fr)
+    n = facade.FilterNode(dict(PARAMS, packed_mask_readback=True), MODELS, camera_offset=((0, 0, 0), (0, 0, 0, 1)))
+    with n:
+        Ts = sc.link_poses(0)
+        n.set_tf("/world", (0, 0, 0, 1), (0, 0, 0))
+        for ln, T in zip(sc.links, Ts):
+            n.set_tf("/EXAMPLE/" + ln.name, synth.quat_from_matrix(T[:3, :3]), T[:3, 3])
+        Tc = synth.make_T(sc.cam_R, sc.cam_xyz)
+        n.set_tf("/camera_rgb_optical_frame", synth.quat_from_matrix(Tc[:3, :3]), Tc[:3, 3])
+        n.callback(fr["depth"], sc.P, stamp=1.0)
+        got_m, em = n.last_image(1, fr["depth"].shape, np.uint8)
+    assert em == "mono8" and np.array_equal(got_m, want_m)
