@@ -69,6 +69,20 @@ struct ruf_context {
 
   int mask_format = RUF_MASK_BYTES;  // ruf_set_mask_format
 
+  // single-frame host call (ruf_filter with pinned buffers): the whole sequence -- uploads, memset, four kernels,
+  // read-backs, status word -- is ONE captured CUDA graph with the depth upload running beside the pose / setup kernels
+  struct FrameGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t n_in = nullptr, n_out = nullptr, n_mask = nullptr;
+    const void *in = nullptr; void *out = nullptr; uint8_t *mask = nullptr;
+    int enc = -1, mask_format = -1, n_parts = -1;
+    float max_diff = 0.f, replace_value = 0.f;
+    const void *ws_bins = nullptr, *stage_in = nullptr;
+    uint32_t cap_big = 0, cap_tile = 0;
+  } fg;
+  bool use_graph = true;             // RUF_NO_GRAPH=1 turns the path off (A/B, debugging)
+
   ruf_stats stats{};
   int last_frames = 0;
 
@@ -109,8 +123,16 @@ static void free_workspace(ruf_context *c)
   c->max_batch = 0;
 }
 
+static void drop_frame_graph(ruf_context *c)
+{
+  if (c->fg.exec) cudaGraphExecDestroy(c->fg.exec);
+  if (c->fg.graph) cudaGraphDestroy(c->fg.graph);
+  c->fg = ruf_context::FrameGraph{};
+}
+
 static void free_staging(ruf_context *c)
 {
+  drop_frame_graph(c);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->d_in[i]); cudaFree(c->d_out[i]); cudaFree(c->d_mask[i]); cudaFree(c->d_mats[i]);
     if (c->h_mats[i]) cudaFreeHost(c->h_mats[i]);
@@ -213,7 +235,7 @@ static ShaderParams shader_params(const ruf_context *c, float max_diff, float re
 
 static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const double *d_proj,
                   const double *d_view, const double *d_model, float max_diff, float replace_value,
-                  void *d_out, uint8_t *d_mask, float *d_zbuf, cudaStream_t s)
+                  void *d_out, uint8_t *d_mask, float *d_zbuf, cudaStream_t s, cudaEvent_t depth_ready = nullptr)
 {
   FrameBuffers fb;
   fb.depth_in = d_in; fb.depth_out = d_out; fb.mask_out = d_mask; fb.zbuf_out = d_zbuf;
@@ -278,7 +300,7 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
     }
   } else {
     cudaError_t e = launch_frames(c->dims, m, c->ws, n_frames, d_proj, d_view, d_model, c->d_lookat, enc,
-                                  sp, fb, s, &launches, ev);
+                                  sp, fb, s, &launches, ev, depth_ready);
     if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   }
   c->stats.kernel_launches += launches;
@@ -319,6 +341,7 @@ int ruf_create(ruf_context **out, int device, int width, int height, double z_ne
     const int v = atoi(e3);
     if (v >= 1 && v <= 64) c->dims.force_fpc = v;
   }
+  if (getenv("RUF_NO_GRAPH")) c->use_graph = false;
   if (const char *e2 = getenv("RUF_SLICE_FRAMES")) {    // tuning aid
     const int v = atoi(e2);
     if (v >= 0 && v <= 65535) c->slice_frames = v;
@@ -377,6 +400,8 @@ int ruf_destroy(ruf_context *c)
     if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
   }
+  if (c->fg.exec) cudaGraphExecDestroy(c->fg.exec);
+  if (c->fg.graph) cudaGraphDestroy(c->fg.graph);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -660,9 +685,130 @@ int ruf_host_copy_ceiling(ruf_context *c, int n_frames, const void *depth_in, in
                        ramp_segments(n_frames, chunk), true);
 }
 
+// ---- single frame, pinned host buffers: one CUDA graph per context ----------------------------------------------
+static bool is_pinned_host(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// RUF_OK: done.  1: not applicable (pageable buffers, caller's stream, profiling) or overflow -> take the pipeline.
+static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, const double *proj, const double *view,
+                              const double *part_model, float max_diff, float replace_value, void *depth_out,
+                              uint8_t *mask_out)
+{
+  if (!c->use_graph || c->profiling || c->stream != c->own_stream || c->slice_frames) return 1;
+  if (!is_pinned_host(depth_in) || !is_pinned_host(depth_out) || (mask_out && !is_pinned_host(mask_out))) return 1;
+  int rc = ensure_workspace(c, 1);
+  if (rc != RUF_OK) return rc;
+  rc = ensure_staging(c, 1);
+  if (rc != RUF_OK) return rc;
+  const size_t es = elem_size(enc), img = (size_t)c->W * c->H, mb = mask_bytes(c);
+  const int P = c->n_parts;
+  cudaStream_t sk = c->stream;
+  double *hm = c->h_mats[0];                      // free: every call of this path ends with a synchronisation
+  std::memcpy(hm, proj, 16 * sizeof(double));
+  std::memcpy(hm + 16, view, 16 * sizeof(double));
+  if (P > 0) std::memcpy(hm + 32, part_model, 16 * sizeof(double) * (size_t)P);
+  const size_t mat_bytes = (32 + 16 * (size_t)P) * sizeof(double);
+  ruf_context::FrameGraph &g = c->fg;
+  const bool same = g.exec && g.enc == enc && g.mask_format == c->mask_format && g.n_parts == P &&
+                    g.max_diff == max_diff && g.replace_value == replace_value && g.ws_bins == c->ws.bins &&
+                    g.stage_in == c->d_in[0] && g.cap_big == c->dims.cap_big && g.cap_tile == c->dims.cap_tile &&
+                    (g.mask != nullptr) == (mask_out != nullptr);
+  if (!same) {
+    drop_frame_graph(c);
+    if (!c->ev_fork) RUF_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    RUF_CUDA(c, cudaStreamBeginCapture(sk, cudaStreamCaptureModeRelaxed));
+    bool ok = true;
+    auto CK = [&](cudaError_t e) { if (e != cudaSuccess) ok = false; };
+    CK(cudaEventRecord(c->ev_fork, sk));
+    CK(cudaStreamWaitEvent(c->s_in, c->ev_fork, 0));
+    CK(cudaMemcpyAsync(c->d_in[0], depth_in, img * es, cudaMemcpyHostToDevice, c->s_in));    // beside the pose / setup kernels
+    CK(cudaEventRecord(c->ev_in[0], c->s_in));
+    CK(cudaMemcpyAsync(c->d_mats[0], hm, mat_bytes, cudaMemcpyHostToDevice, sk));
+    double *dm = c->d_mats[0];
+    const int64_t launches_before = c->stats.kernel_launches;
+    if (ok && launch(c, 1, c->d_in[0], enc, dm, dm + 16, dm + 32, max_diff, replace_value, c->d_out[0],
+                     mask_out ? c->d_mask[0] : nullptr, nullptr, sk, c->ev_in[0]) != RUF_OK) ok = false;
+    c->stats.kernel_launches = launches_before;
+    CK(cudaEventRecord(c->ev_k[0], sk));
+    CK(cudaStreamWaitEvent(c->s_out, c->ev_k[0], 0));
+    if (mask_out) CK(cudaMemcpyAsync(mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost, c->s_out));   // beside the depth read-back
+    CK(cudaEventRecord(c->ev_out[0], c->s_out));
+    CK(cudaMemcpyAsync(depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost, sk));
+    CK(cudaMemcpyAsync(c->h_status, c->ws.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
+    CK(cudaStreamWaitEvent(sk, c->ev_out[0], 0));
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(sk, &graph);
+    if (!ok || ee != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      c->use_graph = false;                       // e.g. a driver that refuses the capture: the pipeline still works
+      return 1;
+    }
+    g.graph = graph;
+    if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); drop_frame_graph(c); c->use_graph = false; return 1; }
+    size_t n = 0;
+    cudaGraphGetNodes(graph, nullptr, &n);
+    std::vector<cudaGraphNode_t> nodes(n);
+    cudaGraphGetNodes(graph, nodes.data(), &n);
+    for (cudaGraphNode_t nd : nodes) {
+      cudaGraphNodeType t;
+      if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeMemcpy) continue;
+      cudaMemcpy3DParms p;
+      if (cudaGraphMemcpyNodeGetParams(nd, &p) != cudaSuccess) continue;
+      if (p.srcPtr.ptr == depth_in) g.n_in = nd;
+      else if (p.dstPtr.ptr == depth_out) g.n_out = nd;
+      else if (mask_out && p.dstPtr.ptr == mask_out) g.n_mask = nd;
+    }
+    if (!g.n_in || !g.n_out || (mask_out && !g.n_mask)) { drop_frame_graph(c); c->use_graph = false; return 1; }
+    g.in = depth_in; g.out = depth_out; g.mask = mask_out;
+    g.enc = enc; g.mask_format = c->mask_format; g.n_parts = P; g.max_diff = max_diff; g.replace_value = replace_value;
+    g.ws_bins = c->ws.bins; g.stage_in = c->d_in[0]; g.cap_big = c->dims.cap_big; g.cap_tile = c->dims.cap_tile;
+  } else {
+    // same shape of work, other host buffers: retarget the three copy nodes of the instantiated graph
+    if (g.in != depth_in) {
+      RUF_CUDA(c, cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_in, c->d_in[0], depth_in, img * es, cudaMemcpyHostToDevice));
+      g.in = depth_in;
+    }
+    if (g.out != depth_out) {
+      RUF_CUDA(c, cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_out, depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost));
+      g.out = depth_out;
+    }
+    if (mask_out && g.mask != mask_out) {
+      RUF_CUDA(c, cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_mask, mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost));
+      g.mask = mask_out;
+    }
+  }
+  RUF_CUDA(c, cudaGraphLaunch(g.exec, sk));
+  RUF_CUDA(c, cudaStreamSynchronize(sk));
+  c->stats = ruf_stats{};
+  c->stats.frames = 1;
+  c->stats.kernel_launches = 4;
+  c->stats.h2d_bytes = (int64_t)(mat_bytes + img * es);
+  c->stats.d2h_bytes = (int64_t)(img * es + (mask_out ? mb : 0));
+  c->last_frames = 1;
+  if (*c->h_status) {                             // an internal list overflowed: grow it and let the pipeline redo the frame
+    const uint32_t flags = *c->h_status;
+    RUF_CUDA(c, cudaMemsetAsync(c->ws.status, 0, sizeof(uint32_t), sk));
+    *c->h_status = 0;
+    if (flags & kFlagBigOverflow) c->want_big = 4LL * c->dims.cap_big;
+    if (flags & kFlagBinOverflow) c->want_bin = 2LL * c->dims.cap_tile;
+    return 1;
+  }
+  return RUF_OK;
+}
+
 int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj, const double *view,
                const double *part_model, float max_diff, float replace_value, void *depth_out, uint8_t *mask_out)
 {
+  if (c && depth_in && depth_out && proj && view && (c->n_parts == 0 || part_model) && c->have_model &&
+      (enc == RUF_ENC_F32_M || enc == RUF_ENC_U16_MM) && cudaSetDevice(c->device) == cudaSuccess) {
+    const int rc = single_frame_graph(c, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out, mask_out);
+    if (rc != 1) return rc;
+  }
   return ruf_filter_batch_host(c, 1, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
                                mask_out);
 }

@@ -201,6 +201,7 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
                           const double *d_proj, const double *d_view, const double *d_part_model,
                           const double *d_lookat, int enc, const ShaderParams &sp,
                           const FrameBuffers &fb, cudaStream_t s, int *n_launches,
-                          cudaEvent_t *stage_events /* null or kNumStages+1 events */);
+                          cudaEvent_t *stage_events /* null or kNumStages+1 events */,
+                          cudaEvent_t depth_ready = nullptr /* the raster kernel waits for it (upload of the depth image) */);
 
 }  // namespace ruf

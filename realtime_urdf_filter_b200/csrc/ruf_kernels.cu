@@ -1388,7 +1388,6 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
 
   // ---- fused fragment stage (include/shaders/urdf_filter.frag:19-35): 8 pixels per thread and row, vector loads/stores ----
   const uint32_t repl_u16 = f32_to_u16(sp.replace_value);     // convertTo(CV_16U, 1000) of the replaced pixels, :311
-  const uint32_t repl2 = repl_u16 | (repl_u16 << 16);
   const float kInf = __int_as_float(0x7f800000);
 #pragma unroll
   for (int half = 0; half < kRowsPerThread; ++half) {
@@ -1666,7 +1665,8 @@ cudaError_t check_kernel_image()
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
                           const double *d_proj, const double *d_view, const double *d_part_model,
                           const double *d_lookat, int enc, const ShaderParams &sp,
-                          const FrameBuffers &fb, cudaStream_t s, int *n_launches, cudaEvent_t *ev)
+                          const FrameBuffers &fb, cudaStream_t s, int *n_launches, cudaEvent_t *ev,
+                          cudaEvent_t depth_ready)
 {
   cudaError_t err;
   int launches = 0;
@@ -1710,6 +1710,8 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (ev) cudaEventRecord(ev[2], s);
   }
   {
+    // the depth image is first touched here: its upload may still be running under the pose / setup kernels
+    if (depth_ready && (err = cudaStreamWaitEvent(s, depth_ready, 0)) != cudaSuccess) return err;
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (enc == 1)
       ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);

@@ -451,3 +451,75 @@ def test_bit_packed_mask_equals_the_byte_mask(enc):
         with pytest.raises(ruf.RufError) as e:
             ctx.set_mask_format(ruf.MASK_BITS)
         assert e.value.code == ruf.RUF_ERR_INVALID
+
+
+def _pinned(shape, dtype):
+    import ctypes
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = ruf.host_alloc(n)
+    buf = (ctypes.c_uint8 * n).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
+
+
+def test_single_frame_graph_path_with_pinned_buffers():
+    """ruf_filter with pinned host buffers runs as ONE captured CUDA graph (uploads, memset, kernels, read-backs).  Same
+    results as the staged pipeline and the oracle: first call (capture), same buffers again, other buffers (copy nodes
+    retargeted), other shader scalars / encoding / no mask (re-capture)."""
+    sc = helpers.scene("pr2_small")
+    proj, _, _ = sc.proj()
+    lib = ruf.load()
+    bufs = []
+    try:
+        sets = []
+        for _ in range(2):
+            d_in, p1 = _pinned((sc.height, sc.width), np.uint16)
+            d_out, p2 = _pinned((sc.height, sc.width), np.uint16)
+            m_out, p3 = _pinned((sc.height, sc.width), np.uint8)
+            bufs += [p1, p2, p3]
+            sets.append((d_in, d_out, m_out))
+        f_in, p4 = _pinned((sc.height, sc.width), np.float32)
+        f_out, p5 = _pinned((sc.height, sc.width), np.float32)
+        bufs += [p4, p5]
+        with ruf.Context(sc.width, sc.height) as ctx:
+            ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+
+            def call(d_in, d_out, m_out, fr, enc, md):
+                v = np.ascontiguousarray(fr["view"], np.float64)
+                pm = np.ascontiguousarray(fr["pm"], np.float64)
+                pr = np.ascontiguousarray(proj, np.float64)
+                rc = lib.ruf_filter(ctx._h, d_in.ctypes.data, enc, pr.ctypes.data, v.ctypes.data, pm.ctypes.data, md,
+                                    sc.replace_value, d_out.ctypes.data, m_out.ctypes.data if m_out is not None else None)
+                assert rc == 0, lib.ruf_last_error(ctx._h)
+                return ctx.stats()
+
+            for i, k in enumerate((0, 5, 5, 12, 20)):
+                d_in, d_out, m_out = sets[i % 2] if i != 2 else sets[1]
+                fr = helpers.make_frame(sc, k, "u16")
+                d_in[:] = fr["depth"]
+                d_out[:] = 0xFFFF
+                m_out[:] = 7
+                st = call(d_in, d_out, m_out, fr, ruf.ENC_U16_MM, sc.max_diff)
+                assert st["kernel_launches"] == 4 and st["d2h_bytes"] == sc.width * sc.height * 3
+                want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+                assert np.array_equal(d_out, want_d) and np.array_equal(m_out, want_m)
+            # other threshold -> re-captured graph; then no mask; then 32FC1
+            fr = helpers.make_frame(sc, 3, "u16")
+            d_in, d_out, m_out = sets[0]
+            d_in[:] = fr["depth"]
+            call(d_in, d_out, m_out, fr, ruf.ENC_U16_MM, 0.2)
+            want_d, want_m, _ = helpers.oracle_filter(sc, fr, max_diff=0.2)
+            assert np.array_equal(d_out, want_d) and np.array_equal(m_out, want_m)
+            m_out[:] = 9
+            call(d_in, d_out, None, fr, ruf.ENC_U16_MM, 0.2)
+            assert np.array_equal(d_out, want_d) and np.all(m_out == 9)
+            fr = helpers.make_frame(sc, 3, "f32")
+            f_in[:] = fr["depth"]
+            call(f_in, f_out, m_out, fr, ruf.ENC_F32_M, sc.max_diff)
+            want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+            assert np.array_equal(f_out.view(np.uint32), want_d.view(np.uint32)) and np.array_equal(m_out, want_m)
+            # pageable buffers still take the staged pipeline on the same context
+            got_d, got_m = ctx.filter(fr["depth"], proj, fr["view"], fr["pm"], sc.max_diff, sc.replace_value)
+            assert np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32)) and np.array_equal(got_m, want_m)
+    finally:
+        for p in bufs:
+            ruf.host_free(p)
