@@ -76,12 +76,15 @@ struct ruf_context {
     cudaGraphExec_t exec = nullptr;
     cudaGraphNode_t n_in = nullptr, n_out = nullptr, n_mask = nullptr;
     const void *in = nullptr; void *out = nullptr; uint8_t *mask = nullptr;
-    int enc = -1, mask_format = -1, n_parts = -1;
+    int enc = -1, mask_format = -1, n_parts = -1, multipass = -1;
     float max_diff = 0.f, replace_value = 0.f;
     const void *ws_bins = nullptr, *stage_in = nullptr;
     uint32_t cap_big = 0, cap_tile = 0;
   } fg;
   bool use_graph = true;             // RUF_NO_GRAPH=1 turns the path off (A/B, debugging)
+  int multipass_mode = -1;           // raster kernel variant: -1 automatic (share of wide records in the last launches), 0 / 1 forced
+  bool multipass = false;            // the current choice
+  double wide_share = -1.0;          // wide / kept records of the launches since the previous status read-back (-1: none yet)
 
   ruf_stats stats{};
   int last_frames = 0;
@@ -246,6 +249,12 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
     return fail(c, RUF_ERR_INVALID, "RUF_MASK_BITS needs an image width that is a multiple of 8 and 16-byte aligned depth buffers");
   const ShaderParams sp = shader_params(c, max_diff, replace_value);
   Model m{c->meshlets, c->mverts, c->mtris, c->part_aabb};
+  // Raster kernel variant of this launch.  Automatic: the share of kept records that span more than kMaxUnits raster
+  // units, as counted by the setup kernel in the launches whose statistics have reached the host by now (they ride on
+  // the status word's read-back, one launch or more behind: a heuristic, both variants give identical results).
+  if (c->multipass_mode == 0 || c->multipass_mode == 1) c->multipass = c->multipass_mode == 1;
+  else if (c->wide_share >= 0.0) c->multipass = c->wide_share > (c->multipass ? 0.10 : 0.15);     // with hysteresis
+  c->dims.multipass = c->multipass ? 1 : 0;
   int launches = 0;
   cudaEvent_t *ev = nullptr;
   if (c->profiling) {
@@ -351,10 +360,11 @@ int ruf_create(ruf_context **out, int device, int width, int height, double z_ne
     if ((e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   }
-  if ((e = cudaMalloc(&c->ws.status, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMemset(c->ws.status, 0, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
-  if ((e = cudaHostAlloc(&c->h_status, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
-  *c->h_status = 0;
+  if ((e = cudaMalloc(&c->ws.status, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(c->ws.status, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaHostAlloc(&c->h_status, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  c->h_status[0] = c->h_status[1] = c->h_status[2] = c->h_status[3] = 0;
+  if (const char *e4 = getenv("RUF_MULTIPASS")) c->multipass_mode = atoi(e4);    // 0 / 1 force a variant, anything else = automatic
   double la[16];
   ruf_lookat(la);
   if ((e = cudaMalloc(&c->d_lookat, sizeof(la))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -419,10 +429,18 @@ int ruf_set_stream(ruf_context *c, void *cuda_stream)
   return RUF_OK;
 }
 
+// the launch statistics that ride on the status word: share of kept records spanning more than kMaxUnits raster units
+static void take_launch_stats(ruf_context *c)
+{
+  if (c->h_status[1] >= 256u) c->wide_share = (double)c->h_status[2] / (double)c->h_status[1];
+}
+
 static int check_status(ruf_context *c, cudaStream_t s)
 {
-  RUF_CUDA(c, cudaMemcpyAsync(c->h_status, c->ws.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  RUF_CUDA(c, cudaMemcpyAsync(c->h_status, c->ws.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  RUF_CUDA(c, cudaMemsetAsync(c->ws.status + 1, 0, 2 * sizeof(uint32_t), s));      // statistics restart with every read-back
   RUF_CUDA(c, cudaStreamSynchronize(s));
+  take_launch_stats(c);
   const uint32_t flags = *c->h_status;
   if (flags) {
     RUF_CUDA(c, cudaMemsetAsync(c->ws.status, 0, sizeof(uint32_t), s));
@@ -713,7 +731,9 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
   if (P > 0) std::memcpy(hm + 32, part_model, 16 * sizeof(double) * (size_t)P);
   const size_t mat_bytes = (32 + 16 * (size_t)P) * sizeof(double);
   ruf_context::FrameGraph &g = c->fg;
-  const bool same = g.exec && g.enc == enc && g.mask_format == c->mask_format && g.n_parts == P &&
+  const bool want_mp = c->multipass_mode == 0 || c->multipass_mode == 1 ? c->multipass_mode == 1
+                       : (c->wide_share >= 0.0 ? c->wide_share > (c->multipass ? 0.10 : 0.15) : c->multipass);
+  const bool same = g.exec && g.multipass == (int)want_mp && g.enc == enc && g.mask_format == c->mask_format && g.n_parts == P &&
                     g.max_diff == max_diff && g.replace_value == replace_value && g.ws_bins == c->ws.bins &&
                     g.stage_in == c->d_in[0] && g.cap_big == c->dims.cap_big && g.cap_tile == c->dims.cap_tile &&
                     (g.mask != nullptr) == (mask_out != nullptr);
@@ -738,7 +758,8 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
     if (mask_out) CK(cudaMemcpyAsync(mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost, c->s_out));   // beside the depth read-back
     CK(cudaEventRecord(c->ev_out[0], c->s_out));
     CK(cudaMemcpyAsync(depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost, sk));
-    CK(cudaMemcpyAsync(c->h_status, c->ws.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
+    CK(cudaMemcpyAsync(c->h_status, c->ws.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
+    CK(cudaMemsetAsync(c->ws.status + 1, 0, 2 * sizeof(uint32_t), sk));
     CK(cudaStreamWaitEvent(sk, c->ev_out[0], 0));
     cudaGraph_t graph = nullptr;
     const cudaError_t ee = cudaStreamEndCapture(sk, &graph);
@@ -765,7 +786,7 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
     }
     if (!g.n_in || !g.n_out || (mask_out && !g.n_mask)) { drop_frame_graph(c); c->use_graph = false; return 1; }
     g.in = depth_in; g.out = depth_out; g.mask = mask_out;
-    g.enc = enc; g.mask_format = c->mask_format; g.n_parts = P; g.max_diff = max_diff; g.replace_value = replace_value;
+    g.multipass = (int)c->multipass; g.enc = enc; g.mask_format = c->mask_format; g.n_parts = P; g.max_diff = max_diff; g.replace_value = replace_value;
     g.ws_bins = c->ws.bins; g.stage_in = c->d_in[0]; g.cap_big = c->dims.cap_big; g.cap_tile = c->dims.cap_tile;
   } else {
     // same shape of work, other host buffers: retarget the three copy nodes of the instantiated graph
@@ -790,6 +811,7 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
   c->stats.h2d_bytes = (int64_t)(mat_bytes + img * es);
   c->stats.d2h_bytes = (int64_t)(img * es + (mask_out ? mb : 0));
   c->last_frames = 1;
+  take_launch_stats(c);
   if (*c->h_status) {                             // an internal list overflowed: grow it and let the pipeline redo the frame
     const uint32_t flags = *c->h_status;
     RUF_CUDA(c, cudaMemsetAsync(c->ws.status, 0, sizeof(uint32_t), sk));

@@ -130,10 +130,10 @@ static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 // dynamic shared memory of the raster kernel: record ring + per-warp unit tables
 constexpr size_t kRasterDynSmem = sizeof(TriRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
 
-// Per-frame counter block (uint32 words): [0] big-list entries  [1] unused  [2] flags
+// Per-frame counter block (uint32 words): [0] big-list entries  [1] kept records spanning > kMaxUnits units  [2] flags
 // [3] kept (binned) triangles  [4 + 2 t], [5 + 2 t]: records at the FRONT of tile t's list (triangles facing
 // the camera) and at its BACK (facing away: drawn last, depth-culled); one 8-byte word per tile
-constexpr int kCtrBig = 0, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
+constexpr int kCtrBig = 0, kCtrWide = 1, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
 
 struct Dims {
   int W, H;
@@ -144,6 +144,7 @@ struct Dims {
   int n_meshlets;              // setup CTAs per frame
   int ctr_stride;              // uint32 words of one frame's counter block = kCtrWords + 2 * ntiles
   int force_fpc;               // > 0: frames per setup CTA (testing aid, RUF_SETUP_FRAMES_FORCE); 0 = heuristic
+  int multipass;               // raster kernel variant of this launch (ruf_raster_filter_kernel<ENC, MP>)
   float halfw, halfh, guard_x, guard_y;
 };
 
@@ -169,7 +170,7 @@ struct Workspace {
   uint32_t *ctr;         // [frame][ctr_stride]
   TriRec *big;           // [frame][cap_big]
   TriRec *bins;          // [frame][tile][cap_tile] one record list per tile
-  uint32_t *status;      // sticky OR of all frame flags
+  uint32_t *status;      // [0] sticky OR of all frame flags  [1] kept records, [2] wide records since the host last cleared them
   uint4 *tinfo;          // [frame][tile] ruf_tile_info_kernel -> ruf_raster_filter_kernel
 };
 

@@ -533,7 +533,14 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         }
         const unsigned act = __ballot_sync(0xffffffffu, has);
         if (!act) continue;
-        if (lane == 0) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
+        // statistics only: kept records, and how many of them span more than kMaxUnits raster units (the host picks the
+        // raster kernel's variant for the NEXT launch from their share)
+        const int bw = (int)(rec.bx >> 16) - (int)(rec.bx & 0xffffu) + 1, bh = (int)(rec.by >> 16) - (int)(rec.by & 0xffffu) + 1;
+        const unsigned wide = __ballot_sync(0xffffffffu, has && ((bw + kUW - 1) / kUW) * ((bh + kUH - 1) / kUH) > kMaxUnits);
+        if (lane == 0) {
+          atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));
+          if (wide) atomicAdd(&ctr[kCtrWide], (uint32_t)__popc(wide));
+        }
         const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, (uint32_t)rec.x1, (uint32_t)rec.y1);
         const uint4 q1 = make_uint4((uint32_t)rec.x2, (uint32_t)rec.y2, __float_as_uint(rec.z0), __float_as_uint(rec.gx));
         const uint4 q2 = make_uint4(__float_as_uint(rec.gy), rec.bx, rec.by, 0u);
@@ -877,7 +884,11 @@ ruf_tile_info_kernel(Dims d, int n_frames, const TriRec *__restrict__ big_all, c
   const uint32_t *ctr = ctr_all + (size_t)frame * d.ctr_stride;
   const uint2 nfb = __ldg(reinterpret_cast<const uint2 *>(ctr + kCtrWords) + tile);
   uint32_t flags = (nfb.x + nfb.y > d.cap_tile) ? kFlagBinOverflow : 0u;     // the two runs met: the host grows cap_tile and retries
-  if (tile == 0) flags |= __ldg(ctr + kCtrFlags);
+  if (tile == 0) {
+    flags |= __ldg(ctr + kCtrFlags);
+    atomicAdd(status + 1, __ldg(ctr + kCtrKept));         // totals of this launch: kept records, "wide" ones among them
+    atomicAdd(status + 2, __ldg(ctr + kCtrWide));
+  }
   if (flags) atomicOr(status, flags);
   uint4 ti = make_uint4(0u, 0u, 0u, 0u);
   const uint32_t nbig = min(__ldg(ctr + kCtrBig), d.cap_big);
@@ -907,7 +918,11 @@ ruf_tile_info_kernel(Dims d, int n_frames, const TriRec *__restrict__ big_all, c
   tinfo[gid] = ti;
 }
 
-template <int ENC>
+// MP ("multi-pass units"): records with more than kMaxUnits units stay on the unit path and are dealt out over several
+// passes instead of being parked for the cooperative 8x4-footprint walk; chosen per launch by the host from the share of
+// such records in the previous launch (ruf_api.cu: choose_multipass).  At 1280x960 the PR2-like model's slivers are
+// mostly above 24 units: MP is 34 % faster on C3; on C2 (5 % such records) the plain variant is 4 % faster.
+template <int ENC, bool MP>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
                          const uint32_t *__restrict__ ctr_all, const uint4 *__restrict__ tinfo, ShaderParams sp, FrameBuffers fb)
@@ -1133,10 +1148,13 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
           j0 = max((int)(r.by & 0xffffu), tile_y0); j1 = min((int)(r.by >> 16), tile_y0 + kTileH - 1);
           const int ex = max(r.x0, max(r.x1, r.x2)) - min(r.x0, min(r.x1, r.x2));
           const int ey = max(r.y0, max(r.y1, r.y2)) - min(r.y0, min(r.y1, r.y2));
-          const bool narrow = ex < 16384 && ey < 16384;     // every edge-function factor < 2^14: int32 is exact
+          // 32-bit unit arithmetic is exact when every edge-function factor is below 2^14; MP admits long thin slivers
+          // too: |E_k| <= 2 ex ey + 256 (ex + ey) at every sample of the bbox, below 2^31 when ex * ey < 2^29
+          const bool narrow = MP ? ((long long)ex * ey < (1LL << 29) && ex < (1 << 21) && ey < (1 << 21))
+                                 : (ex < 16384 && ey < 16384);
           ncb = (i1 - i0 + kUW) / kUW;                       // unit columns
           nunits = ncb * ((j1 - j0 + kUH) / kUH);
-          kind = narrow ? ((nunits <= kMaxUnits) ? 1 : 2) : 3;
+          kind = narrow ? ((MP || nunits <= kMaxUnits) ? 1 : 2) : 3;
           if (pass) {
             // depth cull: z is monotone in both sample coordinates (every step is a correctly rounded fma), so
             // its minimum over the bbox sits on a corner sample, evaluated with the rasteriser's own expressions
@@ -1218,18 +1236,23 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         // ---- phase 2: the units (kUW x kUH samples) of the 32 records are dealt out to the lanes
         // round by round, so every lane does the same amount of branch-free work.  Unit table in
         // shared memory: owner lane | unit row << 5 | unit column << 10.
-        int incl = nunits;
+        int udone = 0;                         // MP: units of this lane's record dealt out in earlier passes
+        for (;;) {
+        const int nu = MP ? min(nunits - udone, kMaxUnits) : nunits;
+        if (MP && !__any_sync(0xffffffffu, nu > 0)) break;
+        int incl = nu;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int y = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += y;
         }
-        const int excl = incl - nunits;
+        const int excl = incl - nu;
         const int items = __shfl_sync(0xffffffffu, incl, 31);
         uint16_t *utab = s_units[warp];
         {
           int row = 0, cb = 0;
-          for (int q = 0; q < nunits; ++q) {
+          if (udone) { row = udone / ncb; cb = udone - row * ncb; }
+          for (int q = 0; q < nu; ++q) {
             utab[excl + q] = (uint16_t)(lane | (row << 5) | (cb << 10));
             if (++cb == ncb) { cb = 0; ++row; }
           }
@@ -1292,7 +1315,10 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
             }
           }
         }
-        __syncwarp();                          // the unit table is rewritten by the next batch
+        __syncwarp();                          // the unit table is rewritten by the next pass / batch
+        if (!MP) break;
+        udone += nu;
+        }
       }
       }
     }
@@ -1652,14 +1678,14 @@ cudaError_t launch_fk(const Kinematics &k, int n_frames, const double *d_joint_q
 cudaError_t check_kernel_image()
 {
   cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)ruf_raster_filter_kernel<1>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)ruf_raster_filter_kernel<1, false>);
   if (e != cudaSuccess) return e;
   // opt in to > 48 KB of dynamic shared memory (per device: call once per context)
-  e = cudaFuncSetAttribute((const void *)ruf_raster_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kRasterDynSmem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void *)ruf_raster_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)kRasterDynSmem);
+  const void *fns[4] = {(const void *)ruf_raster_filter_kernel<0, false>, (const void *)ruf_raster_filter_kernel<1, false>,
+                        (const void *)ruf_raster_filter_kernel<0, true>, (const void *)ruf_raster_filter_kernel<1, true>};
+  for (const void *f : fns)
+    if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterDynSmem)) != cudaSuccess) return e;
+  return cudaSuccess;
 }
 
 cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, int n_frames,
@@ -1713,10 +1739,13 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     // the depth image is first touched here: its upload may still be running under the pose / setup kernels
     if (depth_ready && (err = cudaStreamWaitEvent(s, depth_ready, 0)) != cudaSuccess) return err;
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
-    if (enc == 1)
-      ruf_raster_filter_kernel<1><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
-    else
-      ruf_raster_filter_kernel<0><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
+    if (d.multipass) {
+      if (enc == 1) ruf_raster_filter_kernel<1, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
+      else ruf_raster_filter_kernel<0, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
+    } else {
+      if (enc == 1) ruf_raster_filter_kernel<1, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
+      else ruf_raster_filter_kernel<0, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
+    }
     ++launches;
     if ((err = check("ruf_raster_filter_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[3], s);

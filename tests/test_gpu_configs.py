@@ -523,3 +523,28 @@ def test_single_frame_graph_path_with_pinned_buffers():
     finally:
         for p in bufs:
             ruf.host_free(p)
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "auto"])
+def test_both_raster_kernel_variants_are_bit_exact(monkeypatch, mode):
+    """ruf_raster_filter_kernel<ENC, MP>: records above kMaxUnits units either parked for the cooperative footprint walk
+    (MP = 0) or dealt out over several unit passes (MP = 1); the host picks per launch from the previous launches'
+    statistics (RUF_MULTIPASS forces one).  Same bits either way, on a model whose records are mostly wide (6000
+    triangles at 640x480) and on the 90k one (none are), across the switch-over of the automatic mode."""
+    if mode != "auto":
+        monkeypatch.setenv("RUF_MULTIPASS", mode)
+    else:
+        monkeypatch.delenv("RUF_MULTIPASS", raising=False)
+    for name in ("pr2_small", "pr2"):
+        sc = helpers.scene(name)
+        proj, _, _ = sc.proj()
+        frs = [helpers.make_frame(sc, k, "u16") for k in (1, 6, 14)]
+        depth = np.stack([f["depth"] for f in frs])
+        views, pms = np.stack([f["view"] for f in frs]), np.stack([f["pm"] for f in frs])
+        with ruf.Context(sc.width, sc.height) as ctx:
+            ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+            for rep in range(3):       # automatic mode: the first call runs the default variant, later ones what the statistics say
+                got_d, got_m = ctx.filter_batch_host(depth, proj, views, pms, sc.max_diff, sc.replace_value)
+                for i, f in enumerate(frs):
+                    want_d, want_m, _ = helpers.oracle_filter(sc, f)
+                    assert np.array_equal(got_d[i], want_d) and np.array_equal(got_m[i], want_m), (name, rep, i)
