@@ -101,6 +101,7 @@ constexpr int kMeshParts = 32;
 constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   // triangles per thread
 constexpr int kSetupFrames = RUF_SETUP_FRAMES;  // frames a setup CTA loops over with its meshlet in registers
 static_assert(kMeshVerts <= 1024 && kMeshTris <= 1023, "meshlet indices are packed in 10 bits");
+constexpr int kMultiPassUnits = 128;            // MP variant: records up to this many units are dealt out in passes of kMaxUnits
 constexpr int kWideCap = 16;                    // wide records a raster CTA parks for its cooperative final phase
 constexpr int kMaxTiles = 4096;
 constexpr int kPartStride = 8;                  // floats per part in Model::part_aabb
@@ -130,10 +131,10 @@ static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 // dynamic shared memory of the raster kernel: record ring + per-warp unit tables
 constexpr size_t kRasterDynSmem = sizeof(TriRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
 
-// Per-frame counter block (uint32 words): [0] big-list entries  [1] kept records spanning > kMaxUnits units  [2] flags
+// Per-frame counter block (uint32 words): [0] big-list entries  [1] unused  [2] flags
 // [3] kept (binned) triangles  [4 + 2 t], [5 + 2 t]: records at the FRONT of tile t's list (triangles facing
 // the camera) and at its BACK (facing away: drawn last, depth-culled); one 8-byte word per tile
-constexpr int kCtrBig = 0, kCtrWide = 1, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
+constexpr int kCtrBig = 0, kCtrFlags = 2, kCtrKept = 3, kCtrWords = 4;
 
 struct Dims {
   int W, H;
@@ -170,7 +171,7 @@ struct Workspace {
   uint32_t *ctr;         // [frame][ctr_stride]
   TriRec *big;           // [frame][cap_big]
   TriRec *bins;          // [frame][tile][cap_tile] one record list per tile
-  uint32_t *status;      // [0] sticky OR of all frame flags  [1] kept records, [2] wide records since the host last cleared them
+  uint32_t *status;      // [0] sticky OR of all frame flags  [1] kept records (tile-info kernel), [2] (record, tile) pairs above kMaxUnits units (raster kernel) since the host last cleared them
   uint4 *tinfo;          // [frame][tile] ruf_tile_info_kernel -> ruf_raster_filter_kernel
 };
 

@@ -533,14 +533,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         }
         const unsigned act = __ballot_sync(0xffffffffu, has);
         if (!act) continue;
-        // statistics only: kept records, and how many of them span more than kMaxUnits raster units (the host picks the
-        // raster kernel's variant for the NEXT launch from their share)
-        const int bw = (int)(rec.bx >> 16) - (int)(rec.bx & 0xffffu) + 1, bh = (int)(rec.by >> 16) - (int)(rec.by & 0xffffu) + 1;
-        const unsigned wide = __ballot_sync(0xffffffffu, has && ((bw + kUW - 1) / kUW) * ((bh + kUH - 1) / kUH) > kMaxUnits);
-        if (lane == 0) {
-          atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));
-          if (wide) atomicAdd(&ctr[kCtrWide], (uint32_t)__popc(wide));
-        }
+        if (lane == 0) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
         const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, (uint32_t)rec.x1, (uint32_t)rec.y1);
         const uint4 q1 = make_uint4((uint32_t)rec.x2, (uint32_t)rec.y2, __float_as_uint(rec.z0), __float_as_uint(rec.gx));
         const uint4 q2 = make_uint4(__float_as_uint(rec.gy), rec.bx, rec.by, 0u);
@@ -886,8 +879,7 @@ ruf_tile_info_kernel(Dims d, int n_frames, const TriRec *__restrict__ big_all, c
   uint32_t flags = (nfb.x + nfb.y > d.cap_tile) ? kFlagBinOverflow : 0u;     // the two runs met: the host grows cap_tile and retries
   if (tile == 0) {
     flags |= __ldg(ctr + kCtrFlags);
-    atomicAdd(status + 1, __ldg(ctr + kCtrKept));         // totals of this launch: kept records, "wide" ones among them
-    atomicAdd(status + 2, __ldg(ctr + kCtrWide));
+    atomicAdd(status + 1, __ldg(ctr + kCtrKept));         // kept records of the launches since the last status read-back
   }
   if (flags) atomicOr(status, flags);
   uint4 ti = make_uint4(0u, 0u, 0u, 0u);
@@ -925,7 +917,8 @@ ruf_tile_info_kernel(Dims d, int n_frames, const TriRec *__restrict__ big_all, c
 template <int ENC, bool MP>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
-                         const uint32_t *__restrict__ ctr_all, const uint4 *__restrict__ tinfo, ShaderParams sp, FrameBuffers fb)
+                         const uint32_t *__restrict__ ctr_all, const uint4 *__restrict__ tinfo, ShaderParams sp, FrameBuffers fb,
+                         uint32_t *status)
 {
   // 8 warps rasterise and shade.  The tile's record list streams into a shared-memory ring by bulk async
   // copies (TMA): thread 0 starts the first kStages chunks, later refills are issued by whichever warp
@@ -941,7 +934,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   __shared__ int s_issued[kStages];              // latest chunk whose bulk copies were issued into each ring stage
   __shared__ uint32_t s_zblk[(kTileH / 4) * 16]; // maxima of the 4x4 blocks of the z tile (depth cull)
   __shared__ uint8_t s_bigcls[kRasterThreads];
-  __shared__ uint32_t s_nwide;
+  __shared__ uint32_t s_nwide, s_nstat;
   __shared__ __align__(16) TriRec s_wide[kWideCap];   // wide records of this tile, rasterised by the whole CTA at the end
   __shared__ uint32_t s_zcut, s_zown;            // big-list occlusion: smallest farthest-corner z of a covering record, its index
   __shared__ float s_bigz[kRasterThreads];
@@ -1041,7 +1034,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
       mbar_fence_init();
       s_next[0] = 0; s_next[1] = 0;
-      s_nwide = 0;
+      s_nwide = 0; s_nstat = 0;
 #pragma unroll
       for (int c = 0; c < kStages; ++c) {
         s_issued[c] = -1;
@@ -1154,7 +1147,10 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
                                  : (ex < 16384 && ey < 16384);
           ncb = (i1 - i0 + kUW) / kUW;                       // unit columns
           nunits = ncb * ((j1 - j0 + kUH) / kUH);
-          kind = narrow ? ((MP || nunits <= kMaxUnits) ? 1 : 2) : 3;
+          // MP: up to kMultiPassUnits units (slivers) stay on the unit path; larger, compact triangles are cheaper in the
+          // cooperative 8x4-footprint walk
+          kind = narrow ? ((nunits <= (MP ? kMultiPassUnits : kMaxUnits)) ? 1 : 2) : 3;
+          if (nunits > kMaxUnits) atomicAdd(&s_nstat, 1u);   // statistics for the host's choice of the variant (none on C2)
           if (pass) {
             // depth cull: z is monotone in both sample coordinates (every step is a correctly rounded fma), so
             // its minimum over the bbox sits on a corner sample, evaluated with the rasteriser's own expressions
@@ -1323,6 +1319,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
       }
     }
     consumer_bar_sync();                      // every record of the tile has been rasterised or parked
+    if (tid == 0 && s_nstat) atomicAdd(status + 2, s_nstat);
     const uint32_t nwide = min(s_nwide, (uint32_t)kWideCap);      // CTA-uniform
     if (nwide) {
       for (uint32_t w = 0; w < nwide; ++w) {
@@ -1740,11 +1737,11 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (depth_ready && (err = cudaStreamWaitEvent(s, depth_ready, 0)) != cudaSuccess) return err;
     dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
     if (d.multipass) {
-      if (enc == 1) ruf_raster_filter_kernel<1, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
-      else ruf_raster_filter_kernel<0, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
+      if (enc == 1) ruf_raster_filter_kernel<1, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
+      else ruf_raster_filter_kernel<0, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
     } else {
-      if (enc == 1) ruf_raster_filter_kernel<1, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
-      else ruf_raster_filter_kernel<0, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb);
+      if (enc == 1) ruf_raster_filter_kernel<1, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
+      else ruf_raster_filter_kernel<0, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
     }
     ++launches;
     if ((err = check("ruf_raster_filter_kernel")) != cudaSuccess) return err;
