@@ -9,7 +9,9 @@ tmp=$(mktemp -d)
 cp -r "$root/realtime_urdf_filter_b200" "$root/include" "$tmp/"
 rm -f "$tmp"/realtime_urdf_filter_b200/*.so
 if [ "$commit" != "-" ]; then
-  for f in ruf_kernels.cu ruf_device.cuh; do git -C "$root" show "$commit:realtime_urdf_filter_b200/csrc/$f" > "$tmp/realtime_urdf_filter_b200/csrc/$f"; done
+  files="ruf_kernels.cu ruf_device.cuh"
+  [ "${ALLSRC:-0}" = 1 ] && files="ruf_kernels.cu ruf_device.cuh ruf_api.cu"      # when the C ABI did not change since <commit>
+  for f in $files; do git -C "$root" show "$commit:realtime_urdf_filter_b200/csrc/$f" > "$tmp/realtime_urdf_filter_b200/csrc/$f"; done
 fi
 mkdir -p "$root/variants"
 (cd "$tmp" && RUF_LIB_PATH="$root/variants/lib_$name.so" RUF_EXTRA_NVCC="$*" python -m realtime_urdf_filter_b200.build --force > /dev/null)

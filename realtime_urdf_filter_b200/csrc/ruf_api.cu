@@ -163,7 +163,7 @@ static int max_frames_in_budget(const ruf_context *c)
 {
   static const double gb = [] { const char *e = getenv("RUF_WORKSPACE_GB"); const double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 48.0; }();
   const long long cap_big = c->want_big > 0 ? c->want_big : 1024;
-  const double per_frame = (double)sizeof(TriRec) * ((double)c->dims.ntiles * (double)default_cap_tile(c) + (double)cap_big) +
+  const double per_frame = (double)sizeof(BinRec) * (double)c->dims.ntiles * (double)default_cap_tile(c) + (double)sizeof(TriRec) * (double)cap_big +
                            (double)(c->n_parts + 1) * 65.0 + (double)c->dims.ntiles * 24.0 + 16.0;
   const double n = gb * 1e9 / per_frame;
   return n < 1.0 ? 1 : (n > 65535.0 ? 65535 : (int)n);
@@ -195,7 +195,7 @@ static int ensure_workspace(ruf_context *c, int frames)
   RUF_CUDA(c, cudaMalloc(&c->ws.vis, f * (c->n_parts + 1)));
   RUF_CUDA(c, cudaMalloc(&c->ws.ctr, f * c->dims.ctr_stride * sizeof(uint32_t)));
   RUF_CUDA(c, cudaMalloc(&c->ws.big, f * cap_big * sizeof(TriRec)));
-  RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * c->dims.ntiles * cap_tile * sizeof(TriRec)));
+  RUF_CUDA(c, cudaMalloc(&c->ws.bins, f * c->dims.ntiles * cap_tile * sizeof(BinRec)));
   RUF_CUDA(c, cudaMalloc(&c->ws.tinfo, f * c->dims.ntiles * sizeof(uint4)));
   c->max_batch = frames;
   return RUF_OK;

@@ -128,8 +128,21 @@ struct __align__(16) TriRec {
   uint32_t pad;
 };
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+// The same triangle as it travels through a tile's record list: 32 bytes = one DRAM sector, two 16-byte quantities of the
+// bulk copy.  Vertex 0 absolute, the other two as 20-bit differences (a record is only binned when they fit: bbox of at
+// most kBigTiles tiles and no far off-screen vertex; everything else goes to the per-frame big list as a TriRec); the
+// pixel bbox is recomputed by the raster kernel from the vertices it needs anyway.
+struct __align__(16) BinRec {
+  int32_t x0, y0;
+  uint32_t d0;   // dx1 [0,20) | dy1 [20,32) low 12 bits
+  uint32_t d1;   // dy1 high 8 bits [0,8) | dx2 [8,28) | dy2 low 4 bits [28,32)
+  uint32_t d2;   // dy2 high 16 bits [0,16)
+  float z0, gx, gy;
+};
+static_assert(sizeof(BinRec) == 32, "BinRec must be 32 bytes");
+constexpr int kBinDiffBits = 20;
 // dynamic shared memory of the raster kernel: record ring + per-warp unit tables
-constexpr size_t kRasterDynSmem = sizeof(TriRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
+constexpr size_t kRasterDynSmem = sizeof(BinRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
 
 // Per-frame counter block (uint32 words): [0] big-list entries  [1] unused  [2] flags
 // [3] kept (binned) triangles  [4 + 2 t], [5 + 2 t]: records at the FRONT of tile t's list (triangles facing
@@ -170,7 +183,7 @@ struct Workspace {
                          // POSITIVE window area face the camera (else the negative ones do)
   uint32_t *ctr;         // [frame][ctr_stride]
   TriRec *big;           // [frame][cap_big]
-  TriRec *bins;          // [frame][tile][cap_tile] one record list per tile
+  BinRec *bins;          // [frame][tile][cap_tile] one record list per tile
   uint32_t *status;      // [0] sticky OR of all frame flags  [1] kept records (tile-info kernel), [2] (record, tile) pairs above kMaxUnits units (raster kernel) since the host last cleared them
   uint4 *tinfo;          // [frame][tile] ruf_tile_info_kernel -> ruf_raster_filter_kernel
 };

@@ -375,7 +375,7 @@ __device__ __forceinline__ bool tri_may_touch(const uint4 &a, const uint4 &b, co
 
 __global__ void __launch_bounds__(kSetupThreads, RUF_SETUP_MIN_BLOCKS)
 ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *__restrict__ vis_all, Dims d,
-                     int n_frames, int frames_per_cta, TriRec *big_all, TriRec *bins_all, uint32_t *ctr_all)
+                     int n_frames, int frames_per_cta, TriRec *big_all, BinRec *bins_all, uint32_t *ctr_all)
 {
   constexpr int kVPT = (kMeshVerts + kSetupThreads - 1) / kSetupThreads;   // vertices per thread
   constexpr int kTPT = kSetupSlots;                                       // triangles per thread
@@ -509,7 +509,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
       }
 
       // ---- P3 + P4: one lane per SURVIVOR (dense): full setup, then the warp reserves list space per tile ----
-      TriRec *bins = bins_all + (size_t)f * d.ntiles * d.cap_tile;
+      BinRec *bins = bins_all + (size_t)f * d.ntiles * d.cap_tile;
       for (int s0 = 0; s0 < nkeep; s0 += 32) {
         const int s = s0 + lane;
         TriRec rec;
@@ -527,16 +527,24 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
             back = positive != (((pfront_bits >> ((a.w >> 8) & 31u)) & 1u) != 0u);
             tx0 = (int)(rec.bx & 0xffffu) / kTileW; tx1 = (int)(rec.bx >> 16) / kTileW;
             ty0 = (int)(rec.by & 0xffffu) / kTileH; ty1 = (int)(rec.by >> 16) / kTileH;
-            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) push_big(rec, d, big, ctr);     // read by every tile
+            // a binned record carries vertices 1 and 2 as 20-bit differences: a triangle with a far off-screen vertex
+            // goes to the big list like one that spans many tiles
+            constexpr int kHalf = 1 << (kBinDiffBits - 1);
+            const uint32_t span = (uint32_t)(rec.x1 - rec.x0 + kHalf) | (uint32_t)(rec.y1 - rec.y0 + kHalf) |
+                                  (uint32_t)(rec.x2 - rec.x0 + kHalf) | (uint32_t)(rec.y2 - rec.y0 + kHalf);
+            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles || span >= (1u << kBinDiffBits)) push_big(rec, d, big, ctr);   // read by every tile
             else has = true;
           }
         }
         const unsigned act = __ballot_sync(0xffffffffu, has);
         if (!act) continue;
         if (lane == 0) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
-        const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, (uint32_t)rec.x1, (uint32_t)rec.y1);
-        const uint4 q1 = make_uint4((uint32_t)rec.x2, (uint32_t)rec.y2, __float_as_uint(rec.z0), __float_as_uint(rec.gx));
-        const uint4 q2 = make_uint4(__float_as_uint(rec.gy), rec.bx, rec.by, 0u);
+        // BinRec: vertex 0, three words of 20-bit differences, the depth plane
+        const uint32_t m20 = (1u << kBinDiffBits) - 1u;
+        const uint32_t dx1 = (uint32_t)(rec.x1 - rec.x0) & m20, dy1 = (uint32_t)(rec.y1 - rec.y0) & m20;
+        const uint32_t dx2 = (uint32_t)(rec.x2 - rec.x0) & m20, dy2 = (uint32_t)(rec.y2 - rec.y0) & m20;
+        const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, dx1 | (dy1 << 20), (dy1 >> 12) | (dx2 << 8) | (dy2 << 28));
+        const uint4 q1 = make_uint4(dy2 >> 4, __float_as_uint(rec.z0), __float_as_uint(rec.gx), __float_as_uint(rec.gy));
         // P4.  Every lane walks the tiles of its bbox (1 for three quarters of the records, 2 or 4 for most of
         // the rest); lanes that stand on the same tile in the same step (match.any) share ONE 8-byte global
         // atomic that reserves room in that tile's list: front count in the low word, back count in the high
@@ -551,7 +559,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
           if (pos < d.cap_tile) {
             const size_t slot = back ? (size_t)d.cap_tile - 1 - pos : (size_t)pos;
             uint4 *dst = reinterpret_cast<uint4 *>(bins + (size_t)tile * d.cap_tile + slot);
-            dst[0] = q0; dst[1] = q1; dst[2] = q2;
+            dst[0] = q0; dst[1] = q1;
           }
         };
         constexpr int kWalk = RUF_WALK;
@@ -627,6 +635,20 @@ __device__ __forceinline__ TriRec load_rec_smem(const TriRec *p)
   r.x0 = (int)q0.x; r.y0 = (int)q0.y; r.x1 = (int)q0.z; r.y1 = (int)q0.w;
   r.x2 = (int)q1.x; r.y2 = (int)q1.y; r.z0 = __uint_as_float(q1.z); r.gx = __uint_as_float(q1.w);
   r.gy = __uint_as_float(q2.x); r.bx = q2.y; r.by = q2.z; r.pad = q2.w;
+  return r;
+}
+// a binned record from the shared-memory ring: vertices restored, bbox fields left to the caller
+__device__ __forceinline__ TriRec load_bin_smem(const BinRec *p)
+{
+  const uint4 *s = reinterpret_cast<const uint4 *>(p);
+  const uint4 q0 = s[0], q1 = s[1];
+  auto sx = [](uint32_t v) { return (int)(v << (32 - kBinDiffBits)) >> (32 - kBinDiffBits); };
+  TriRec r;
+  r.x0 = (int)q0.x; r.y0 = (int)q0.y;
+  r.x1 = r.x0 + sx(q0.z); r.y1 = r.y0 + sx(__funnelshift_r(q0.z, q0.w, 20));
+  r.x2 = r.x0 + sx(q0.w >> 8); r.y2 = r.y0 + sx(__funnelshift_r(q0.w, q1.x, 28));
+  r.z0 = __uint_as_float(q1.y); r.gx = __uint_as_float(q1.z); r.gy = __uint_as_float(q1.w);
+  r.bx = r.by = r.pad = 0u;
   return r;
 }
 __device__ __forceinline__ TriRec load_rec_global(const TriRec *p)
@@ -916,7 +938,7 @@ ruf_tile_info_kernel(Dims d, int n_frames, const TriRec *__restrict__ big_all, c
 // mostly above 24 units: MP is 34 % faster on C3; on C2 (5 % such records) the plain variant is 4 % faster.
 template <int ENC, bool MP>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
-ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRec *__restrict__ bins_all,
+ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRec *__restrict__ bins_all,
                          const uint32_t *__restrict__ ctr_all, const uint4 *__restrict__ tinfo, ShaderParams sp, FrameBuffers fb,
                          uint32_t *status)
 {
@@ -925,9 +947,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   // takes the last batch of a chunk (there is no dedicated producer warp holding registers).
   // dynamic shared memory (more than the 48 KB static limit): record ring, then the unit tables
   extern __shared__ __align__(128) unsigned char s_raster_dyn[];
-  TriRec (*sbuf)[kChunk] = reinterpret_cast<TriRec (*)[kChunk]>(s_raster_dyn);
+  BinRec (*sbuf)[kChunk] = reinterpret_cast<BinRec (*)[kChunk]>(s_raster_dyn);
   uint16_t (*s_units)[32 * kMaxUnits] =
-      reinterpret_cast<uint16_t (*)[32 * kMaxUnits]>(s_raster_dyn + sizeof(TriRec) * kStages * kChunk);
+      reinterpret_cast<uint16_t (*)[32 * kMaxUnits]>(s_raster_dyn + sizeof(BinRec) * kStages * kChunk);
   __shared__ __align__(16) uint32_t sz[kTilePix + kZPad];
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ uint32_t s_next[2];                 // batch claim counters of the two passes
@@ -1013,16 +1035,16 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
   nb = min(nb, d.cap_tile - nf);
   const uint32_t cnt = nf + nb;
   const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
-  const TriRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
+  const BinRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
   // chunk c of the virtual list "front run, then back run": at most two bulk copies into one ring stage
   auto issue_chunk = [&](int c, int stage) {
     const uint32_t lo = (uint32_t)c * kChunk, hi = min(lo + (uint32_t)kChunk, cnt);
-    mbar_arrive_expect_tx(&full_bar[stage], (hi - lo) * (uint32_t)sizeof(TriRec));
+    mbar_arrive_expect_tx(&full_bar[stage], (hi - lo) * (uint32_t)sizeof(BinRec));
     const uint32_t fhi = min(hi, nf);
-    if (lo < fhi) bulk_g2s(&sbuf[stage][0], list + lo, (fhi - lo) * (uint32_t)sizeof(TriRec), &full_bar[stage]);
+    if (lo < fhi) bulk_g2s(&sbuf[stage][0], list + lo, (fhi - lo) * (uint32_t)sizeof(BinRec), &full_bar[stage]);
     const uint32_t blo = max(lo, nf);
     if (blo < hi)
-      bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(TriRec),
+      bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(BinRec),
                &full_bar[stage]);
   };
   if (cnt) {
@@ -1136,11 +1158,16 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const TriRe
         int ncb = 0, nunits = 0;
         int geo = 0, bx = 0, by = 0;   // tile-local bbox origin and extent (packed); sample (i0, j0) relative to vertex 0
         if (idx < nrec) {
-          r = load_rec_smem(&sbuf[stage][idx]);
-          i0 = max((int)(r.bx & 0xffffu), tile_x0); i1 = min((int)(r.bx >> 16), tile_x0 + kTileW - 1);
-          j0 = max((int)(r.by & 0xffffu), tile_y0); j1 = min((int)(r.by >> 16), tile_y0 + kTileH - 1);
-          const int ex = max(r.x0, max(r.x1, r.x2)) - min(r.x0, min(r.x1, r.x2));
-          const int ey = max(r.y0, max(r.y1, r.y2)) - min(r.y0, min(r.y1, r.y2));
+          r = load_bin_smem(&sbuf[stage][idx]);
+          // candidate samples (S6): the pixel bbox of the snapped vertices, clipped to this tile and to the viewport
+          const int xmin = min(r.x0, min(r.x1, r.x2)), xmax = max(r.x0, max(r.x1, r.x2));
+          const int ymin = min(r.y0, min(r.y1, r.y2)), ymax = max(r.y0, max(r.y1, r.y2));
+          i0 = max((xmin - kSubpixHalf + (kSubpix - 1)) >> kSubpixBits, tile_x0);
+          i1 = min((xmax - kSubpixHalf) >> kSubpixBits, min(tile_x0 + kTileW, d.W) - 1);
+          j0 = max((ymin - kSubpixHalf + (kSubpix - 1)) >> kSubpixBits, tile_y0);
+          j1 = min((ymax - kSubpixHalf) >> kSubpixBits, min(tile_y0 + kTileH, d.H) - 1);
+          r.bx = (uint32_t)i0 | ((uint32_t)i1 << 16); r.by = (uint32_t)j0 | ((uint32_t)j1 << 16);
+          const int ex = xmax - xmin, ey = ymax - ymin;
           // 32-bit unit arithmetic is exact when every edge-function factor is below 2^14; MP admits long thin slivers
           // too: |E_k| <= 2 ex ey + 256 (ex + ey) at every sample of the bbox, below 2^31 when ex * ey < 2^29
           const bool narrow = MP ? ((long long)ex * ey < (1LL << 29) && ex < (1 << 21) && ey < (1 << 21))
