@@ -129,18 +129,16 @@ struct __align__(16) TriRec {
 };
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 // The same triangle as it travels through a tile's record list: 32 bytes = one DRAM sector, two 16-byte quantities of the
-// bulk copy.  Vertex 0 absolute, the other two as 20-bit differences (a record is only binned when they fit: bbox of at
-// most kBigTiles tiles and no far off-screen vertex; everything else goes to the per-frame big list as a TriRec); the
-// pixel bbox is recomputed by the raster kernel from the vertices it needs anyway.
+// bulk copy.  Vertex 0 absolute, the other two as 24-bit differences (12 bytes: dx1, dy1, dx2, dy2, three bytes each,
+// little endian; the guard band bounds every coordinate by 6144 px = 2^20.6 sub-pixel units, so every difference fits)
+// -- one PRMT with a sign-replicating selector restores each -- and the depth plane; the pixel bbox is recomputed by the
+// raster kernel from the vertices it needs anyway.
 struct __align__(16) BinRec {
   int32_t x0, y0;
-  uint32_t d0;   // dx1 [0,20) | dy1 [20,32) low 12 bits
-  uint32_t d1;   // dy1 high 8 bits [0,8) | dx2 [8,28) | dy2 low 4 bits [28,32)
-  uint32_t d2;   // dy2 high 16 bits [0,16)
+  uint32_t d[3];
   float z0, gx, gy;
 };
 static_assert(sizeof(BinRec) == 32, "BinRec must be 32 bytes");
-constexpr int kBinDiffBits = 20;
 // dynamic shared memory of the raster kernel: record ring + per-warp unit tables
 constexpr size_t kRasterDynSmem = sizeof(BinRec) * kStages * kChunk + sizeof(uint16_t) * (kRasterThreads / 32) * 32 * kMaxUnits;
 

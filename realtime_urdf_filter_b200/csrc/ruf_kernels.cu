@@ -47,6 +47,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// byte permute; selector nibble | 8 replicates the sign of the selected byte (PTX prmt, default mode)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 // 16-byte asynchronous copy global -> shared (LDGSTS); completion is per thread (cp.async.wait_all)
 __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
@@ -527,24 +534,18 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
             back = positive != (((pfront_bits >> ((a.w >> 8) & 31u)) & 1u) != 0u);
             tx0 = (int)(rec.bx & 0xffffu) / kTileW; tx1 = (int)(rec.bx >> 16) / kTileW;
             ty0 = (int)(rec.by & 0xffffu) / kTileH; ty1 = (int)(rec.by >> 16) / kTileH;
-            // a binned record carries vertices 1 and 2 as 20-bit differences: a triangle with a far off-screen vertex
-            // goes to the big list like one that spans many tiles
-            constexpr int kHalf = 1 << (kBinDiffBits - 1);
-            const uint32_t span = (uint32_t)(rec.x1 - rec.x0 + kHalf) | (uint32_t)(rec.y1 - rec.y0 + kHalf) |
-                                  (uint32_t)(rec.x2 - rec.x0 + kHalf) | (uint32_t)(rec.y2 - rec.y0 + kHalf);
-            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles || span >= (1u << kBinDiffBits)) push_big(rec, d, big, ctr);   // read by every tile
+            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) push_big(rec, d, big, ctr);     // read by every tile
             else has = true;
           }
         }
         const unsigned act = __ballot_sync(0xffffffffu, has);
         if (!act) continue;
         if (lane == 0) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
-        // BinRec: vertex 0, three words of 20-bit differences, the depth plane
-        const uint32_t m20 = (1u << kBinDiffBits) - 1u;
-        const uint32_t dx1 = (uint32_t)(rec.x1 - rec.x0) & m20, dy1 = (uint32_t)(rec.y1 - rec.y0) & m20;
-        const uint32_t dx2 = (uint32_t)(rec.x2 - rec.x0) & m20, dy2 = (uint32_t)(rec.y2 - rec.y0) & m20;
-        const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, dx1 | (dy1 << 20), (dy1 >> 12) | (dx2 << 8) | (dy2 << 28));
-        const uint4 q1 = make_uint4(dy2 >> 4, __float_as_uint(rec.z0), __float_as_uint(rec.gx), __float_as_uint(rec.gy));
+        // BinRec: vertex 0, the other two vertices as 24-bit differences (12 bytes, three PRMTs), the depth plane
+        const uint32_t dx1 = (uint32_t)(rec.x1 - rec.x0), dy1 = (uint32_t)(rec.y1 - rec.y0);
+        const uint32_t dx2 = (uint32_t)(rec.x2 - rec.x0), dy2 = (uint32_t)(rec.y2 - rec.y0);
+        const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, prmt(dx1, dy1, 0x4210u), prmt(dy1, dx2, 0x5421u));
+        const uint4 q1 = make_uint4(prmt(dx2, dy2, 0x6542u), __float_as_uint(rec.z0), __float_as_uint(rec.gx), __float_as_uint(rec.gy));
         // P4.  Every lane walks the tiles of its bbox (1 for three quarters of the records, 2 or 4 for most of
         // the rest); lanes that stand on the same tile in the same step (match.any) share ONE 8-byte global
         // atomic that reserves room in that tile's list: front count in the low word, back count in the high
@@ -642,11 +643,11 @@ __device__ __forceinline__ TriRec load_bin_smem(const BinRec *p)
 {
   const uint4 *s = reinterpret_cast<const uint4 *>(p);
   const uint4 q0 = s[0], q1 = s[1];
-  auto sx = [](uint32_t v) { return (int)(v << (32 - kBinDiffBits)) >> (32 - kBinDiffBits); };
   TriRec r;
   r.x0 = (int)q0.x; r.y0 = (int)q0.y;
-  r.x1 = r.x0 + sx(q0.z); r.y1 = r.y0 + sx(__funnelshift_r(q0.z, q0.w, 20));
-  r.x2 = r.x0 + sx(q0.w >> 8); r.y2 = r.y0 + sx(__funnelshift_r(q0.w, q1.x, 28));
+  // three bytes each, the fourth replicated from the sign of the third: one PRMT per difference
+  r.x1 = r.x0 + (int)prmt(q0.z, 0u, 0xa210u); r.y1 = r.y0 + (int)prmt(q0.z, q0.w, 0xd543u);
+  r.x2 = r.x0 + (int)prmt(q0.w, q1.x, 0xc432u); r.y2 = r.y0 + (int)prmt(q1.x, 0u, 0xb321u);
   r.z0 = __uint_as_float(q1.y); r.gx = __uint_as_float(q1.z); r.gy = __uint_as_float(q1.w);
   r.bx = r.by = r.pad = 0u;
   return r;
@@ -734,13 +735,6 @@ __device__ __forceinline__ uint32_t f32_to_u16(float x)
 }
 
 // ---- fragment stage helpers -----------------------------------------------------------------------------
-// PRMT with the sign-replicate selector bit (nibble | 8: the byte becomes 0xff / 0x00 after the msb of the source byte)
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-}
 // 16UC1 input: sensor = float(raw) * 0.001f (convertTo(CV_32F, 0.001), src/urdf_filter.cpp:288) is strictly increasing
 // in raw, so `sensor > thr` (frag:23) is `raw > R` with R = the largest raw whose sensor value is <= thr (-1: every
 // raw is filtered, 65535: none is; thr = NaN compares false for every raw, like the float compare).  floor(thr * 1000)
