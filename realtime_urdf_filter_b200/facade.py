@@ -187,7 +187,7 @@ class FilterNode:
         return (out if n == out.nbytes else None), enc.value.decode()
 
     def counts(self):
-        names = ["renderers", "parts", "triangles", "tf_lookups", "frames", "renderables"]
+        names = ["renderers", "parts", "triangles", "tf_lookups", "frames", "renderables", "mesh_errors"]
         return {n: self.L.ruf_facade_counts(self.h, i) for i, n in enumerate(names)}
 
     def log(self, clear=False):

@@ -135,6 +135,7 @@ RUF_API long ruf_facade_counts(void *h, int what)
     case 3: return (long)F->f->tf_.lookups;
     case 4: return (long)F->f->frames_;
     case 5: { long n = 0; for (auto *r : F->f->renderers_) n += (long)r->num_renderables(); return n; }
+    case 6: { long n = 0; for (auto *r : F->f->renderers_) n += (long)r->mesh_errors().size(); return n; }
     default: return -1;
   }
 }

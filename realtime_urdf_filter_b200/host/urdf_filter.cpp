@@ -60,6 +60,14 @@ void RealtimeURDFFilter::loadModels()
     logf(LOG_INFO, "Loading URDF model: %s", elem.model.c_str());
     renderers_.push_back(new URDFRenderer(content, elem.tf_prefix, cam_frame_, fixed_frame_, tf_, elem.geometry_type,
                                           elem.scale, ignore, resource_roots_));                           // :190
+    // Only STL meshes are read here (the reference reads whatever Assimp does): a mesh that could not be loaded leaves
+    // its link unfiltered.  `strict_meshes` (not a parameter of the reference) turns that into the same exception a
+    // model-less filter raises (:426-427) instead of an ERROR line per mesh.
+    bool strict = false;
+    nh_.getParam("strict_meshes", strict);
+    const std::vector<std::string> &bad = renderers_.back()->mesh_errors();
+    if (strict && !bad.empty())
+      throw std::runtime_error("Could not load " + std::to_string(bad.size()) + " mesh(es), first: " + bad.front());
   }
 }
 

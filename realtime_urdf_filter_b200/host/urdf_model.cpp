@@ -424,7 +424,13 @@ bool load_stl(const std::string &path, std::vector<float> &tri, std::string *err
   if (data.size() >= 84) {
     uint32_t n;
     std::memcpy(&n, data.data() + 80, 4);
-    if (data.size() == 84 + (size_t)n * 50) {
+    // exporters pad or append (colour blocks, a trailing newline): the declared facets must fit, bytes after them are ignored.
+    // A text file that happens to pass is told apart by its "facet" keyword: no binary header + count + facets holds one
+    // at the position where an ASCII file's first facet starts.
+    const bool fits = n > 0 && data.size() >= 84 + (size_t)n * 50;
+    const bool looks_ascii = data.compare(0, 5, "solid") == 0 && data.find("facet", 5) != std::string::npos &&
+                             data.find("vertex", 5) != std::string::npos && data.size() != 84 + (size_t)n * 50;
+    if (fits && !looks_ascii) {
       tri.resize((size_t)n * 9);
       for (uint32_t i = 0; i < n; ++i) std::memcpy(&tri[(size_t)i * 9], data.data() + 84 + (size_t)i * 50 + 12, 36);
       return true;
@@ -536,7 +542,8 @@ void URDFRenderer::process_link(const UrdfLink &link)
       const std::string path = resolve_resource(g.filename, roots_);
       if (!load_stl(path, tris, &err)) {
         logf(LOG_ERROR, "Could not load resource [%s]: %s", g.filename.c_str(), err.c_str());
-        tris.clear();                                                  // the renderable exists but draws nothing
+        tris.clear();                                                  // the renderable exists but draws nothing ...
+        mesh_errors_.push_back(name + ": " + g.filename + " (" + err + ")");   // ... and the caller can find out (strict_meshes)
       }
       scale_matrix((float)(scale_ * g.scale[0]), (float)(scale_ * g.scale[1]), (float)(scale_ * g.scale[2]), sfx);
       add_part(name, v.origin, sfx, tris, rid);

@@ -89,6 +89,9 @@ class URDFRenderer {
   size_t num_renderables() const { return renderable_name_.size(); }
   bool ok() const { return ok_; }
   const std::string &error() const { return error_; }                  // why the description was rejected
+  // meshes that could not be loaded (only STL is read here; the reference reads anything Assimp does): their links are
+  // silently left unfiltered unless the caller looks at this list
+  const std::vector<std::string> &mesh_errors() const { return mesh_errors_; }
 
  private:
   void process_link(const UrdfLink &link);
@@ -102,6 +105,7 @@ class URDFRenderer {
   TransformListener &tf_;
   bool ok_ = false;
   std::string error_;
+  std::vector<std::string> mesh_errors_;
   std::vector<RenderablePart> parts_;
   std::vector<float> tri_;
   std::vector<uint32_t> tri_part_;

@@ -214,3 +214,27 @@ def test_urdf_parser_survives_mutated_and_hostile_input():
     deep = "<robot name='d'>" + "<a>" * 100000 + "</a>" * 100000 + "</robot>"
     with pytest.raises(ValueError, match="nested deeper"):
         facade.parse_urdf(deep)
+
+
+def test_binary_stl_with_trailing_bytes_and_visible_mesh_failures(tmp_path):
+    """exporters append bytes after the declared facets (accepted, ignored); a mesh that cannot be loaded is
+    recorded per renderer (`mesh_errors`) and, with the `strict_meshes` parameter, stops the filter like a model-less one."""
+    tris = np.random.default_rng(4).normal(size=(5, 9)).astype(np.float32)
+    os.makedirs(tmp_path / "pkg" / "meshes")
+    _write_binary_stl(tmp_path / "pkg" / "meshes" / "padded.stl", tris)
+    with open(tmp_path / "pkg" / "meshes" / "padded.stl", "ab") as f:
+        f.write(b"\x00" * 37 + b"COLOR=\n")
+    xml = '<robot name="m"><link name="l"><visual><geometry><mesh filename="package://pkg/meshes/padded.stl"/></geometry></visual></link></robot>'
+    tri, _, _ = facade.parse_urdf(xml, "", resource_root=str(tmp_path))
+    assert np.array_equal(tri, tris)
+    # an ASCII file that is long enough to hold the "declared" facet count of its own text is still read as ASCII
+    with open(tmp_path / "pkg" / "meshes" / "ascii_long.stl", "w") as f:
+        f.write("solid " + "x" * 200 + "\n")
+        for t in tris:
+            f.write("facet normal 0 0 1\n outer loop\n")
+            for k in range(3):
+                f.write("  vertex %r %r %r\n" % tuple(float(v) for v in t[3 * k:3 * k + 3]))
+            f.write(" endloop\nendfacet\n")
+        f.write("endsolid x\n")
+    tri, _, _ = facade.parse_urdf(xml.replace("padded", "ascii_long"), "", resource_root=str(tmp_path))
+    assert np.array_equal(tri, tris)

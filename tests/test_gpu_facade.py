@@ -125,3 +125,20 @@ def test_packed_mask_readback_publishes_the_same_mono8_mask():
         n.callback(fr["depth"], sc.P, stamp=1.0)
         got_m, em = n.last_image(1, fr["depth"].shape, np.uint8)
     assert em == "mono8" and np.array_equal(got_m, want_m)
+
+
+def test_missing_mesh_is_counted_and_strict_meshes_raises():
+    xml = ('<robot name="m"><link name="l"><visual><geometry><mesh filename="package://pkg/nope.stl"/></geometry></visual>'
+           '</link><link name="b"><visual><geometry><box size="1 1 1"/></geometry></visual></link>'
+           '<joint name="j" type="fixed"><parent link="l"/><child link="b"/></joint></robot>')
+    params = dict(PARAMS, robot_description=xml)
+    depth = np.full((480, 640), 1500, np.uint16)
+    with facade.FilterNode(params, MODELS, camera_offset=((0, 0, 0), (0, 0, 0, 1))) as n:
+        for f in ("/world", "/EXAMPLE/l", "/EXAMPLE/b", "/camera_rgb_optical_frame"):
+            n.set_tf(f, (0, 0, 0, 1), (0, 0, 0))
+        n.callback(depth, synth.kinect_P(640, 480))
+        assert n.counts()["mesh_errors"] == 1 and "Could not load resource" in n.log()
+    with facade.FilterNode(dict(params, strict_meshes=True), MODELS, camera_offset=((0, 0, 0), (0, 0, 0, 1))) as n:
+        n.set_tf("/world", (0, 0, 0, 1), (0, 0, 0))
+        with pytest.raises(RuntimeError, match="Could not load 1 mesh"):
+            n.callback(depth, synth.kinect_P(640, 480))
