@@ -39,3 +39,29 @@ for i, fr in enumerate(frames):
     want_d, want_m, _ = helpers.oracle_filter(sc, fr)
     assert np.array_equal(d_out[i].cpu().numpy().view(np.uint16), want_d) and np.array_equal(d_mask[i].cpu().numpy(), want_m)
 print("batch ok")
+# round 2: the single-frame CUDA-graph path (pinned host buffers), the packed mask, and whichever raster kernel variant
+# RUF_MULTIPASS selects (pr2_small: 80 % of its records are above 24 units -> parked wide records / multi-pass units)
+import ctypes
+lib = ruf.load()
+sc = helpers.scene("pr2_small"); proj, _, _ = sc.proj()
+n = sc.width * sc.height
+ptrs = [ruf.host_alloc(n * 2), ruf.host_alloc(n * 2), ruf.host_alloc(n)]
+view = lambda p, dt, cnt: np.frombuffer((ctypes.c_uint8 * (cnt * np.dtype(dt).itemsize)).from_address(p), dtype=dt)
+h_in, h_out, h_mask = view(ptrs[0], np.uint16, n), view(ptrs[1], np.uint16, n), view(ptrs[2], np.uint8, n)
+with ruf.Context(sc.width, sc.height) as ctx:
+    ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+    for k in (3, 8):
+        fr = helpers.make_frame(sc, k, "u16")
+        h_in[:] = fr["depth"].reshape(-1)
+        v, pm, pr = [np.ascontiguousarray(a, np.float64) for a in (fr["view"], fr["pm"], proj)]
+        rc = lib.ruf_filter(ctx._h, ptrs[0], ruf.ENC_U16_MM, pr.ctypes.data, v.ctypes.data, pm.ctypes.data, sc.max_diff,
+                            sc.replace_value, ptrs[1], ptrs[2])
+        assert rc == 0
+        want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+        assert np.array_equal(h_out.reshape(want_d.shape), want_d) and np.array_equal(h_mask.reshape(want_m.shape), want_m)
+    ctx.set_mask_format(ruf.MASK_BITS)
+    d, bits = ctx.filter(fr["depth"], proj, fr["view"], fr["pm"], sc.max_diff, sc.replace_value)
+    assert np.array_equal(np.unpackbits(bits, axis=-1, bitorder="little") * np.uint8(255), want_m)
+for p in ptrs:
+    ruf.host_free(p)
+print("graph + packed mask ok, RUF_MULTIPASS =", os.environ.get("RUF_MULTIPASS", "auto"))
