@@ -53,7 +53,7 @@ CONFIGS = {
                what="PR2-like synthetic model"),
     "c3": dict(scene="walls", size=(1280, 960), batch=256, cpu_frames=8, baseline="configs[2]",
                what="PR2-like synthetic model + two static wall boxes"),
-    "c5": dict(scene="multi", size=(1920, 1080), batch=64, cpu_frames=2, baseline="configs[4]",
+    "c5": dict(scene="multi", size=(1920, 1080), batch=128, cpu_frames=2, baseline="configs[4]",
                what="four articulated PR2-like URDFs, animated joint sweep"),
 }
 

@@ -548,3 +548,65 @@ def test_both_raster_kernel_variants_are_bit_exact(monkeypatch, mode):
                 for i, f in enumerate(frs):
                     want_d, want_m, _ = helpers.oracle_filter(sc, f)
                     assert np.array_equal(got_d[i], want_d) and np.array_equal(got_m[i], want_m), (name, rep, i)
+
+
+def test_device_batch_larger_than_the_workspace_budget_runs_as_sub_batches():
+    """The record lists are sized per (frame, tile), so the workspace grows with the batch; it is capped at a byte budget
+    (RUF_WORKSPACE_GB) and a device batch that does not fit runs as equal sub-batches through the same workspace."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import os, sys
+        import numpy as np, torch
+        sys.path[:0] = [%r, %r, %r]
+        import helpers, realtime_urdf_filter_b200 as ruf
+        sc = helpers.scene("pr2_small")
+        proj, _, _ = sc.proj()
+        ks = list(range(11))
+        frs = [helpers.make_frame(sc, k, "u16") for k in ks]
+        dev = torch.device("cuda:0")
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d_in = t(np.stack([f["depth"] for f in frs]).view(np.int16)); d_out = torch.zeros_like(d_in)
+        d_mask = torch.zeros(d_in.shape, dtype=torch.uint8, device=dev)
+        d_proj, d_view, d_pm = t(proj), t(np.stack([f["view"] for f in frs])), t(np.stack([f["pm"] for f in frs]))
+        torch.cuda.synchronize()
+        with ruf.Context(sc.width, sc.height) as ctx:
+            ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+            ctx.filter_batch_device(len(ks), d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                                    sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
+            ctx.sync()
+            st = ctx.stats()
+        print("LAUNCHES", st["kernel_launches"])
+        for i, fr in enumerate(frs):
+            want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+            assert np.array_equal(d_out[i].cpu().numpy().view(np.uint16), want_d), i
+            assert np.array_equal(d_mask[i].cpu().numpy(), want_m), i
+        print("OK")
+    ''') % (helpers.__file__.rsplit("/", 2)[0], helpers.__file__.rsplit("/", 2)[0] + "/oracle", helpers.__file__.rsplit("/", 1)[0])
+    # pr2_small at 640x480: 80 tiles x 2048 records x 32 B = 5.2 MB per frame -> a 0.02 GB budget holds 3 frames
+    env = dict(__import__("os").environ, RUF_WORKSPACE_GB="0.02")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+    launches = int(res.stdout.split("LAUNCHES")[1].split()[0])
+    assert launches >= 4 * 3, launches          # 11 frames in sub-batches of at most 3-4 frames: at least 3 launch sequences
+
+
+def test_copy_ceiling_call_moves_the_same_bytes():
+    sc = helpers.scene("pr2_small")
+    proj, _, _ = sc.proj()
+    frs = [helpers.make_frame(sc, k, "u16") for k in (0, 1, 2, 3, 4)]
+    depth = np.stack([f["depth"] for f in frs])
+    views, pms = np.stack([f["view"] for f in frs]), np.stack([f["pm"] for f in frs])
+    out, mask = np.empty_like(depth), np.empty(depth.shape, np.uint8)
+    lib = ruf.load()
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        ctx.filter_batch_host(depth, proj, views, pms, sc.max_diff, sc.replace_value)
+        want = ctx.stats()
+        pr = np.ascontiguousarray(proj, np.float64)
+        rc = lib.ruf_host_copy_ceiling(ctx._h, 5, depth.ctypes.data, ruf.ENC_U16_MM, pr.ctypes.data, views.ctypes.data,
+                                       pms.ctypes.data, out.ctypes.data, mask.ctypes.data)
+        assert rc == 0
+        got = ctx.stats()
+    assert got["h2d_bytes"] == want["h2d_bytes"] and got["d2h_bytes"] == want["d2h_bytes"] and got["kernel_launches"] == 0
