@@ -83,6 +83,9 @@ static_assert((kUW == 8 && kUH == 1) || (kUW == 4 && kUH == 2) || (kUW == 4 && k
 #ifndef RUF_MIN_BACK_BATCHES
 #define RUF_MIN_BACK_BATCHES 6u
 #endif
+#ifndef RUF_EARLY_RESERVE
+#define RUF_EARLY_RESERVE 1       // setup kernel: tile reservation atomics issued before the depth-plane divisions (-7 % on the kernel)
+#endif
 #ifndef RUF_OCCLUDE_MIN
 #define RUF_OCCLUDE_MIN 8
 #endif

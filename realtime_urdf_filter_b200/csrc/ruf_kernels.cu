@@ -172,6 +172,36 @@ __device__ __forceinline__ bool setup_window_tri(WV a, WV b, WV c, const Dims &d
   return true;
 }
 
+// setup_window_tri in two halves (RUF_EARLY_RESERVE): what the tile reservation needs -- orientation, pixel bbox -- and the
+// depth plane with its two divisions, which then runs while the reservation atomics are in flight.  Same operations on the
+// same operands as setup_window_tri: same bits.
+__device__ __forceinline__ bool setup_cover(WV a, WV &b, WV &c, const Dims &d, long long &area2, bool &positive, int &i0,
+                                            int &i1, int &j0, int &j1)
+{
+  area2 = (long long)(b.X - a.X) * (c.Y - a.Y) - (long long)(c.X - a.X) * (b.Y - a.Y);
+  if (area2 == 0) return false;
+  positive = area2 > 0;
+  if (area2 < 0) { WV t = b; b = c; c = t; area2 = -area2; }
+  const int xmin = min(a.X, min(b.X, c.X)), xmax = max(a.X, max(b.X, c.X));
+  const int ymin = min(a.Y, min(b.Y, c.Y)), ymax = max(a.Y, max(b.Y, c.Y));
+  i0 = max((xmin - kSubpixHalf + (kSubpix - 1)) >> kSubpixBits, 0);
+  i1 = min((xmax - kSubpixHalf) >> kSubpixBits, d.W - 1);
+  j0 = max((ymin - kSubpixHalf + (kSubpix - 1)) >> kSubpixBits, 0);
+  j1 = min((ymax - kSubpixHalf) >> kSubpixBits, d.H - 1);
+  return i0 <= i1 && j0 <= j1;
+}
+__device__ __forceinline__ void setup_plane(const WV &a, const WV &b, const WV &c, long long area2, float &gxz, float &gyz)
+{
+  const float dx1 = (float)(b.X - a.X), dy1 = (float)(b.Y - a.Y);
+  const float dx2 = (float)(c.X - a.X), dy2 = (float)(c.Y - a.Y);
+  const float dz1 = b.z - a.z, dz2 = c.z - a.z;
+  const float fa = __ll2float_rn(area2);
+  const float t1 = dz2 * dy1;
+  gxz = fmaf(dz1, dy2, -t1) / fa;
+  const float t2 = dz1 * dx2;
+  gyz = fmaf(dz2, dx1, -t2) / fa;
+}
+
 // per-frame list read by every tile: triangles spanning many tiles and everything the clipper made
 __device__ __forceinline__ void push_big(const TriRec &r, const Dims &d, TriRec *big, uint32_t *ctr)
 {
@@ -519,9 +549,44 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
       BinRec *bins = bins_all + (size_t)f * d.ntiles * d.cap_tile;
       for (int s0 = 0; s0 < nkeep; s0 += 32) {
         const int s = s0 + lane;
-        TriRec rec;
         int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
         bool has = false, back = false;            // back: the triangle faces away from the camera (drawing-order hint)
+#if RUF_EARLY_RESERVE
+        // first only what the reservation needs (orientation, bbox, tile range); the depth plane follows below, under
+        // the reservation atomics
+        WV wa, wb, wc;
+        long long area2 = 0;
+        int bi0 = 0, bi1 = 0, bj0 = 0, bj1 = 0;
+        bool isbig = false;
+        wa.X = wa.Y = wb.X = wb.Y = wc.X = wc.Y = 0; wa.z = wb.z = wc.z = 0.f;
+        if (s < nkeep) {
+          const uint32_t ixs = list[s];
+          const uint4 a = sv[ixs & 1023u], b = sv[(ixs >> 10) & 1023u], c = sv[ixs >> 20];
+          wa.X = (int)a.x; wa.Y = (int)a.y; wa.z = __uint_as_float(a.z);
+          wb.X = (int)b.x; wb.Y = (int)b.y; wb.z = __uint_as_float(b.z);
+          wc.X = (int)c.x; wc.Y = (int)c.y; wc.z = __uint_as_float(c.z);
+          bool positive = false;
+          if (setup_cover(wa, wb, wc, d, area2, positive, bi0, bi1, bj0, bj1)) {
+            back = positive != (((pfront_bits >> ((a.w >> 8) & 31u)) & 1u) != 0u);
+            tx0 = bi0 / kTileW; tx1 = bi1 / kTileW;
+            ty0 = bj0 / kTileH; ty1 = bj1 / kTileH;
+            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kBigTiles) isbig = true;     // read by every tile
+            else has = true;
+          }
+        }
+        if (isbig) {                               // rare: the whole record at once
+          TriRec rec;
+          rec.x0 = wa.X; rec.y0 = wa.Y; rec.x1 = wb.X; rec.y1 = wb.Y; rec.x2 = wc.X; rec.y2 = wc.Y; rec.z0 = wa.z;
+          setup_plane(wa, wb, wc, area2, rec.gx, rec.gy);
+          rec.bx = (uint32_t)bi0 | ((uint32_t)bi1 << 16); rec.by = (uint32_t)bj0 | ((uint32_t)bj1 << 16); rec.pad = 0;
+          push_big(rec, d, big, ctr);
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!act) continue;
+        if (lane == 0) atomicAdd(&ctr[kCtrKept], (uint32_t)__popc(act));     // statistics only
+        uint4 q0, q1;
+#else
+        TriRec rec;
         if (s < nkeep) {
           const uint32_t ixs = list[s];
           const uint4 a = sv[ixs & 1023u], b = sv[(ixs >> 10) & 1023u], c = sv[ixs >> 20];
@@ -546,6 +611,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         const uint32_t dx2 = (uint32_t)(rec.x2 - rec.x0), dy2 = (uint32_t)(rec.y2 - rec.y0);
         const uint4 q0 = make_uint4((uint32_t)rec.x0, (uint32_t)rec.y0, prmt(dx1, dy1, 0x4210u), prmt(dy1, dx2, 0x5421u));
         const uint4 q1 = make_uint4(prmt(dx2, dy2, 0x6542u), __float_as_uint(rec.z0), __float_as_uint(rec.gx), __float_as_uint(rec.gy));
+#endif
         // P4.  Every lane walks the tiles of its bbox (1 for three quarters of the records, 2 or 4 for most of
         // the rest); lanes that stand on the same tile in the same step (match.any) share ONE 8-byte global
         // atomic that reserves room in that tile's list: front count in the low word, back count in the high
@@ -584,6 +650,17 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
             more = ty <= ty1;
           }
         }
+#if RUF_EARLY_RESERVE
+        {
+          // the atomics are in flight: now the two divisions of the depth plane and the packing of the record
+          float gxz = 0.f, gyz = 0.f;
+          if (has) setup_plane(wa, wb, wc, area2, gxz, gyz);
+          const uint32_t dx1 = (uint32_t)(wb.X - wa.X), dy1 = (uint32_t)(wb.Y - wa.Y);
+          const uint32_t dx2 = (uint32_t)(wc.X - wa.X), dy2 = (uint32_t)(wc.Y - wa.Y);
+          q0 = make_uint4((uint32_t)wa.X, (uint32_t)wa.Y, prmt(dx1, dy1, 0x4210u), prmt(dy1, dx2, 0x5421u));
+          q1 = make_uint4(prmt(dx2, dy2, 0x6542u), __float_as_uint(wa.z), __float_as_uint(gxz), __float_as_uint(gyz));
+        }
+#endif
 #pragma unroll
         for (int k = 0; k < kWalk; ++k) {
           const unsigned long long b = __shfl_sync(0xffffffffu, base[k], __ffs(grp[k]) - 1);
