@@ -433,8 +433,15 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
   // nothing of this meshlet visible in any frame of the run (per-part cull bytes of the pose kernel)? leave
   // before touching the model.  Every warp decides by itself from the same bytes: consistent across the CTA.
   {
+    // (all frames' bytes are requested before the first one is looked at: one round trip instead of frames_per_cta)
+    uint32_t vb[kSetupFrames];
+#pragma unroll
+    for (int j = 0; j < kSetupFrames; ++j)
+      vb[j] = (f0 + j < f1 && lane <= npm1) ? (uint32_t)__ldg(vis_all + (size_t)(f0 + j) * rows + part_lo + lane) : 0u;
     bool any = false;
-    for (int f = f0; f < f1; ++f)
+#pragma unroll
+    for (int j = 0; j < kSetupFrames; ++j) any |= (vb[j] & 1u) != 0u;
+    for (int f = f0 + kSetupFrames; f < f1; ++f)       // frames_per_cta above kSetupFrames (RUF_SETUP_FRAMES_FORCE)
       any |= (lane <= npm1) && (__ldg(vis_all + (size_t)f * rows + part_lo + lane) & 1) != 0;
     if (!__any_sync(0xffffffffu, any)) return;
   }
