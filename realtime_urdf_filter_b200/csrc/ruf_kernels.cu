@@ -342,7 +342,7 @@ ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view
 // snap run ONCE per distinct vertex instead of once per triangle corner.  The per-vertex result
 // is a pure function of (MVP, position), so sharing it cannot change a bit of the output.
 //
-// A CTA keeps its meshlet (positions, indices) in REGISTERS and loops over `frames_per_cta` frames;
+// A CTA keeps its meshlet (positions in REGISTERS, index triples in shared memory) and loops over `frames_per_cta` frames;
 // per frame only the meshlet's MVP rows (contiguous, staged in shared memory one frame ahead) and
 // its parts' cull bytes are read.  Per frame:
 //   P1  thread per vertex:    clip = MVP * v, clip-plane flags, window coordinates -> shared memory
@@ -445,9 +445,9 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
       any |= (lane <= npm1) && (__ldg(vis_all + (size_t)f * rows + part_lo + lane) & 1) != 0;
     if (!__any_sync(0xffffffffu, any)) return;
   }
-  // the meshlet stays in registers for all frames of this CTA
+  // the meshlet stays on chip for all frames of this CTA: vertex positions in registers, index triples in shared memory
   float4 vq[kVPT];
-  uint32_t ix[kTPT];
+  __shared__ uint32_t s_tri[kTPT * kSetupThreads];     // the meshlet's packed index triples (registers are the scarce resource: 40 per thread)
 #pragma unroll
   for (int k = 0; k < kVPT; ++k) {
     const int v = k * kSetupThreads + tid;
@@ -456,7 +456,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
 #pragma unroll
   for (int k = 0; k < kTPT; ++k) {
     const int t = k * kSetupThreads + tid;
-    ix[k] = (t < ntris) ? __ldg(m.tris + tri_off + t) : kNoTri;
+    s_tri[t] = (t < ntris) ? __ldg(m.tris + tri_off + t) : kNoTri;
   }
 
   // stage the matrices of the first two frames; cull bytes -> one bit per part (every warp builds its own copy)
@@ -524,8 +524,9 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
 #pragma unroll
       for (int k = 0; k < kTPT; ++k) {
         bool keep = false, clip = false;
-        if (ix[k] != kNoTri) {
-          const uint4 a = sv[ix[k] & 1023u], b = sv[(ix[k] >> 10) & 1023u], c = sv[ix[k] >> 20];
+        const uint32_t ixk = s_tri[k * kSetupThreads + tid];       // written by this very thread: no barrier needed
+        if (ixk != kNoTri) {
+          const uint4 a = sv[ixk & 1023u], b = sv[(ixk >> 10) & 1023u], c = sv[ixk >> 20];
           const uint32_t f_or = a.w | b.w | c.w, f_and = a.w & b.w & c.w;
           if (!(f_or & kVfDead) && !(f_and & kVfAllOut)) {
             if (f_or & kVfClip) clip = true;
@@ -533,8 +534,8 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
           }
         }
         const unsigned bk = __ballot_sync(0xffffffffu, keep), bc = __ballot_sync(0xffffffffu, clip);
-        if (keep) list[nkeep + __popc(bk & lanemask_lt)] = ix[k];
-        if (clip) list[kWarpList - 1 - nclip - __popc(bc & lanemask_lt)] = ix[k];
+        if (keep) list[nkeep + __popc(bk & lanemask_lt)] = ixk;
+        if (clip) list[kWarpList - 1 - nclip - __popc(bc & lanemask_lt)] = ixk;
         nkeep += __popc(bk);
         nclip += __popc(bc);
       }
