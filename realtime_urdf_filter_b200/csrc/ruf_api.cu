@@ -36,7 +36,8 @@ struct ruf_context {
   long long n_tris = 0;
   int n_parts = 0;
   bool have_model = false;
-  int n_meshlets = 0;
+  int n_meshlets = 0;            // throughput cut: headers [0, n_meshlets)
+  int n_meshlets_fine = 0;       // fine cut (launches of one or a few frames): headers [n_meshlets, n_meshlets + n_meshlets_fine)
   uint4 *meshlets = nullptr;    // [n_meshlets] headers (ruf_device.cuh Model)
   float4 *mverts = nullptr;     // welded vertices of all meshlets
   uint32_t *mtris = nullptr;    // packed local indices
@@ -74,7 +75,8 @@ struct ruf_context {
   struct FrameGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t n_in = nullptr, n_out = nullptr, n_mask = nullptr;
+    cudaGraphNode_t n_in = nullptr, n_out = nullptr, n_mask = nullptr, n_raster = nullptr;
+    int direct = -1;
     const void *in = nullptr; void *out = nullptr; uint8_t *mask = nullptr;
     int enc = -1, mask_format = -1, n_parts = -1, multipass = -1;
     float max_diff = 0.f, replace_value = 0.f;
@@ -82,6 +84,10 @@ struct ruf_context {
     uint32_t cap_big = 0, cap_tile = 0;
   } fg;
   bool use_graph = true;             // RUF_NO_GRAPH=1 turns the path off (A/B, debugging)
+  int direct_mode = 7;               // single-frame graph: zero-copy bits (1 outputs, 2 input, 4 matrices + status), RUF_DIRECT
+  uint32_t *launch_host_status = nullptr;   // set around the capture of the single-frame graph: FrameBuffers::host_status
+  int fine_mode = -1;                // fine meshlet cut for small launches: -1 automatic, 0 / 1 forced (RUF_FINE_MESHLETS)
+  int cluster_mode = -1;             // cluster-split raster variant: -1 automatic (small launches), 0 / 1 forced (RUF_CLUSTER)
   int multipass_mode = -1;           // raster kernel variant: -1 automatic (share of wide records in the last launches), 0 / 1 forced
   bool multipass = false;            // the current choice
   double wide_share = -1.0;          // wide / kept records of the launches since the previous status read-back (-1: none yet)
@@ -244,17 +250,25 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
   fb.depth_in = d_in; fb.depth_out = d_out; fb.mask_out = d_mask; fb.zbuf_out = d_zbuf;
   const uintptr_t al = (uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_zbuf;
   fb.mask_bits = c->mask_format == RUF_MASK_BITS;
+  fb.host_status = c->launch_host_status;
   fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (fb.mask_bits || ((uintptr_t)d_mask & 7) == 0);
   if (fb.mask_bits && d_mask && !fb.vec_ok)
     return fail(c, RUF_ERR_INVALID, "RUF_MASK_BITS needs an image width that is a multiple of 8 and 16-byte aligned depth buffers");
   const ShaderParams sp = shader_params(c, max_diff, replace_value);
   Model m{c->meshlets, c->mverts, c->mtris, c->part_aabb};
+  // launches that cannot fill the machine with one CTA per (meshlet, run of frames) take the fine cut of the model
+  const bool fine = c->n_meshlets_fine > 0 && (c->fine_mode >= 0 ? c->fine_mode != 0 : (long long)n_frames * c->n_meshlets <= kFineMaxCtas);
+  if (fine) m.meshlets += c->n_meshlets;
+  c->dims.n_meshlets = fine ? c->n_meshlets_fine : c->n_meshlets;
   // Raster kernel variant of this launch.  Automatic: the share of kept records that span more than kMaxUnits raster
   // units, as counted by the setup kernel in the launches whose statistics have reached the host by now (they ride on
   // the status word's read-back, one launch or more behind: a heuristic, both variants give identical results).
   if (c->multipass_mode == 0 || c->multipass_mode == 1) c->multipass = c->multipass_mode == 1;
   else if (c->wide_share >= 0.0) c->multipass = c->wide_share > (c->multipass ? 0.10 : 0.15);     // with hysteresis
   c->dims.multipass = c->multipass ? 1 : 0;
+  // Launches too small to fill the machine (a single frame is 80 tiles at 640x480, a third of them busy): the cluster-split
+  // raster variant.  RUF_CLUSTER=0 / 1 forces it off / on (A/B, tests).
+  c->dims.cluster_split = c->cluster_mode >= 0 ? c->cluster_mode : ((long long)n_frames * c->dims.ntiles <= kClusterMaxTiles ? 1 : 0);
   int launches = 0;
   cudaEvent_t *ev = nullptr;
   if (c->profiling) {
@@ -351,6 +365,9 @@ int ruf_create(ruf_context **out, int device, int width, int height, double z_ne
     if (v >= 1 && v <= 64) c->dims.force_fpc = v;
   }
   if (getenv("RUF_NO_GRAPH")) c->use_graph = false;
+  if (const char *e = getenv("RUF_CLUSTER")) c->cluster_mode = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("RUF_FINE_MESHLETS")) c->fine_mode = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("RUF_DIRECT")) c->direct_mode = atoi(e) & 7;
   if (const char *e2 = getenv("RUF_SLICE_FRAMES")) {    // tuning aid
     const int v = atoi(e2);
     if (v >= 0 && v <= 65535) c->slice_frames = v;
@@ -473,7 +490,8 @@ static int alloc_model(ruf_context *c, const MeshletModel &mm, int64_t n_tris, i
   RUF_CUDA(c, cudaMalloc(&c->mverts, mm.verts.size() * sizeof(float)));
   RUF_CUDA(c, cudaMalloc(&c->mtris, mm.tris.size() * sizeof(uint32_t)));
   RUF_CUDA(c, cudaMalloc(&c->part_aabb, mm.part_aabb.size() * sizeof(float)));
-  c->n_meshlets = (int)mm.n_meshlets();
+  c->n_meshlets = (int)mm.n_primary;
+  c->n_meshlets_fine = (int)(mm.n_meshlets() - mm.n_primary);
   c->n_tris = n_tris; c->n_parts = n_parts;
   c->dims.n_tris = n_tris; c->dims.n_parts = n_parts;
   c->have_model = true;
@@ -497,7 +515,7 @@ static int build_model(ruf_context *c, const float *h_xyz, const uint32_t *h_par
 {
   MeshletModel mm;
   // glVertex3f(.., far_plane_*0.99), src/urdf_filter.cpp:592
-  build_meshlets(h_xyz, h_part, n_tris, n_parts, (float)(c->z_far * 0.99), kMeshVerts, kMeshTris, kMeshParts, mm);
+  build_meshlet_sets(h_xyz, h_part, n_tris, n_parts, (float)(c->z_far * 0.99), kMeshVerts, kMeshTris, kMeshTrisFine, kMeshParts, mm);
   const int rc = alloc_model(c, mm, n_tris, n_parts);
   return rc != RUF_OK ? rc : upload_model(c, mm);
 }
@@ -711,7 +729,23 @@ static bool is_pinned_host(const void *p)
   return a.type == cudaMemoryTypeHost;
 }
 
+// The device's address of a pinned host buffer the kernels may read or write themselves (zero copy), or null
+static void *mapped_alias(const void *p)
+{
+  void *d = nullptr;
+  if (!p || cudaHostGetDevicePointer(&d, const_cast<void *>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return d;
+}
+
 // RUF_OK: done.  1: not applicable (pageable buffers, caller's stream, profiling) or overflow -> take the pipeline.
+//
+// Latency path.  Everything a 30 Hz caller waits for is on the critical path of ONE frame, so the graph holds as few nodes
+// as the buffers allow.  With mapped pinned buffers (cudaHostAlloc / ruf_host_alloc: the default) it is four kernel nodes
+// and nothing else: the pose kernel reads the matrices from the context's pinned block and clears the frame's counters,
+// the raster kernel (cluster-split variant) reads the depth image from and writes depth + mask to the caller's buffers
+// over PCIe while it works, and its last CTA stores the status words into the host's copy.  Buffers that are pinned but
+// not mapped get copy nodes instead (depth upload beside the pose / setup kernels, mask read-back beside the depth
+// read-back).  RUF_DIRECT = bit mask 1 outputs, 2 input, 4 matrices + status (default 7) for A/B runs.
 static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, const double *proj, const double *view,
                               const double *part_model, float max_diff, float replace_value, void *depth_out,
                               uint8_t *mask_out)
@@ -733,8 +767,19 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
   ruf_context::FrameGraph &g = c->fg;
   const bool want_mp = c->multipass_mode == 0 || c->multipass_mode == 1 ? c->multipass_mode == 1
                        : (c->wide_share >= 0.0 ? c->wide_share > (c->multipass ? 0.10 : 0.15) : c->multipass);
-  const bool same = g.exec && g.multipass == (int)want_mp && g.enc == enc && g.mask_format == c->mask_format && g.n_parts == P &&
-                    g.max_diff == max_diff && g.replace_value == replace_value && g.ws_bins == c->ws.bins &&
+  int direct = c->direct_mode;
+  void *dev_in = (direct & 2) ? mapped_alias(depth_in) : nullptr;
+  void *dev_out = (direct & 1) ? mapped_alias(depth_out) : nullptr;
+  void *dev_mask = (direct & 1) && mask_out ? mapped_alias(mask_out) : nullptr;
+  if (!dev_in) direct &= ~2;
+  if (!dev_out || (mask_out && !dev_mask)) direct &= ~1;
+  double *dev_mats = (direct & 4) ? (double *)mapped_alias(hm) : nullptr;
+  uint32_t *dev_status = (direct & 4) ? (uint32_t *)mapped_alias(c->h_status) : nullptr;
+  // (the status export needs the cluster-split raster variant: its last CTA does it)
+  const bool cluster = c->cluster_mode >= 0 ? c->cluster_mode != 0 : c->dims.ntiles <= kClusterMaxTiles;
+  if (!dev_mats || !dev_status || !cluster) { direct &= ~4; dev_mats = nullptr; dev_status = nullptr; }
+  const bool same = g.exec && g.direct == direct && g.multipass == (int)want_mp && g.enc == enc && g.mask_format == c->mask_format &&
+                    g.n_parts == P && g.max_diff == max_diff && g.replace_value == replace_value && g.ws_bins == c->ws.bins &&
                     g.stage_in == c->d_in[0] && g.cap_big == c->dims.cap_big && g.cap_tile == c->dims.cap_tile &&
                     (g.mask != nullptr) == (mask_out != nullptr);
   if (!same) {
@@ -743,24 +788,37 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
     RUF_CUDA(c, cudaStreamBeginCapture(sk, cudaStreamCaptureModeRelaxed));
     bool ok = true;
     auto CK = [&](cudaError_t e) { if (e != cudaSuccess) ok = false; };
-    CK(cudaEventRecord(c->ev_fork, sk));
-    CK(cudaStreamWaitEvent(c->s_in, c->ev_fork, 0));
-    CK(cudaMemcpyAsync(c->d_in[0], depth_in, img * es, cudaMemcpyHostToDevice, c->s_in));    // beside the pose / setup kernels
-    CK(cudaEventRecord(c->ev_in[0], c->s_in));
-    CK(cudaMemcpyAsync(c->d_mats[0], hm, mat_bytes, cudaMemcpyHostToDevice, sk));
-    double *dm = c->d_mats[0];
+    const bool copy_in = !(direct & 2), copy_out = !(direct & 1);
+    if (copy_in) {
+      CK(cudaEventRecord(c->ev_fork, sk));
+      CK(cudaStreamWaitEvent(c->s_in, c->ev_fork, 0));
+      CK(cudaMemcpyAsync(c->d_in[0], depth_in, img * es, cudaMemcpyHostToDevice, c->s_in));    // beside the pose / setup kernels
+      CK(cudaEventRecord(c->ev_in[0], c->s_in));
+    }
+    double *dm = dev_mats ? dev_mats : c->d_mats[0];
+    if (!dev_mats) CK(cudaMemcpyAsync(c->d_mats[0], hm, mat_bytes, cudaMemcpyHostToDevice, sk));
     const int64_t launches_before = c->stats.kernel_launches;
-    if (ok && launch(c, 1, c->d_in[0], enc, dm, dm + 16, dm + 32, max_diff, replace_value, c->d_out[0],
-                     mask_out ? c->d_mask[0] : nullptr, nullptr, sk, c->ev_in[0]) != RUF_OK) ok = false;
+    c->dims.fold_clear = 1;
+    c->launch_host_status = dev_status;
+    if (ok && launch(c, 1, copy_in ? c->d_in[0] : dev_in, enc, dm, dm + 16, dm + 32, max_diff, replace_value,
+                     copy_out ? c->d_out[0] : dev_out, mask_out ? (copy_out ? c->d_mask[0] : (uint8_t *)dev_mask) : nullptr, nullptr, sk,
+                     copy_in ? c->ev_in[0] : nullptr) != RUF_OK)
+      ok = false;
+    c->dims.fold_clear = 0;
+    c->launch_host_status = nullptr;
     c->stats.kernel_launches = launches_before;
-    CK(cudaEventRecord(c->ev_k[0], sk));
-    CK(cudaStreamWaitEvent(c->s_out, c->ev_k[0], 0));
-    if (mask_out) CK(cudaMemcpyAsync(mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost, c->s_out));   // beside the depth read-back
-    CK(cudaEventRecord(c->ev_out[0], c->s_out));
-    CK(cudaMemcpyAsync(depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost, sk));
-    CK(cudaMemcpyAsync(c->h_status, c->ws.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
-    CK(cudaMemsetAsync(c->ws.status + 1, 0, 2 * sizeof(uint32_t), sk));
-    CK(cudaStreamWaitEvent(sk, c->ev_out[0], 0));
+    if (copy_out) {
+      CK(cudaEventRecord(c->ev_k[0], sk));
+      CK(cudaStreamWaitEvent(c->s_out, c->ev_k[0], 0));
+      if (mask_out) CK(cudaMemcpyAsync(mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost, c->s_out));   // beside the depth read-back
+      CK(cudaEventRecord(c->ev_out[0], c->s_out));
+      CK(cudaMemcpyAsync(depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost, sk));
+    }
+    if (!dev_status) {
+      CK(cudaMemcpyAsync(c->h_status, c->ws.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
+      CK(cudaMemsetAsync(c->ws.status + 1, 0, 2 * sizeof(uint32_t), sk));
+    }
+    if (copy_out) CK(cudaStreamWaitEvent(sk, c->ev_out[0], 0));
     cudaGraph_t graph = nullptr;
     const cudaError_t ee = cudaStreamEndCapture(sk, &graph);
     if (!ok || ee != cudaSuccess || !graph) {
@@ -777,31 +835,47 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
     cudaGraphGetNodes(graph, nodes.data(), &n);
     for (cudaGraphNode_t nd : nodes) {
       cudaGraphNodeType t;
-      if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeMemcpy) continue;
-      cudaMemcpy3DParms p;
-      if (cudaGraphMemcpyNodeGetParams(nd, &p) != cudaSuccess) continue;
-      if (p.srcPtr.ptr == depth_in) g.n_in = nd;
-      else if (p.dstPtr.ptr == depth_out) g.n_out = nd;
-      else if (mask_out && p.dstPtr.ptr == mask_out) g.n_mask = nd;
+      if (cudaGraphNodeGetType(nd, &t) != cudaSuccess) continue;
+      if (t == cudaGraphNodeTypeMemcpy) {
+        cudaMemcpy3DParms p;
+        if (cudaGraphMemcpyNodeGetParams(nd, &p) != cudaSuccess) continue;
+        if (p.srcPtr.ptr == depth_in) g.n_in = nd;
+        else if (p.dstPtr.ptr == depth_out) g.n_out = nd;
+        else if (mask_out && p.dstPtr.ptr == mask_out) g.n_mask = nd;
+      } else if (t == cudaGraphNodeTypeKernel) {
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && is_raster_kernel(kp.func)) g.n_raster = nd;
+      }
     }
-    if (!g.n_in || !g.n_out || (mask_out && !g.n_mask)) { drop_frame_graph(c); c->use_graph = false; return 1; }
-    g.in = depth_in; g.out = depth_out; g.mask = mask_out;
+    if ((copy_in && !g.n_in) || (copy_out && (!g.n_out || (mask_out && !g.n_mask))) || ((direct & 3) && !g.n_raster)) {
+      drop_frame_graph(c); c->use_graph = false; return 1;
+    }
+    g.in = depth_in; g.out = depth_out; g.mask = mask_out; g.direct = direct;
     g.multipass = (int)c->multipass; g.enc = enc; g.mask_format = c->mask_format; g.n_parts = P; g.max_diff = max_diff; g.replace_value = replace_value;
     g.ws_bins = c->ws.bins; g.stage_in = c->d_in[0]; g.cap_big = c->dims.cap_big; g.cap_tile = c->dims.cap_tile;
   } else {
-    // same shape of work, other host buffers: retarget the three copy nodes of the instantiated graph
-    if (g.in != depth_in) {
+    // same shape of work, other host buffers: retarget the copy nodes of the instantiated graph and, where the raster
+    // kernel itself reads or writes the caller's buffers, its FrameBuffers argument
+    if (g.in != depth_in && g.n_in)
       RUF_CUDA(c, cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_in, c->d_in[0], depth_in, img * es, cudaMemcpyHostToDevice));
-      g.in = depth_in;
-    }
-    if (g.out != depth_out) {
+    if (g.out != depth_out && g.n_out)
       RUF_CUDA(c, cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_out, depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost));
-      g.out = depth_out;
-    }
-    if (mask_out && g.mask != mask_out) {
+    if (mask_out && g.mask != mask_out && g.n_mask)
       RUF_CUDA(c, cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_mask, mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost));
-      g.mask = mask_out;
+    if ((direct & 3) && (g.in != depth_in || g.out != depth_out || g.mask != mask_out)) {
+      cudaKernelNodeParams kp;
+      RUF_CUDA(c, cudaGraphKernelNodeGetParams(g.n_raster, &kp));
+      FrameBuffers fb = *static_cast<const FrameBuffers *>(kp.kernelParams[kRasterArgFrameBuffers]);
+      if (direct & 2) fb.depth_in = dev_in;
+      if (direct & 1) { fb.depth_out = dev_out; fb.mask_out = (uint8_t *)dev_mask; }
+      void *args[kRasterArgCount];
+      for (int i = 0; i < kRasterArgCount; ++i) args[i] = kp.kernelParams[i];
+      args[kRasterArgFrameBuffers] = &fb;
+      kp.kernelParams = args;
+      RUF_CUDA(c, cudaGraphExecKernelNodeSetParams(g.exec, g.n_raster, &kp));
+      RUF_CUDA(c, cudaGraphKernelNodeSetParams(g.n_raster, &kp));     // the template graph follows: the next retarget starts from here
     }
+    g.in = depth_in; g.out = depth_out; g.mask = mask_out;
   }
   RUF_CUDA(c, cudaGraphLaunch(g.exec, sk));
   RUF_CUDA(c, cudaStreamSynchronize(sk));
@@ -1134,7 +1208,7 @@ int ruf_group_set_model(ruf_group *g, const float *tri_xyz, const uint32_t *tri_
     if (tri_part[t] >= (uint32_t)n_parts) return gfail(g, RUF_ERR_INVALID, "tri_part out of range");
   ruf_context *c0 = g->ctx[0];
   MeshletModel mm;                 // built once on the host, uploaded once (device 0), broadcast to the rest
-  build_meshlets(tri_xyz, tri_part, n_tris, n_parts, (float)(c0->z_far * 0.99), kMeshVerts, kMeshTris, kMeshParts, mm);
+  build_meshlet_sets(tri_xyz, tri_part, n_tris, n_parts, (float)(c0->z_far * 0.99), kMeshVerts, kMeshTris, kMeshTrisFine, kMeshParts, mm);
   for (ruf_context *c : g->ctx) {
     if (cudaSetDevice(c->device) != cudaSuccess) return gfail(g, RUF_ERR_CUDA, "cudaSetDevice failed");
     const int rc = alloc_model(c, mm, n_tris, n_parts);

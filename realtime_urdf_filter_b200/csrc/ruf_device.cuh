@@ -101,10 +101,21 @@ constexpr int kSetupThreads = RUF_SETUP_THREADS;
 constexpr int kMeshVerts = RUF_MESH_VERTS;
 constexpr int kMeshTris = RUF_MESH_TRIS;
 constexpr int kMeshParts = 32;
+constexpr int kMeshTrisFine = RUF_SETUP_THREADS;  // the fine cut of the model: one triangle per setup thread
+constexpr int kFineMaxCtas = 2 * 148;             // (frames x meshlets) of a launch up to which the fine cut is used
 constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   // triangles per thread
 constexpr int kSetupFrames = RUF_SETUP_FRAMES;  // frames a setup CTA loops over with its meshlet in registers
 static_assert(kMeshVerts <= 1024 && kMeshTris <= 1023, "meshlet indices are packed in 10 bits");
 constexpr int kMultiPassUnits = 128;            // MP variant: records up to this many units are dealt out in passes of kMaxUnits
+#ifndef RUF_CLUSTER_SPLIT
+#define RUF_CLUSTER_SPLIT 4
+#endif
+#ifndef RUF_CLUSTER_BATCH
+#define RUF_CLUSTER_BATCH 8
+#endif
+constexpr int kClusterBatch = RUF_CLUSTER_BATCH;   // records per warp batch of that variant (divides 32)
+constexpr int kClusterSplit = RUF_CLUSTER_SPLIT;   // CTAs per tile of the low-latency raster variant (divides 32)
+constexpr int kClusterMaxTiles = 1024;           // (frames x tiles) of a launch up to which the cluster-split variant is used
 constexpr int kWideCap = 16;                    // wide records a raster CTA parks for its cooperative final phase
 constexpr int kMaxTiles = 4096;
 constexpr int kPartStride = 8;                  // floats per part in Model::part_aabb
@@ -159,7 +170,9 @@ struct Dims {
   int n_meshlets;              // setup CTAs per frame
   int ctr_stride;              // uint32 words of one frame's counter block = kCtrWords + 2 * ntiles
   int force_fpc;               // > 0: frames per setup CTA (testing aid, RUF_SETUP_FRAMES_FORCE); 0 = heuristic
-  int multipass;               // raster kernel variant of this launch (ruf_raster_filter_kernel<ENC, MP>)
+  int multipass;               // raster kernel variant of this launch (ruf_raster_filter_kernel<ENC, MP, CL>)
+  int fold_clear;              // the pose kernel clears the counter blocks (single-frame graph) instead of a memset before it
+  int cluster_split;           // low-latency variant: kClusterSplit CTAs (one thread-block cluster) share a tile
   float halfw, halfh, guard_x, guard_y;
 };
 
@@ -176,6 +189,8 @@ struct FrameBuffers {
   float *zbuf_out;       // may be null
   int vec_ok;            // rows are 16-byte aligned for 8-pixel vectors
   int mask_bits;         // mask_out holds 1 bit per pixel (W % 8 == 0 required) instead of one 0 / 255 byte
+  uint32_t *host_status; // cluster-split variant only, may be null: the host's pinned (mapped) copy of the status words, written
+                         // by the last CTA of the launch
 };
 
 struct Workspace {
@@ -198,6 +213,8 @@ struct Model {
 
 // cudaSuccess iff the loaded module has an image the current device can run (sm_100a only)
 cudaError_t check_kernel_image();
+bool is_raster_kernel(const void *func);   // for the host's graph bookkeeping
+constexpr int kRasterArgCount = 8, kRasterArgFrameBuffers = 6;   // ruf_raster_filter_kernel's parameter list
 // forward kinematics: joint positions -> link poses -> part models + view matrix
 struct Kinematics {
   int n_links, n_parts, cam_link;

@@ -255,11 +255,13 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
 __global__ void __launch_bounds__(256)
 ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view, const double *__restrict__ part_model,
                 const double *__restrict__ lookat, const float *__restrict__ part_aabb, int n_parts, int n_frames,
-                float *__restrict__ mvp, uint8_t *__restrict__ vis)
+                float *__restrict__ mvp, uint8_t *__restrict__ vis, uint32_t *__restrict__ clear, long long n_clear)
 {
   __shared__ __align__(16) float s_m[16][16];
   const int rows = n_parts + 1;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // single-frame graph: the frame's counter block is cleared here instead of by a memset node of its own
+  for (long long i = gid; i < n_clear; i += (long long)gridDim.x * blockDim.x) clear[i] = 0u;
   const long long n_mats = (long long)n_frames * rows;
   float val = 0.0f;
   if (gid < n_mats * 16) {
@@ -410,6 +412,21 @@ __device__ __forceinline__ bool tri_may_touch(const uint4 &a, const uint4 &b, co
   return i0 <= i1 && j0 <= j1;
 }
 
+#ifdef RUF_X_TIMELINE
+__device__ unsigned long long g_timeline1[1024 * 8 * 8];      // setup kernel: [cta][warp][mark]
+__device__ __forceinline__ void tl1_mark(int slot)
+{
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta < 1024) g_timeline1[(cta * 8 + (threadIdx.x >> 5)) * 8 + slot] = t;
+  }
+}
+#define TL1(x) tl1_mark(x)
+#else
+#define TL1(x)
+#endif
 __global__ void __launch_bounds__(kSetupThreads, RUF_SETUP_MIN_BLOCKS)
 ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *__restrict__ vis_all, Dims d,
                      int n_frames, int frames_per_cta, TriRec *big_all, BinRec *bins_all, uint32_t *ctr_all)
@@ -423,6 +440,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 
+  TL1(0);
   const uint4 hdr = __ldg(m.meshlets + blockIdx.x);
   const uint32_t vert_off = hdr.x, tri_off = hdr.y, part_lo = hdr.w;
   const int nverts = (int)(hdr.z & 1023u), ntris = (int)((hdr.z >> 10) & 1023u), npm1 = (int)(hdr.z >> 20);
@@ -445,6 +463,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
       any |= (lane <= npm1) && (__ldg(vis_all + (size_t)f * rows + part_lo + lane) & 1) != 0;
     if (!__any_sync(0xffffffffu, any)) return;
   }
+  TL1(1);
   // the meshlet stays on chip for all frames of this CTA: vertex positions in registers, index triples in shared memory
   float4 vq[kVPT];
   __shared__ uint32_t s_tri[kTPT * kSetupThreads];     // the meshlet's packed index triples (registers are the scarce resource: 40 per thread)
@@ -474,6 +493,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
     pfront_next = __ballot_sync(0xffffffffu, (vb & 2u) != 0u);
   }
   __syncthreads();
+  TL1(2);
 
   // One barrier per frame (B1: the frame's vertices are in shared memory).  Between two B1 the warps run
   // independently: a warp classifies ITS triangles, compacts ITS survivors and reserves list space itself.
@@ -506,6 +526,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
     }
     cp_async_wait_all();                           // this thread's share of the matrices of frame f + 1 has landed
     __syncthreads();                               // B1 (also taken when the whole meshlet is culled in this frame)
+    TL1(3);
     // matrices of frame f + 2 -> shared memory (cp.async: no registers held).  Their buffer was last read in
     // frame f - 1, which every warp has left by now; they are read after B1 of frame f + 1.
     if (f + 2 < f1) {
@@ -540,6 +561,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         nclip += __popc(bc);
       }
       __syncwarp();
+      TL1(4);
 
       // ---- S3 for the rare triangles that cross the near plane or the guard band: recompute the three
       // clip-space vertices (same inputs, same bits as P1), clip, set up, append to the frame's big list ----
@@ -553,6 +575,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
                       xform(c0, c1, c2, c3, qc.x, qc.y, qc.z), d, big, ctr);
       }
 
+      TL1(5);
       // ---- P3 + P4: one lane per SURVIVOR (dense): full setup, then the warp reserves list space per tile ----
       BinRec *bins = bins_all + (size_t)f * d.ntiles * d.cap_tile;
       for (int s0 = 0; s0 < nkeep; s0 += 32) {
@@ -689,6 +712,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         }
       }
       __syncwarp();                                // the warp's list is rewritten in the next frame
+      TL1(6);
     }
   }
 }
@@ -805,6 +829,70 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
+// thread-block cluster: barrier over all threads of all CTAs (release / acquire: shared-memory writes made before it are
+// visible to the other CTAs' ld.shared::cluster after it) and loads from another CTA's shared memory (DSMEM)
+__device__ __forceinline__ void cluster_sync_all()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_map(const void *p, uint32_t rank)
+{
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_cluster_v4(uint32_t a)
+{
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
+#ifdef RUF_X_TIMELINE
+// debugging aid (never in the shipped library): per-CTA timestamps of the raster kernel's phases
+__device__ unsigned long long g_timeline[8192 * 8];
+__device__ __forceinline__ void tl_mark(int slot)
+{
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (cta < 8192) g_timeline[cta * 8 + slot] = t;
+  }
+}
+#define TL(x) tl_mark(x)
+// per-warp batch log: [cta][warp][slot] = (t_claim, t_ready, t_units, t_done | items << 48)
+__device__ unsigned long long g_batchlog[1024 * 8 * 16 * 4];
+__device__ __forceinline__ unsigned long long tl_now()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define BL_DECL unsigned long long bl_t0 = 0, bl_t1 = 0, bl_t2 = 0; int bl_items = 0; int bl_k = 0
+#define BL(v) v = tl_now()
+#define BL_END(pass)                                                                                         \
+  do {                                                                                                       \
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                     \
+    if (lane == 0 && cta < 1024 && bl_k < 16) {                                                              \
+      unsigned long long *q = g_batchlog + ((size_t)(cta * 8 + warp) * 16 + bl_k) * 4;                       \
+      q[0] = bl_t0; q[1] = bl_t1; q[2] = bl_t2; q[3] = (tl_now() - bl_t2) | ((unsigned long long)(bl_items | (pass << 15)) << 48);                \
+    }                                                                                                        \
+    ++bl_k;                                                                                                  \
+  } while (0)
+#else
+#define TL(x)
+#define BL_DECL
+#define BL(v)
+#define BL_END(pass)
+#endif
+
 __device__ __forceinline__ void consumer_bar_sync()
 {
   __syncthreads();
@@ -1015,7 +1103,15 @@ ruf_tile_info_kernel(Dims d, int n_frames, const TriRec *__restrict__ big_all, c
 // passes instead of being parked for the cooperative 8x4-footprint walk; chosen per launch by the host from the share of
 // such records in the previous launch (ruf_api.cu: choose_multipass).  At 1280x960 the PR2-like model's slivers are
 // mostly above 24 units: MP is 34 % faster on C3; on C2 (5 % such records) the plain variant is 4 % faster.
-template <int ENC, bool MP>
+//
+// CL ("cluster split", the low-latency variant for launches of one or a few frames, where a frame's few dozen busy tiles
+// would leave most of the 148 SMs idle and the busiest tile is the critical path): a thread-block cluster of CL CTAs
+// shares ONE tile.  Each CTA rasterises 1/CL of the tile's record list into its own shared-memory z tile; after a cluster
+// barrier the CTA that owns a band of 64/CL tile rows reads those rows from all CL z tiles through distributed shared
+// memory, takes the minimum (min is associative and commutative: the same z image as one CTA walking the whole list)
+// and runs the fragment stage for them.  The depth cull of the back pass uses, per 4x4 block, the smallest of the CL
+// partial block maxima: an upper bound of the block maximum of the merged image, so still result-neutral.
+template <int ENC, bool MP, int CL>
 __global__ void __launch_bounds__(kRasterThreads, RUF_RASTER_MIN_BLOCKS)
 ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRec *__restrict__ bins_all,
                          const uint32_t *__restrict__ ctr_all, const uint4 *__restrict__ tinfo, ShaderParams sp, FrameBuffers fb,
@@ -1034,6 +1130,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   __shared__ uint32_t s_next[2];                 // batch claim counters of the two passes
   __shared__ int s_issued[kStages];              // latest chunk whose bulk copies were issued into each ring stage
   __shared__ uint32_t s_zblk[(kTileH / 4) * 16]; // maxima of the 4x4 blocks of the z tile (depth cull)
+  __shared__ uint32_t s_zblk_cl[CL > 1 ? (kTileH / 4) * 16 : 1];   // CL: the smallest of the cluster's partial block maxima
   __shared__ uint8_t s_bigcls[kRasterThreads];
   __shared__ uint32_t s_nwide, s_nstat;
   __shared__ __align__(16) TriRec s_wide[kWideCap];   // wide records of this tile, rasterised by the whole CTA at the end
@@ -1041,9 +1138,34 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   __shared__ float s_bigz[kRasterThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + blockIdx.x;
-  const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
+  // CL: grid.x = tiles_x * CL with cluster dimensions (CL, 1, 1): blockIdx.x % CL is the rank in the cluster
+  const int tbx = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const uint32_t crank = CL > 1 ? blockIdx.x % CL : 0u;
+  const int frame = blockIdx.z, tile = blockIdx.y * d.tiles_x + tbx;
+  const int tile_x0 = tbx * kTileW, tile_y0 = blockIdx.y * kTileH;
   const int prow = tid >> 3, pcol = (tid & 7) * 8;
+  // CL: this thread runs the fragment stage (its rows prow and prow + 32 belong to this CTA's band); warp-uniform
+  const bool frag = CL == 1 || (uint32_t)(prow / (32 / CL)) == crank;
+  // records per warp batch: a full warp of 32 in the throughput variant; in the cluster-split variant the SMs are nearly
+  // empty and a lone warp needs ~0.6 us per round of 32 units, so the records are spread over more warps in smaller batches
+  constexpr uint32_t RB = CL > 1 ? (uint32_t)kClusterBatch : 32u;
+  TL(0);
+  // CL, single-frame graph: the last CTA of the launch writes the status words straight into the host's pinned copy and
+  // restarts the statistics -- no read-back copy and no memset node behind the kernel.  Every CTA calls this once, on
+  // whichever path it leaves (flat tiles write no status word, so they may take their ticket early).
+  auto export_status = [&]() {
+    if (CL > 1 && fb.host_status && tid == 0) {
+      __threadfence();
+      if (atomicAdd(status + 3, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u) {
+        __threadfence();
+        volatile uint32_t *hs = fb.host_status;
+        hs[0] = atomicOr(status, 0u);
+        hs[1] = atomicExch(status + 1, 0u);
+        hs[2] = atomicExch(status + 2, 0u);
+        status[3] = 0u;
+      }
+    }
+  };
   // FLAT tiles (two thirds of the tiles of a typical frame: no binned record, only constant-depth covering records in
   // the big list = the background quad) were recognised by ruf_tile_info_kernel, which also took the virtual depth
   // through to_linear_depth and the threshold: what is left is a streaming pass (5 B/px for 16UC1) that never touches
@@ -1055,6 +1177,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
       const uint32_t repl_u16 = f32_to_u16(sp.replace_value);
       const uint32_t repl2 = repl_u16 | (repl_u16 << 16);
       const float zt = __uint_as_float(ti.z);
+      export_status();
+      if (!frag) return;
 #pragma unroll
       for (int half = 0; half < kRowsPerThread; ++half) {
         const int gy = tile_y0 + prow + 32 * half, gx = tile_x0 + pcol;
@@ -1112,26 +1236,36 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   uint32_t nf = nfb.x, nb = nfb.y;
   nf = min(nf, d.cap_tile);                  // an overflow (the two runs met) was flagged by ruf_tile_info_kernel
   nb = min(nb, d.cap_tile - nf);
+  const BinRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
+  const BinRec *flist = list, *blist = list + (d.cap_tile - nb);
+  const uint32_t nb_tile = nb;               // cluster-uniform
+  const uint32_t cnt_any = nf + nb;          // records of the whole tile (CL: cluster-uniform, decides which barriers exist)
+  if (CL > 1) {
+    // this CTA's share of both runs, in whole batches of RB records
+    const uint32_t fbt = (nf + RB - 1u) / RB, bbt = (nb + RB - 1u) / RB;
+    const uint32_t f0 = min(nf, RB * (fbt * crank / CL)), f1 = min(nf, RB * (fbt * (crank + 1u) / CL));
+    const uint32_t b0 = min(nb, RB * (bbt * crank / CL)), b1 = min(nb, RB * (bbt * (crank + 1u) / CL));
+    flist += f0; blist += b0;
+    nf = f1 - f0; nb = b1 - b0;
+  }
   const uint32_t cnt = nf + nb;
   const int nchunks = (int)((cnt + kChunk - 1) / kChunk);
-  const BinRec *list = bins_all + ((size_t)frame * d.ntiles + tile) * d.cap_tile;
   // chunk c of the virtual list "front run, then back run": at most two bulk copies into one ring stage
   auto issue_chunk = [&](int c, int stage) {
     const uint32_t lo = (uint32_t)c * kChunk, hi = min(lo + (uint32_t)kChunk, cnt);
     mbar_arrive_expect_tx(&full_bar[stage], (hi - lo) * (uint32_t)sizeof(BinRec));
     const uint32_t fhi = min(hi, nf);
-    if (lo < fhi) bulk_g2s(&sbuf[stage][0], list + lo, (fhi - lo) * (uint32_t)sizeof(BinRec), &full_bar[stage]);
+    if (lo < fhi) bulk_g2s(&sbuf[stage][0], flist + lo, (fhi - lo) * (uint32_t)sizeof(BinRec), &full_bar[stage]);
     const uint32_t blo = max(lo, nf);
     if (blo < hi)
-      bulk_g2s(&sbuf[stage][blo - lo], list + (d.cap_tile - nb) + (blo - nf), (hi - blo) * (uint32_t)sizeof(BinRec),
-               &full_bar[stage]);
+      bulk_g2s(&sbuf[stage][blo - lo], blist + (blo - nf), (hi - blo) * (uint32_t)sizeof(BinRec), &full_bar[stage]);
   };
-  if (cnt) {
+  if (cnt_any) {
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&full_bar[s], 1);                        // the issuing thread's arrive.expect_tx
-        mbar_init(&empty_bar[s], kChunk / 32);             // one arrive per batch of 32 records
+        mbar_init(&empty_bar[s], kChunk / RB);             // one arrive per batch of RB records
       }
       mbar_fence_init();
       s_next[0] = 0; s_next[1] = 0;
@@ -1180,10 +1314,11 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   // results are only read behind the end-of-raster barrier, so the other warps start on the tile's records while warp 0
   // still waits for its big-list records (two dependent global loads and ~150 instructions of 64-bit arithmetic).
   __syncthreads();
+  TL(1);
   classify(0);
-  if (!cnt) __syncthreads();       // no raster phase (and no end-of-raster barrier) on this path
+  if (!cnt_any) __syncthreads();   // no raster phase (and no end-of-raster barrier) on this path
 
-  if (cnt) {
+  if (cnt_any) {
     {
       // binned triangles: a chunk's records are batches of 32; warps claim batches from a shared
       // counter (a warp that drew light triangles simply takes the next batch), and a stage goes
@@ -1194,32 +1329,66 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
       // barrier the maximum of every 4x4 block of the z tile is taken once; a record whose nearest bbox sample
       // is not in front of the block maxima under its bbox cannot change a pixel (z-tile values only ever
       // decrease) and is dropped before any unit is dealt.  On closed meshes that is nearly all of them.
-      const uint32_t nbatches = (cnt + 31u) / 32u;
-      uint32_t nb_front = kDepthCull ? min(nbatches, (nf + 31u) / 32u) : nbatches;
-      if (nbatches - nb_front < RUF_MIN_BACK_BATCHES) nb_front = nbatches;   // a second pass (two barriers) must pay for itself
+      const uint32_t nbatches = (cnt + RB - 1u) / RB;
+      BL_DECL;
+      uint32_t nb_front = kDepthCull ? min(nbatches, (nf + RB - 1u) / RB) : nbatches;
+      if (CL == 1) {
+        if (nbatches - nb_front < RUF_MIN_BACK_BATCHES) nb_front = nbatches;   // a second pass (two barriers) must pay for itself
+      } else if (nb_tile < 32u * RUF_MIN_BACK_BATCHES) {
+        nb_front = nbatches;                   // CL: every CTA of the cluster takes the same decision (cluster barrier inside)
+      }
       for (int pass = 0; pass < 2; ++pass) {
       const uint32_t b_lo = pass ? nb_front : 0u, b_hi = pass ? nbatches : nb_front;
       if (pass) {
-        if (b_lo >= b_hi) break;
+        if (CL == 1 ? (b_lo >= b_hi) : (!kDepthCull || nb_tile < 32u * RUF_MIN_BACK_BATCHES)) break;
         __syncthreads();                      // every front record is in the z tile
-        if (tid < (kTileH / 4) * 16) {
-          const uint4 *row = reinterpret_cast<const uint4 *>(&sz[(tid >> 4) * 4 * kTileW + (tid & 15) * 4]);
-          uint32_t m = 0;
+        TL(2);
+        if (CL == 1) {
+          if (tid < (kTileH / 4) * 16) {
+            const uint4 *row = reinterpret_cast<const uint4 *>(&sz[(tid >> 4) * 4 * kTileW + (tid & 15) * 4]);
+            uint32_t m = 0;
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const uint4 q = row[rr * (kTileW / 4)];
-            m = max(max(m, max(q.x, q.y)), max(q.z, q.w));
+            for (int rr = 0; rr < 4; ++rr) {
+              const uint4 q = row[rr * (kTileW / 4)];
+              m = max(max(m, max(q.x, q.y)), max(q.z, q.w));
+            }
+            s_zblk[tid] = m;
           }
-          s_zblk[tid] = m;
+        } else {
+          // CL: the block maxima of the MERGED front image.  This CTA merges its band of 256 / CL blocks (one thread per
+          // block row: the CL partial rows through DSMEM, min per pixel, max over the row, max over the block's four
+          // rows by shuffles); after a second cluster barrier every CTA collects all 256 maxima from their owners.
+          cluster_sync_all();                 // every CTA's front records are in its z tile
+          constexpr int kBand = 256 / CL;     // blocks per CTA
+          uint32_t m = 0;
+          if (tid < 4 * kBand) {
+            const int b = (int)crank * kBand + (tid >> 2), rr = tid & 3;
+            const uint32_t *src = &sz[((b >> 4) * 4 + rr) * kTileW + (b & 15) * 4];
+            uint4 q = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+#pragma unroll
+            for (uint32_t rk = 0; rk < (uint32_t)CL; ++rk) {
+              const uint4 a = ld_cluster_v4(cluster_map(src, rk));
+              q = make_uint4(min(q.x, a.x), min(q.y, a.y), min(q.z, a.z), min(q.w, a.w));
+            }
+            m = max(max(q.x, q.y), max(q.z, q.w));
+          }
+          m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          if (tid < 4 * kBand && (tid & 3) == 0) s_zblk[(int)crank * kBand + (tid >> 2)] = m;
+          cluster_sync_all();
+          if (tid < 256) s_zblk_cl[tid] = ld_cluster_u32(cluster_map(&s_zblk[tid], (uint32_t)(tid / kBand)));
         }
         __syncthreads();
       }
+      if (pass) TL(3);
+      const uint32_t *zblk = CL > 1 ? s_zblk_cl : s_zblk;
       for (;;) {
         uint32_t bt = 0;
+        BL(bl_t0);
         if (lane == 0) bt = b_lo + smem_add(smem_u32(&s_next[pass]), 1u);
         bt = __shfl_sync(0xffffffffu, bt, 0);
         if (bt >= b_hi) break;
-        const int c = (int)(bt / (kChunk / 32));              // ring position of the chunk
+        const int c = (int)(bt / (kChunk / RB));              // ring position of the chunk
         const int stage = c % kStages;
         // A parity wait can only tell the current phase from the one before it.  Warps whose batches were
         // cheap (depth-culled) can claim a batch of a chunk that has not even been issued yet, while the
@@ -1227,8 +1396,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         // for "complete".  So first wait until the chunk's copies have been issued into the stage.
         while (*reinterpret_cast<volatile int *>(&s_issued[stage]) < c) {}
         mbar_wait(&full_bar[stage], ((uint32_t)c / kStages) & 1);
+        BL(bl_t1);
         const uint32_t nrec = min(cnt - (uint32_t)c * kChunk, (uint32_t)kChunk);
-        const uint32_t idx = (bt % (kChunk / 32)) * 32u + (uint32_t)lane;
+        const uint32_t idx = (bt % (kChunk / RB)) * RB + (uint32_t)lane;
         // ---- phase 1: one lane per record: clip to the tile, derive the incremental edge setup ----
         TriRec r;
         int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
@@ -1236,7 +1406,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         int sA0 = 0, sA1 = 0, sA2 = 0, sB0 = 0, sB1 = 0, sB2 = 0, r0 = 0, r1 = 0, r2 = 0;
         int ncb = 0, nunits = 0;
         int geo = 0, bx = 0, by = 0;   // tile-local bbox origin and extent (packed); sample (i0, j0) relative to vertex 0
-        if (idx < nrec) {
+        if ((RB == 32u || (uint32_t)lane < RB) && idx < nrec) {
           r = load_bin_smem(&sbuf[stage][idx]);
           // candidate samples (S6): the pixel bbox of the snapped vertices, clipped to this tile and to the viewport
           const int xmin = min(r.x0, min(r.x1, r.x2)), xmax = max(r.x0, max(r.x1, r.x2));
@@ -1264,7 +1434,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
             if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 16) {
               uint32_t zmaxb = 0;
               for (int yy = cy0; yy <= cy1; ++yy)
-                for (int xx = cx0; xx <= cx1; ++xx) zmaxb = max(zmaxb, s_zblk[yy * 16 + xx]);
+                for (int xx = cx0; xx <= cx1; ++xx) zmaxb = max(zmaxb, zblk[yy * 16 + xx]);
               const float fxa = (float)(i0 * kSubpix + kSubpixHalf - r.x0), fxb = (float)(i1 * kSubpix + kSubpixHalf - r.x0);
               const float rza = fmaf(r.gy, (float)(j0 * kSubpix + kSubpixHalf - r.y0), r.z0);
               const float rzb = fmaf(r.gy, (float)(j1 * kSubpix + kSubpixHalf - r.y0), r.z0);
@@ -1297,13 +1467,13 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         if (lane == 0) {
           // this batch sits in registers.  A short last chunk has fewer batches: whoever drew its
           // first batch also arrives for the missing ones so that the barrier phase always completes.
-          const uint32_t in_chunk = (nrec + 31u) / 32u;
-          const uint32_t extra = ((bt % (kChunk / 32)) == 0) ? (kChunk / 32 - in_chunk) : 0u;
+          const uint32_t in_chunk = (nrec + RB - 1u) / RB;
+          const uint32_t extra = ((bt % (kChunk / RB)) == 0) ? (kChunk / RB - in_chunk) : 0u;
           mbar_arrive_n(&empty_bar[stage], 1u + extra);
           // whoever took the chunk's last batch refills the stage with chunk c + kStages once all batches of
           // chunk c sit in registers (the other warps are at most a few shared-memory loads away from that)
           const int cn = c + kStages;
-          if ((bt % (kChunk / 32)) == (kChunk / 32) - 1 && cn < nchunks) {
+          if ((bt % (kChunk / RB)) == (kChunk / RB) - 1 && cn < nchunks) {
             mbar_wait(&empty_bar[stage], ((uint32_t)c / kStages) & 1);
             issue_chunk(cn, stage);
             __threadfence_block();                          // the barrier's new phase is set up before the flag says so
@@ -1339,6 +1509,10 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         // round by round, so every lane does the same amount of branch-free work.  Unit table in
         // shared memory: owner lane | unit row << 5 | unit column << 10.
         int udone = 0;                         // MP: units of this lane's record dealt out in earlier passes
+        BL(bl_t2);
+#ifdef RUF_X_TIMELINE
+        bl_items = 0;
+#endif
         for (;;) {
         const int nu = MP ? min(nunits - udone, kMaxUnits) : nunits;
         if (MP && !__any_sync(0xffffffffu, nu > 0)) break;
@@ -1350,6 +1524,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         }
         const int excl = incl - nu;
         const int items = __shfl_sync(0xffffffffu, incl, 31);
+#ifdef RUF_X_TIMELINE
+        bl_items += items;
+#endif
         uint16_t *utab = s_units[warp];
         {
           int row = 0, cb = 0;
@@ -1421,6 +1598,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         if (!MP) break;
         udone += nu;
         }
+        BL_END(pass);
       }
       }
     }
@@ -1437,6 +1615,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
       }
       __syncthreads();
     }
+    TL(4);
+    if (CL > 1) cluster_sync_all();           // every CTA of the cluster has finished its share of the tile's records
+    TL(5);
   }
 
   // Every thread owns 8 consecutive pixels of kRowsPerThread tile rows (32 rows apart): fetch the rasterised
@@ -1445,9 +1626,23 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   float zall[kRowsPerThread][8];
 #pragma unroll
   for (int half = 0; half < kRowsPerThread; ++half) {
-    if (cnt) {
-      const uint4 zq0 = *reinterpret_cast<const uint4 *>(&sz[(prow + 32 * half) * kTileW + pcol]);
-      const uint4 zq1 = *reinterpret_cast<const uint4 *>(&sz[(prow + 32 * half) * kTileW + pcol + 4]);
+    if (cnt_any) {
+      uint4 zq0, zq1;
+      if (CL == 1) {
+        zq0 = *reinterpret_cast<const uint4 *>(&sz[(prow + 32 * half) * kTileW + pcol]);
+        zq1 = *reinterpret_cast<const uint4 *>(&sz[(prow + 32 * half) * kTileW + pcol + 4]);
+      } else {
+        zq0 = zq1 = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+        if (frag) {
+#pragma unroll
+          for (uint32_t rk = 0; rk < (uint32_t)CL; ++rk) {
+            const uint32_t a = cluster_map(&sz[(prow + 32 * half) * kTileW + pcol], rk);
+            const uint4 a0 = ld_cluster_v4(a), a1 = ld_cluster_v4(a + 16u);
+            zq0 = make_uint4(min(zq0.x, a0.x), min(zq0.y, a0.y), min(zq0.z, a0.z), min(zq0.w, a0.w));
+            zq1 = make_uint4(min(zq1.x, a1.x), min(zq1.y, a1.y), min(zq1.z, a1.z), min(zq1.w, a1.w));
+          }
+        }
+      }
       zall[half][0] = __uint_as_float(zq0.x); zall[half][1] = __uint_as_float(zq0.y); zall[half][2] = __uint_as_float(zq0.z);
       zall[half][3] = __uint_as_float(zq0.w); zall[half][4] = __uint_as_float(zq1.x); zall[half][5] = __uint_as_float(zq1.y);
       zall[half][6] = __uint_as_float(zq1.z); zall[half][7] = __uint_as_float(zq1.w);
@@ -1467,6 +1662,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         __syncthreads();
       }
       const uint32_t nl = min(nbig - b0, (uint32_t)kRasterThreads);
+      if (CL > 1 && !frag) continue;
       for (uint32_t b = 0; b < nl; ++b) {
         const uint32_t c = s_bigcls[b];
         if (c == 0) continue;
@@ -1515,6 +1711,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
     }
   }
 
+  TL(6);
   // ---- fused fragment stage (include/shaders/urdf_filter.frag:19-35): 8 pixels per thread and row, vector loads/stores ----
   const uint32_t repl_u16 = f32_to_u16(sp.replace_value);     // convertTo(CV_16U, 1000) of the replaced pixels, :311
   const float kInf = __int_as_float(0x7f800000);
@@ -1522,7 +1719,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   for (int half = 0; half < kRowsPerThread; ++half) {
     const int trow = prow + 32 * half;
     const int gy = tile_y0 + trow, gx = tile_x0 + pcol;
-    if (gy >= d.H || gx >= d.W) continue;
+    if (gy >= d.H || gx >= d.W || !frag) continue;
     const size_t base = (size_t)frame * d.W * d.H + (size_t)gy * d.W + gx;
     const float (&zw)[8] = zall[half];
     if (fb.vec_ok && gx + 8 <= d.W) {
@@ -1598,6 +1795,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
       shade_scalar<ENC>(fb, sp, base, min(8, d.W - gx), ztmp, 1);
     }
   }
+  if (CL > 1 && cnt_any) cluster_sync_all();   // no CTA leaves while another one may still read its z tile
+  export_status();
+  TL(7);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1778,16 +1978,62 @@ cudaError_t launch_fk(const Kinematics &k, int n_frames, const double *d_joint_q
   return cudaGetLastError();
 }
 
+// the raster kernel's instantiations: [cluster split][multi-pass][encoding]
+typedef void (*RasterFn)(Dims, const TriRec *, const BinRec *, const uint32_t *, const uint4 *, ShaderParams, FrameBuffers, uint32_t *);
+static RasterFn raster_fn(int enc, bool mp, bool cl)
+{
+  static const RasterFn fns[2][2][2] = {
+      {{ruf_raster_filter_kernel<0, false, 1>, ruf_raster_filter_kernel<1, false, 1>},
+       {ruf_raster_filter_kernel<0, true, 1>, ruf_raster_filter_kernel<1, true, 1>}},
+      {{ruf_raster_filter_kernel<0, false, kClusterSplit>, ruf_raster_filter_kernel<1, false, kClusterSplit>},
+       {ruf_raster_filter_kernel<0, true, kClusterSplit>, ruf_raster_filter_kernel<1, true, kClusterSplit>}}};
+  return fns[cl ? 1 : 0][mp ? 1 : 0][enc == 1 ? 1 : 0];
+}
+
+#ifdef RUF_X_TIMELINE
+extern "C" __attribute__((visibility("default"))) int ruf_debug_timeline(unsigned long long *out, int n_words)
+{
+  cudaMemcpyFromSymbol(out, g_timeline, (size_t)n_words * 8);
+  static unsigned long long zero[8192 * 8];
+  cudaMemcpyToSymbol(g_timeline, zero, sizeof(zero));
+  return (int)cudaGetLastError();
+}
+extern "C" __attribute__((visibility("default"))) int ruf_debug_timeline1(unsigned long long *out)
+{
+  cudaMemcpyFromSymbol(out, g_timeline1, sizeof(unsigned long long) * 1024 * 64);
+  void *p = nullptr;
+  cudaGetSymbolAddress(&p, g_timeline1);
+  cudaMemset(p, 0, sizeof(unsigned long long) * 1024 * 64);
+  return (int)cudaGetLastError();
+}
+extern "C" __attribute__((visibility("default"))) int ruf_debug_batchlog(unsigned long long *out)
+{
+  cudaMemcpyFromSymbol(out, g_batchlog, sizeof(unsigned long long) * 1024 * 8 * 16 * 4);
+  cudaMemset(nullptr, 0, 0);
+  void *p = nullptr;
+  cudaGetSymbolAddress(&p, g_batchlog);
+  cudaMemset(p, 0, sizeof(unsigned long long) * 1024 * 8 * 16 * 4);
+  return (int)cudaGetLastError();
+}
+#endif
+
+bool is_raster_kernel(const void *func)
+{
+  for (int i = 0; i < 8; ++i)
+    if (func == (const void *)raster_fn(i & 1, (i & 2) != 0, (i & 4) != 0)) return true;
+  return false;
+}
+
 cudaError_t check_kernel_image()
 {
   cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)ruf_raster_filter_kernel<1, false>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)raster_fn(1, false, false));
   if (e != cudaSuccess) return e;
   // opt in to > 48 KB of dynamic shared memory (per device: call once per context)
-  const void *fns[4] = {(const void *)ruf_raster_filter_kernel<0, false>, (const void *)ruf_raster_filter_kernel<1, false>,
-                        (const void *)ruf_raster_filter_kernel<0, true>, (const void *)ruf_raster_filter_kernel<1, true>};
-  for (const void *f : fns)
-    if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterDynSmem)) != cudaSuccess) return e;
+  for (int i = 0; i < 8; ++i)
+    if ((e = cudaFuncSetAttribute((const void *)raster_fn(i & 1, (i & 2) != 0, (i & 4) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kRasterDynSmem)) != cudaSuccess)
+      return e;
   return cudaSuccess;
 }
 
@@ -1808,14 +2054,17 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     if (e != cudaSuccess) fprintf(stderr, "[ruf] %s failed: %s\n", what, cudaGetErrorString(e));
     return e;
   };
-  err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_frames * d.ctr_stride * sizeof(uint32_t), s);
-  if (err != cudaSuccess) return err;
+  const long long n_ctr = (long long)n_frames * d.ctr_stride;
+  if (!d.fold_clear) {
+    err = cudaMemsetAsync(ws.ctr, 0, (size_t)n_ctr * sizeof(uint32_t), s);
+    if (err != cudaSuccess) return err;
+  }
   if (ev) cudaEventRecord(ev[0], s);
   {
     long long total = (long long)n_frames * (d.n_parts + 1) * 16;
     unsigned blocks = (unsigned)((total + 255) / 256);
     ruf_pose_kernel<<<blocks, 256, 0, s>>>(d_proj, d_view, d_part_model, d_lookat, m.part_aabb, d.n_parts, n_frames,
-                                           ws.mvp, ws.vis);
+                                           ws.mvp, ws.vis, ws.ctr, d.fold_clear ? n_ctr : 0LL);
     ++launches;
     if ((err = check("ruf_pose_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[1], s);
@@ -1841,14 +2090,20 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
   {
     // the depth image is first touched here: its upload may still be running under the pose / setup kernels
     if (depth_ready && (err = cudaStreamWaitEvent(s, depth_ready, 0)) != cudaSuccess) return err;
-    dim3 grid((unsigned)d.tiles_x, (unsigned)d.tiles_y, (unsigned)n_frames);
-    if (d.multipass) {
-      if (enc == 1) ruf_raster_filter_kernel<1, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
-      else ruf_raster_filter_kernel<0, true><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
-    } else {
-      if (enc == 1) ruf_raster_filter_kernel<1, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
-      else ruf_raster_filter_kernel<0, false><<<grid, kRasterThreads, kRasterDynSmem, s>>>(d, ws.big, ws.bins, ws.ctr, ws.tinfo, sp, fb, ws.status);
-    }
+    const bool cl = d.cluster_split != 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)d.tiles_x * (cl ? kClusterSplit : 1), (unsigned)d.tiles_y, (unsigned)n_frames);
+    cfg.blockDim = dim3(kRasterThreads);
+    cfg.dynamicSmemBytes = kRasterDynSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterSplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl ? 1 : 0;
+    if ((err = cudaLaunchKernelEx(&cfg, raster_fn(enc, d.multipass != 0, cl), d, (const TriRec *)ws.big, (const BinRec *)ws.bins,
+                                  (const uint32_t *)ws.ctr, (const uint4 *)ws.tinfo, sp, fb, ws.status)) != cudaSuccess)
+      return err;
     ++launches;
     if ((err = check("ruf_raster_filter_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[3], s);

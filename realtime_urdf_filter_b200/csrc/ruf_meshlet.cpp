@@ -112,6 +112,24 @@ void build_meshlets(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tr
   close();
 }
 
+void build_meshlet_sets(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts, float bg_z,
+                        int max_verts, int max_tris, int fine_tris, int max_parts, MeshletModel &out)
+{
+  build_meshlets(tri_xyz, tri_part, n_tris, n_parts, bg_z, max_verts, max_tris, max_parts, out);
+  out.n_primary = out.n_meshlets();
+  MeshletModel fine;
+  build_meshlets(tri_xyz, tri_part, n_tris, n_parts, bg_z, max_verts, fine_tris, max_parts, fine);
+  const uint32_t voff = (uint32_t)(out.verts.size() / 4), toff = (uint32_t)out.tris.size();
+  for (size_t m = 0; m < fine.n_meshlets(); ++m) {
+    out.hdr.push_back(fine.hdr[4 * m] + voff);
+    out.hdr.push_back(fine.hdr[4 * m + 1] + toff);
+    out.hdr.push_back(fine.hdr[4 * m + 2]);
+    out.hdr.push_back(fine.hdr[4 * m + 3]);
+  }
+  out.verts.insert(out.verts.end(), fine.verts.begin(), fine.verts.end());
+  out.tris.insert(out.tris.end(), fine.tris.begin(), fine.tris.end());
+}
+
 }  // namespace ruf
 
 // Diagnostics (CPU only): build the meshlets of a soup with the library's limits and expand them again.

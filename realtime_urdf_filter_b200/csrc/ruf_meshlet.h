@@ -23,10 +23,18 @@ struct MeshletModel {
   std::vector<float> part_aabb;  // kPartStrideHost floats per part: object-space min xyz, max xyz (inverted when the part is
                                  // empty), winding (+1 counter-clockwise seen from outside, -1 clockwise), pad
   size_t n_meshlets() const { return hdr.size() / 4; }
+  size_t n_primary = 0;          // build_meshlet_sets: headers [0, n_primary) are the throughput cut, the rest the fine cut
 };
 
 // bg_z: the background quad's z (float(0.99 * z_far)).  Triangles with tri_part >= n_parts are skipped.
 void build_meshlets(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts, float bg_z,
                     int max_verts, int max_tris, int max_parts, MeshletModel &out);
+
+// The model cut twice into the SAME arrays (one upload, one broadcast): headers [0, n_primary) with at most max_tris
+// triangles per meshlet (throughput: a setup CTA amortises its meshlet over a run of frames) followed by a second cut
+// with at most fine_tris (launches of one or a few frames: four times the CTAs, a quarter of the serial work each).
+// Both cuts hold every triangle and the background quad once; a launch uses one of them.
+void build_meshlet_sets(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts, float bg_z,
+                        int max_verts, int max_tris, int fine_tris, int max_parts, MeshletModel &out);
 
 }  // namespace ruf

@@ -461,10 +461,14 @@ def _pinned(shape, dtype):
     return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
 
 
-def test_single_frame_graph_path_with_pinned_buffers():
-    """ruf_filter with pinned host buffers runs as ONE captured CUDA graph (uploads, memset, kernels, read-backs).  Same
-    results as the staged pipeline and the oracle: first call (capture), same buffers again, other buffers (copy nodes
-    retargeted), other shader scalars / encoding / no mask (re-capture)."""
+@pytest.mark.parametrize("direct", ["7", "3", "0", "5"])
+def test_single_frame_graph_path_with_pinned_buffers(direct, monkeypatch):
+    """ruf_filter with pinned host buffers runs as ONE captured CUDA graph.  RUF_DIRECT = 7 (default): four kernel nodes, the
+    kernels read / write the caller's mapped buffers, the matrices and the status words themselves; 3: matrices and status
+    by copy nodes; 0: every buffer by copy nodes (uploads, memset, kernels, read-backs); 5: a mix.  Same results as the
+    staged pipeline and the oracle: first call (capture), same buffers again, other buffers (copy nodes / the raster
+    kernel's arguments retargeted), other shader scalars / encoding / no mask (re-capture)."""
+    monkeypatch.setenv("RUF_DIRECT", direct)
     sc = helpers.scene("pr2_small")
     proj, _, _ = sc.proj()
     lib = ruf.load()
