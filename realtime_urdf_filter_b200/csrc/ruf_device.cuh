@@ -111,7 +111,7 @@ constexpr int kMultiPassUnits = 128;            // MP variant: records up to thi
 #define RUF_CLUSTER_SPLIT 4
 #endif
 #ifndef RUF_CLUSTER_BATCH
-#define RUF_CLUSTER_BATCH 8
+#define RUF_CLUSTER_BATCH 32
 #endif
 constexpr int kClusterBatch = RUF_CLUSTER_BATCH;   // records per warp batch of that variant (divides 32)
 constexpr int kClusterSplit = RUF_CLUSTER_SPLIT;   // CTAs per tile of the low-latency raster variant (divides 32)
@@ -127,6 +127,8 @@ constexpr uint32_t kFlagBinOverflow = 2u;
 // per (frame, tile) word written by ruf_tile_info_kernel: x = flags, y = integer threshold (16UC1) or bits of the float
 // threshold (32FC1), z = bits of the tile's single window z
 constexpr uint32_t kTileFlat = 1u, kTileUndrawn = 2u;
+constexpr int kBgSkip = 1, kBgOnly = 2;
+constexpr int kBgSeedMax = 8;                   // records the background quad may clip into (two triangles, five planes)
 constexpr int kFlatMaxBig = 8;                  // big-list records a tile-info thread is willing to classify
 
 // One window-space triangle after setup: 48 bytes = 3 x 16 B (bulk-copy granularity).
@@ -172,6 +174,9 @@ struct Dims {
   int force_fpc;               // > 0: frames per setup CTA (testing aid, RUF_SETUP_FRAMES_FORCE); 0 = heuristic
   int multipass;               // raster kernel variant of this launch (ruf_raster_filter_kernel<ENC, MP, CL>)
   int fold_clear;              // the pose kernel clears the counter blocks (single-frame graph) instead of a memset before it
+  int bg_mode;                 // background quad (the model's last meshlet): 0 = set up by the setup kernel like every triangle;
+                               // kBgSkip = its records come from Workspace::bg_seed (fold_clear launches only), the setup kernel
+                               // leaves the last meshlet out; kBgOnly = pose + setup of the last meshlet alone (fills the seed)
   int cluster_split;           // low-latency variant: kClusterSplit CTAs (one thread-block cluster) share a tile
   float halfw, halfh, guard_x, guard_y;
 };
@@ -202,6 +207,7 @@ struct Workspace {
   BinRec *bins;          // [frame][tile][cap_tile] one record list per tile
   uint32_t *status;      // [0] sticky OR of all frame flags  [1] kept records (tile-info kernel), [2] (record, tile) pairs above kMaxUnits units (raster kernel) since the host last cleared them
   uint4 *tinfo;          // [frame][tile] ruf_tile_info_kernel -> ruf_raster_filter_kernel
+  const uint32_t *bg_seed;   // kBgSkip: word 0 = record count n, words 4.. = n TriRecs (the background quad's big-list records)
 };
 
 struct Model {

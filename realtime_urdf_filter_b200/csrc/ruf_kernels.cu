@@ -255,13 +255,25 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
 __global__ void __launch_bounds__(256)
 ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view, const double *__restrict__ part_model,
                 const double *__restrict__ lookat, const float *__restrict__ part_aabb, int n_parts, int n_frames,
-                float *__restrict__ mvp, uint8_t *__restrict__ vis, uint32_t *__restrict__ clear, long long n_clear)
+                float *__restrict__ mvp, uint8_t *__restrict__ vis, uint32_t *__restrict__ clear, long long n_clear,
+                const uint32_t *__restrict__ bg_seed, uint32_t *__restrict__ big_words, int ctr_stride, uint32_t cap_big)
 {
   __shared__ __align__(16) float s_m[16][16];
   const int rows = n_parts + 1;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  // single-frame graph: the frame's counter block is cleared here instead of by a memset node of its own
-  for (long long i = gid; i < n_clear; i += (long long)gridDim.x * blockDim.x) clear[i] = 0u;
+  // single-frame graph: the frame's counter block is cleared here instead of by a memset node of its own; with a seed,
+  // every frame's big list starts with the background quad's records (they depend on the projection matrix alone and
+  // were set up once: ruf_api.cu fill_bg_seed) instead of waiting for one warp of the setup kernel to clip the quad again
+  const uint32_t n_seed = bg_seed ? min(__ldg(bg_seed), min((uint32_t)kBgSeedMax, cap_big)) : 0u;
+  for (long long i = gid; i < n_clear; i += (long long)gridDim.x * blockDim.x)
+    clear[i] = (n_seed && i % ctr_stride == kCtrBig) ? n_seed : 0u;
+  if (n_seed) {
+    const long long per = (long long)n_seed * (sizeof(TriRec) / 4);
+    for (long long i = gid; i < per * n_frames; i += (long long)gridDim.x * blockDim.x) {
+      const long long f = i / per, w = i - f * per;
+      big_words[f * (long long)cap_big * (sizeof(TriRec) / 4) + w] = __ldg(bg_seed + 4 + w);
+    }
+  }
   const long long n_mats = (long long)n_frames * rows;
   float val = 0.0f;
   if (gid < n_mats * 16) {
@@ -1146,8 +1158,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   const int prow = tid >> 3, pcol = (tid & 7) * 8;
   // CL: this thread runs the fragment stage (its rows prow and prow + 32 belong to this CTA's band); warp-uniform
   const bool frag = CL == 1 || (uint32_t)(prow / (32 / CL)) == crank;
-  // records per warp batch: a full warp of 32 in the throughput variant; in the cluster-split variant the SMs are nearly
-  // empty and a lone warp needs ~0.6 us per round of 32 units, so the records are spread over more warps in smaller batches
+  // records per warp batch: a full warp of 32; RUF_CLUSTER_BATCH lets the cluster-split variant take smaller batches (a
+  // lone warp on a nearly empty SM needs ~0.5 us per round of 32 units, but also ~1.3 us per batch whatever its size:
+  // 8 / 16 / 32 measured within 1 us of each other on the single-frame call)
   constexpr uint32_t RB = CL > 1 ? (uint32_t)kClusterBatch : 32u;
   TL(0);
   // CL, single-frame graph: the last CTA of the launch writes the status words straight into the host's pinned copy and
@@ -2063,8 +2076,10 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
   {
     long long total = (long long)n_frames * (d.n_parts + 1) * 16;
     unsigned blocks = (unsigned)((total + 255) / 256);
+    const bool seed = d.fold_clear && d.bg_mode == kBgSkip && ws.bg_seed;
     ruf_pose_kernel<<<blocks, 256, 0, s>>>(d_proj, d_view, d_part_model, d_lookat, m.part_aabb, d.n_parts, n_frames,
-                                           ws.mvp, ws.vis, ws.ctr, d.fold_clear ? n_ctr : 0LL);
+                                           ws.mvp, ws.vis, ws.ctr, d.fold_clear ? n_ctr : 0LL, seed ? ws.bg_seed : nullptr,
+                                           reinterpret_cast<uint32_t *>(ws.big), d.ctr_stride, d.cap_big);
     ++launches;
     if ((err = check("ruf_pose_kernel")) != cudaSuccess) return err;
     if (ev) cudaEventRecord(ev[1], s);
@@ -2075,10 +2090,22 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
     int fpc = kSetupFrames;
     while (fpc > 1 && (long long)d.n_meshlets * ((n_frames + fpc - 1) / fpc) < 12000) fpc >>= 1;
     if (d.force_fpc > 0) fpc = d.force_fpc;
-    dim3 grid((unsigned)d.n_meshlets, (unsigned)((n_frames + fpc - 1) / fpc));
-    ruf_setup_bin_kernel<<<grid, kSetupThreads, 0, s>>>(m, ws.mvp, ws.vis, d, n_frames, fpc, ws.big, ws.bins, ws.ctr);
-    ++launches;
-    if ((err = check("ruf_setup_bin_kernel")) != cudaSuccess) return err;
+    // the background quad is the model's last meshlet
+    const bool seeded = d.fold_clear && d.bg_mode == kBgSkip && ws.bg_seed;
+    Model mk = m;
+    int nm = d.n_meshlets;
+    if (d.bg_mode == kBgOnly) { mk.meshlets += nm - 1; nm = 1; }
+    else if (seeded) nm -= 1;
+    if (nm > 0) {
+      dim3 grid((unsigned)nm, (unsigned)((n_frames + fpc - 1) / fpc));
+      ruf_setup_bin_kernel<<<grid, kSetupThreads, 0, s>>>(mk, ws.mvp, ws.vis, d, n_frames, fpc, ws.big, ws.bins, ws.ctr);
+      ++launches;
+      if ((err = check("ruf_setup_bin_kernel")) != cudaSuccess) return err;
+    }
+    if (d.bg_mode == kBgOnly) {
+      if (n_launches) *n_launches = launches;
+      return cudaGetLastError();
+    }
     const long long n_items = (long long)n_frames * d.ntiles;
     const unsigned tblocks = (unsigned)((n_items + 127) / 128);
     if (enc == 1) ruf_tile_info_kernel<1><<<tblocks, 128, 0, s>>>(d, n_frames, ws.big, ws.ctr, ws.status, sp, ws.tinfo);

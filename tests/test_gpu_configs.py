@@ -529,6 +529,42 @@ def test_single_frame_graph_path_with_pinned_buffers(direct, monkeypatch):
             ruf.host_free(p)
 
 
+@pytest.mark.parametrize("bg_cache", ["1", "0"])
+def test_single_frame_graph_background_seed_follows_the_projection_matrix(bg_cache, monkeypatch):
+    """The single-frame graph seeds the big list with the background quad's records, set up once per projection matrix
+    (ruf_api.cu fill_bg_seed).  A caller that changes camera_info between frames -- other focal lengths, other principal
+    point, back again -- gets the records of the matrix it passed: oracle-exact every time, with the cache and without."""
+    monkeypatch.setenv("RUF_BG_CACHE", bg_cache)
+    import dataclasses
+    sc = helpers.scene("pr2_small")
+    P2 = np.array(sc.P, dtype=np.float64, copy=True)
+    P2[0] *= 0.7; P2[5] *= 0.85; P2[2] += 31.0; P2[6] -= 17.0
+    sc2 = dataclasses.replace(sc, P=P2)
+    assert not np.array_equal(sc.proj()[0], sc2.proj()[0])
+    lib = ruf.load()
+    bufs = []
+    try:
+        d_in, p1 = _pinned((sc.height, sc.width), np.uint16)
+        d_out, p2 = _pinned((sc.height, sc.width), np.uint16)
+        m_out, p3 = _pinned((sc.height, sc.width), np.uint8)
+        bufs += [p1, p2, p3]
+        with ruf.Context(sc.width, sc.height) as ctx:
+            ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+            for s, k in ((sc, 0), (sc, 3), (sc2, 4), (sc2, 9), (sc, 6)):
+                fr = helpers.make_frame(s, k, "u16")
+                d_in[:] = fr["depth"]; d_out[:] = 0xFFFF; m_out[:] = 7
+                pr = np.ascontiguousarray(s.proj()[0], np.float64)
+                v, pm = np.ascontiguousarray(fr["view"], np.float64), np.ascontiguousarray(fr["pm"], np.float64)
+                rc = lib.ruf_filter(ctx._h, d_in.ctypes.data, ruf.ENC_U16_MM, pr.ctypes.data, v.ctypes.data, pm.ctypes.data,
+                                    sc.max_diff, sc.replace_value, d_out.ctypes.data, m_out.ctypes.data)
+                assert rc == 0, lib.ruf_last_error(ctx._h)
+                want_d, want_m, _ = helpers.oracle_filter(s, fr)
+                assert np.array_equal(d_out, want_d) and np.array_equal(m_out, want_m), (k, bg_cache)
+    finally:
+        for p in bufs:
+            ruf.host_free(p)
+
+
 @pytest.mark.parametrize("mode", ["0", "1", "auto"])
 def test_both_raster_kernel_variants_are_bit_exact(monkeypatch, mode):
     """ruf_raster_filter_kernel<ENC, MP>: records above kMaxUnits units either parked for the cooperative footprint walk
