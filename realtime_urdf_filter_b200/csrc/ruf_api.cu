@@ -929,7 +929,7 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
   RUF_CUDA(c, cudaStreamSynchronize(sk));
   c->stats = ruf_stats{};
   c->stats.frames = 1;
-  c->stats.kernel_launches = 4;
+  c->stats.kernel_launches = cluster ? 3 : 4;
   c->stats.h2d_bytes = (int64_t)(mat_bytes + img * es);
   c->stats.d2h_bytes = (int64_t)(img * es + (mask_out ? mb : 0));
   c->last_frames = 1;

@@ -1183,8 +1183,59 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
   // the big list = the background quad) were recognised by ruf_tile_info_kernel, which also took the virtual depth
   // through to_linear_depth and the threshold: what is left is a streaming pass (5 B/px for 16UC1) that never touches
   // shared memory, the record lists or a barrier.
+  //
+  // CL: there is no tile-info launch in front of this variant (on a launch of one frame a kernel boundary costs more
+  // than the kernel saves): the cluster's CTAs do for their tile what a thread of ruf_tile_info_kernel does -- same
+  // tests, same expressions, one lane per big-list record -- and rank 0 folds the overflow flags into the status words.
+  __shared__ uint32_t s_ti[4];
   {
-    const uint4 ti = __ldg(tinfo + (size_t)frame * d.ntiles + tile);
+    uint4 ti;
+    if (CL == 1) {
+      ti = __ldg(tinfo + (size_t)frame * d.ntiles + tile);
+    } else {
+      const uint32_t *ctr0 = ctr_all + (size_t)frame * d.ctr_stride;
+      const uint2 nfb0 = __ldg(reinterpret_cast<const uint2 *>(ctr0 + kCtrWords) + tile);
+      const uint32_t nbig0 = min(__ldg(ctr0 + kCtrBig), d.cap_big);
+      if (crank == 0u && tid == 0) {
+        uint32_t flags = (nfb0.x + nfb0.y > d.cap_tile) ? kFlagBinOverflow : 0u;
+        if (tile == 0) {
+          flags |= __ldg(ctr0 + kCtrFlags);
+          atomicAdd(status + 1, __ldg(ctr0 + kCtrKept));
+        }
+        if (flags) atomicOr(status, flags);
+      }
+      ti = make_uint4(0u, 0u, 0u, 0u);
+      if (nfb0.x + nfb0.y == 0u && nbig0 <= (uint32_t)kFlatMaxBig) {       // CTA-uniform
+        if (warp == 0) {
+          uint32_t cls = 0;
+          float zf = 1.0f;                                                 // glClear depth
+          if ((uint32_t)lane < nbig0) {
+            const TriRec r = load_rec_global(big_all + (size_t)frame * d.cap_big + lane);
+            float zc = 0.0f;
+            cls = classify_big_record(r, tile_x0, tile_y0, &zc);
+            if (cls == 3u) zf = fminf(zf, zc);
+          }
+          const bool mixed = __any_sync(0xffffffffu, cls == 1u || cls == 2u);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) zf = fminf(zf, __shfl_xor_sync(0xffffffffu, zf, o));
+          if (lane == 0) {
+            uint32_t fl = 0, th = 0;
+            if (!mixed) {
+              fl = kTileFlat;
+              const float zt = zf;
+              if (zt == 1.0f) fl |= kTileUndrawn;
+              else {
+                const float thr = (sp.k1 / (zt - sp.k2)) - sp.max_diff;
+                th = (ENC == 1) ? (uint32_t)u16_threshold(thr) : __float_as_uint(thr);
+              }
+            }
+            s_ti[0] = fl; s_ti[1] = th; s_ti[2] = __float_as_uint(zf);
+          }
+        }
+        __syncthreads();
+        ti = make_uint4(s_ti[0], s_ti[1], s_ti[2], 0u);
+      }
+    }
     if (ti.x & kTileFlat) {
       const bool drawn = !(ti.x & kTileUndrawn);
       const uint32_t repl_u16 = f32_to_u16(sp.replace_value);
@@ -2106,12 +2157,14 @@ cudaError_t launch_frames(const Dims &d, const Model &m, const Workspace &ws, in
       if (n_launches) *n_launches = launches;
       return cudaGetLastError();
     }
-    const long long n_items = (long long)n_frames * d.ntiles;
-    const unsigned tblocks = (unsigned)((n_items + 127) / 128);
-    if (enc == 1) ruf_tile_info_kernel<1><<<tblocks, 128, 0, s>>>(d, n_frames, ws.big, ws.ctr, ws.status, sp, ws.tinfo);
-    else ruf_tile_info_kernel<0><<<tblocks, 128, 0, s>>>(d, n_frames, ws.big, ws.ctr, ws.status, sp, ws.tinfo);
-    ++launches;
-    if ((err = check("ruf_tile_info_kernel")) != cudaSuccess) return err;
+    if (!d.cluster_split) {        // (the cluster-split raster variant does this for itself)
+      const long long n_items = (long long)n_frames * d.ntiles;
+      const unsigned tblocks = (unsigned)((n_items + 127) / 128);
+      if (enc == 1) ruf_tile_info_kernel<1><<<tblocks, 128, 0, s>>>(d, n_frames, ws.big, ws.ctr, ws.status, sp, ws.tinfo);
+      else ruf_tile_info_kernel<0><<<tblocks, 128, 0, s>>>(d, n_frames, ws.big, ws.ctr, ws.status, sp, ws.tinfo);
+      ++launches;
+      if ((err = check("ruf_tile_info_kernel")) != cudaSuccess) return err;
+    }
     if (ev) cudaEventRecord(ev[2], s);
   }
   {

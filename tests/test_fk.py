@@ -73,7 +73,7 @@ def test_device_fk_bit_exact_and_filter_through_fk():
         ctx.filter_batch_device_fk(len(ks), d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_q.data_ptr(), tx, ty,
                                    sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
         ctx.sync()
-        assert ctx.stats()["kernel_launches"] == 6
+        assert ctx.stats()["kernel_launches"] in (5, 6)      # 2 FK kernels + 3 (small launch: cluster-split raster variant) or 4
     for i, fr in enumerate(frames):
         want_d, want_m, _ = helpers.oracle_filter(sc, fr)
         assert np.array_equal(d_out[i].cpu().numpy().view(np.uint16), want_d)

@@ -313,7 +313,7 @@ def test_sliced_two_stream_launch_matches_single_launch(monkeypatch):
             ctx.sync()
             launches = ctx.stats()["kernel_launches"]
         outs.append((d_out.cpu().numpy().view(np.uint16), d_mask.cpu().numpy(), launches))
-    assert outs[0][2] == 12 and outs[1][2] == 4         # 3 slices x 4 kernels vs one launch sequence
+    assert outs[1][2] in (3, 4) and outs[0][2] == 3 * outs[1][2]     # 3 slices x 4 kernels vs one launch sequence (3 with RUF_CLUSTER=1)
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     # and a few frames against the oracle
     for k in (0, 255, 256, 529):
@@ -503,7 +503,7 @@ def test_single_frame_graph_path_with_pinned_buffers(direct, monkeypatch):
                 d_out[:] = 0xFFFF
                 m_out[:] = 7
                 st = call(d_in, d_out, m_out, fr, ruf.ENC_U16_MM, sc.max_diff)
-                assert st["kernel_launches"] == 4 and st["d2h_bytes"] == sc.width * sc.height * 3
+                assert st["kernel_launches"] == 3 and st["d2h_bytes"] == sc.width * sc.height * 3
                 want_d, want_m, _ = helpers.oracle_filter(sc, fr)
                 assert np.array_equal(d_out, want_d) and np.array_equal(m_out, want_m)
             # other threshold -> re-captured graph; then no mask; then 32FC1
@@ -629,7 +629,7 @@ def test_device_batch_larger_than_the_workspace_budget_runs_as_sub_batches():
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
     launches = int(res.stdout.split("LAUNCHES")[1].split()[0])
-    assert launches >= 4 * 3, launches          # 11 frames in sub-batches of at most 3-4 frames: at least 3 launch sequences
+    assert launches >= 3 * 3, launches          # 11 frames in sub-batches of at most 3-4 frames: at least 3 launch sequences
 
 
 def test_copy_ceiling_call_moves_the_same_bytes():

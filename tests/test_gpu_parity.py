@@ -56,7 +56,7 @@ def test_zbuf_bit_exact_device_batch():
                                 d_mask.data_ptr(), d_z.data_ptr())
         ctx.sync()
         st = ctx.stats()
-    assert st["kernel_launches"] == 4 and st["visible_tris"] > 0
+    assert st["kernel_launches"] in (3, 4) and st["visible_tris"] > 0     # 3: small launch, cluster-split raster variant (no tile-info kernel)
     z = d_z.cpu().numpy()
     for i, fr in enumerate(frames):
         want_d, want_m, want_z = helpers.oracle_filter(sc, fr)
