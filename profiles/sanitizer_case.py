@@ -64,4 +64,5 @@ with ruf.Context(sc.width, sc.height) as ctx:
     assert np.array_equal(np.unpackbits(bits, axis=-1, bitorder="little") * np.uint8(255), want_m)
 for p in ptrs:
     ruf.host_free(p)
-print("graph + packed mask ok, RUF_MULTIPASS =", os.environ.get("RUF_MULTIPASS", "auto"))
+print("graph + packed mask ok, RUF_MULTIPASS =", os.environ.get("RUF_MULTIPASS", "auto"), "RUF_CLUSTER =", os.environ.get("RUF_CLUSTER", "auto"),
+      "RUF_DIRECT =", os.environ.get("RUF_DIRECT", "7"))

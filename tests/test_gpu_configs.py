@@ -388,6 +388,43 @@ def test_million_frames_stay_identical():
     assert torch.equal(d_out, first_d) and torch.equal(d_mask, first_m)
 
 
+@pytest.mark.parametrize("n", [5, 12])
+def test_small_launch_soak_cluster_split_variant(n, monkeypatch):
+    """Soak of what small launches get (cluster-split raster variant: four CTAs per tile, DSMEM merge, cluster barriers;
+    fine meshlet cut): 20000 launches of n frames -- several waves of clusters per launch --, every 1000th compared with
+    the first, the first with the oracle."""
+    import torch
+    monkeypatch.setenv("RUF_CLUSTER", "1")
+    monkeypatch.setenv("RUF_FINE_MESHLETS", "1")
+    sc = helpers.scene("pr2")
+    proj, _, _ = sc.proj()
+    frs = [helpers.make_frame(sc, k, "u16", nthreads=8) for k in range(n)]
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_in = t(np.stack([f["depth"] for f in frs]).view(np.int16))
+    d_proj, d_view, d_pm = t(proj), t(np.stack([f["view"] for f in frs])), t(np.stack([f["pm"] for f in frs]))
+    d_out = torch.zeros_like(d_in)
+    d_mask = torch.zeros(d_in.shape, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        args = (n, d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)
+        ctx.filter_batch_device(*args)
+        ctx.sync()
+        first_d, first_m = d_out.clone(), d_mask.clone()
+        for i in (0, n - 1):
+            want_d, want_m, _ = helpers.oracle_filter(sc, frs[i], nthreads=8)
+            assert np.array_equal(first_d[i].cpu().numpy().view(np.uint16), want_d) and np.array_equal(first_m[i].cpu().numpy(), want_m)
+        for it in range(20000):
+            ctx.filter_batch_device(*args)
+            if it % 1000 == 999:
+                ctx.sync()
+                assert torch.equal(d_out, first_d) and torch.equal(d_mask, first_m), f"differs after {it + 1} launches"
+        ctx.sync()
+    assert torch.equal(d_out, first_d) and torch.equal(d_mask, first_m)
+
+
 @pytest.mark.parametrize("enc", ["u16", "f32"])
 def test_sensor_values_straddling_the_threshold(enc):
     """Every pixel's sensor depth sits within a few units of its own `virtual - threshold`: the compare of

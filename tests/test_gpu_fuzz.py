@@ -1,7 +1,8 @@
 """Seeded random triangle soups through the CUDA path against the oracle, bit for bit (depth, mask AND the raw z-buffer):
 what no hand-made scene covers -- slivers, huge and sub-pixel triangles, degenerate and non-finite vertices, triangles
 through the near plane and far outside the guard band, parts whose matrices mirror or shear, image sizes that are not
-multiples of anything, both encodings, both instantiations of the raster kernel (RUF_MULTIPASS)."""
+multiples of anything, both encodings, all four kinds of instantiations of the raster kernel (RUF_MULTIPASS x
+RUF_CLUSTER: the automatic choice would give these small launches the cluster-split variant only)."""
 import numpy as np
 import pytest
 
@@ -59,10 +60,13 @@ def _part_models(rng, n_parts):
     return pm
 
 
+@pytest.mark.parametrize("cluster", ["0", "1"])
 @pytest.mark.parametrize("mode", ["0", "1"])
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
-def test_random_soups_match_the_oracle(monkeypatch, mode, seed):
+def test_random_soups_match_the_oracle(monkeypatch, mode, seed, cluster):
     monkeypatch.setenv("RUF_MULTIPASS", mode)
+    monkeypatch.setenv("RUF_CLUSTER", cluster)
+    monkeypatch.setenv("RUF_FINE_MESHLETS", cluster)
     rng = np.random.default_rng(1000 + seed)
     W, H = [(640, 480), (200, 151), (333, 77), (96, 200), (1280, 96), (64, 64)][seed - 1]
     n_parts = int(rng.integers(3, 14))

@@ -8,6 +8,15 @@ import realtime_urdf_filter_b200 as ruf
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["throughput", "small-launch"])
+def raster_variant(request, monkeypatch):
+    """Every test of this file runs twice: with the throughput kernels (one CTA per tile, coarse meshlet cut) and with what
+    small launches get by default (cluster-split raster variant, fine meshlet cut).  Same bits either way."""
+    v = "0" if request.param == "throughput" else "1"
+    monkeypatch.setenv("RUF_CLUSTER", v)
+    monkeypatch.setenv("RUF_FINE_MESHLETS", v)
+
+
 def _ctx(sc):
     ctx = ruf.Context(sc.width, sc.height)
     ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
