@@ -102,7 +102,7 @@ constexpr int kMeshVerts = RUF_MESH_VERTS;
 constexpr int kMeshTris = RUF_MESH_TRIS;
 constexpr int kMeshParts = 32;
 constexpr int kMeshTrisFine = RUF_SETUP_THREADS;  // the fine cut of the model: one triangle per setup thread
-constexpr int kFineMaxCtas = 2 * 148;             // (frames x meshlets) of a launch up to which the fine cut is used
+constexpr int kFineMaxCtas = 148;                 // (frames x meshlets) of a launch up to which the fine cut is used (one frame of a 90k model)
 constexpr int kSetupSlots = (kMeshTris + kSetupThreads - 1) / kSetupThreads;   // triangles per thread
 constexpr int kSetupFrames = RUF_SETUP_FRAMES;  // frames a setup CTA loops over with its meshlet in registers
 static_assert(kMeshVerts <= 1024 && kMeshTris <= 1023, "meshlet indices are packed in 10 bits");
@@ -115,7 +115,8 @@ constexpr int kMultiPassUnits = 128;            // MP variant: records up to thi
 #endif
 constexpr int kClusterBatch = RUF_CLUSTER_BATCH;   // records per warp batch of that variant (divides 32)
 constexpr int kClusterSplit = RUF_CLUSTER_SPLIT;   // CTAs per tile of the low-latency raster variant (divides 32)
-constexpr int kClusterMaxTiles = 1024;           // (frames x tiles) of a launch up to which the cluster-split variant is used
+constexpr int kClusterMaxTiles = 384;            // (frames x tiles) of a launch up to which the cluster-split variant is used: measured
+                                                 // at 640x480 (profiles/small_batch_probe.py) it wins up to 4 frames per launch, loses from 8
 constexpr int kWideCap = 16;                    // wide records a raster CTA parks for its cooperative final phase
 constexpr int kMaxTiles = 4096;
 constexpr int kPartStride = 8;                  // floats per part in Model::part_aabb

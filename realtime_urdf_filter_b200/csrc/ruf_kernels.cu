@@ -210,8 +210,13 @@ __device__ __forceinline__ void push_big(const TriRec &r, const Dims &d, TriRec 
   else atomicOr(&ctr[kCtrFlags], kFlagBigOverflow);
 }
 
-__device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, TriRec *big, uint32_t *ctr)
+// (out of line, and it takes the few fields it needs BY VALUE: a reference to the kernel's Dims parameter would make every
+// thread of the setup kernel copy the whole structure from the constant bank to its stack at kernel start)
+__device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, float halfw, float halfh, float guard_x, float guard_y, int W,
+                                           int H, uint32_t cap_big, TriRec *big, uint32_t *ctr)
 {
+  Dims d{};
+  d.halfw = halfw; d.halfh = halfh; d.guard_x = guard_x; d.guard_y = guard_y; d.W = W; d.H = H; d.cap_big = cap_big;
   V4 poly[kMaxPoly], tmp[kMaxPoly];
   poly[0] = p0; poly[1] = p1; poly[2] = p2;
   int n = 3;
@@ -252,7 +257,7 @@ __device__ __noinline__ void clip_and_emit(V4 p0, V4 p1, V4 p2, const Dims &d, T
 // would be rejected one by one by the setup kernel, so vis[frame][part] = 0 lets it skip the part's
 // vertices wholesale.  8 threads per matrix.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view, const double *__restrict__ part_model,
                 const double *__restrict__ lookat, const float *__restrict__ part_aabb, int n_parts, int n_frames,
                 float *__restrict__ mvp, uint8_t *__restrict__ vis, uint32_t *__restrict__ clear, long long n_clear,
@@ -261,6 +266,27 @@ ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view
   __shared__ __align__(16) float s_m[16][16];
   const int rows = n_parts + 1;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_mats = (long long)n_frames * rows;
+  // The block's inputs -- its 16 part matrices with the view matrices of their frames, the projection matrix, LookAt --
+  // are requested first, at most three loads per thread, all in flight together, and reach the arithmetic through shared
+  // memory: in the single-frame graph they are read straight from the host's pinned block, and a thread that fetched
+  // its 36 operands one after the other (32 registers) paid several PCIe round trips.  Same products in the same order.
+  __shared__ double s_in[16][16], s_V[16][16], s_P[16], s_L[16];
+  double r_in = 0.0, r_v = 0.0, r_pl = 0.0;
+  {
+    const int t = threadIdx.x;
+    const long long matl = (long long)blockIdx.x * 16 + (t >> 4);
+    if (matl < n_mats) {
+      const int p = (int)(matl % rows);
+      const long long f = matl / rows;
+      if (p < n_parts) {
+        r_in = part_model[16 * (f * n_parts + p) + (t & 15)];
+        r_v = view[16 * f + (t & 15)];
+      }
+    }
+    if (t < 16) r_pl = proj[t];
+    else if (t < 32) r_pl = lookat[t & 15];
+  }
   // single-frame graph: the frame's counter block is cleared here instead of by a memset node of its own; with a seed,
   // every frame's big list starts with the background quad's records (they depend on the projection matrix alone and
   // were set up once: ruf_api.cu fill_bg_seed) instead of waiting for one warp of the setup kernel to clip the quad again
@@ -274,28 +300,34 @@ ruf_pose_kernel(const double *__restrict__ proj, const double *__restrict__ view
       big_words[f * (long long)cap_big * (sizeof(TriRec) / 4) + w] = __ldg(bg_seed + 4 + w);
     }
   }
-  const long long n_mats = (long long)n_frames * rows;
+  {
+    const int t = threadIdx.x;
+    s_in[t >> 4][t & 15] = r_in;
+    s_V[t >> 4][t & 15] = r_v;
+    if (t < 16) s_P[t] = r_pl;
+    else if (t < 32) s_L[t & 15] = r_pl;
+  }
+  __syncthreads();
   float val = 0.0f;
   if (gid < n_mats * 16) {
     const int e = (int)(gid & 15);
     const long long mat = gid >> 4;
     const int p = (int)(mat % rows);
-    const int f = (int)(mat / rows);
     const int r = e & 3, c = e >> 2;
     double s;
     if (p == n_parts) {
       s = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s += proj[k * 4 + r] * lookat[c * 4 + k];
+      for (int k = 0; k < 4; ++k) s += s_P[k * 4 + r] * s_L[c * 4 + k];
     } else {
-      const double *V = view + 16 * (long long)f;
-      const double *M = part_model + 16 * ((long long)f * n_parts + p);
+      const double *V = s_V[threadIdx.x >> 4];
+      const double *M = s_in[threadIdx.x >> 4];
       double pv[4];   // row r of P*V
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         double a = 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a += proj[j * 4 + r] * V[k * 4 + j];
+        for (int j = 0; j < 4; ++j) a += s_P[j * 4 + r] * V[k * 4 + j];
         pv[k] = a;
       }
       s = 0.0;
@@ -584,7 +616,7 @@ ruf_setup_bin_kernel(Model m, const float *__restrict__ mvp_all, const uint8_t *
         const float4 *M = reinterpret_cast<const float4 *>(&s_mvp[mbuf][16 * __float_as_uint(qa.w)]);
         const float4 c0 = M[0], c1 = M[1], c2 = M[2], c3 = M[3];
         clip_and_emit(xform(c0, c1, c2, c3, qa.x, qa.y, qa.z), xform(c0, c1, c2, c3, qb.x, qb.y, qb.z),
-                      xform(c0, c1, c2, c3, qc.x, qc.y, qc.z), d, big, ctr);
+                      xform(c0, c1, c2, c3, qc.x, qc.y, qc.z), d.halfw, d.halfh, d.guard_x, d.guard_y, d.W, d.H, d.cap_big, big, ctr);
       }
 
       TL1(5);
