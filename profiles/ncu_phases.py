@@ -37,7 +37,7 @@ def main(rep, which, lib=None):
                  ("unit loop", find("for (int base = 0; base < items; base += 32) {", k)), ("last barrier, z reload", find("every record of the tile has been rasterised", k) - 4),
                  ("big list: apply", find("per-frame big list, part 2", k)), ("fragment stage", find("---- fused fragment stage", k)),
                  ("(after)", find("Forward kinematics on the device", k))]
-        kernel, mangled = "ruf_raster_filter", "ruf_raster_filter_kernelILi1"
+        kernel, mangled = "ruf_raster_filter", "ruf_raster_filter_kernelILi1ELb0ELi1"     # the 16UC1 throughput instantiation
     else:
         k = find("ruf_setup_bin_kernel(Model m")
         marks = [("inlined helpers", 1), ("xform", find("__device__ __forceinline__ V4 xform")), ("clip helpers", find("__device__ __forceinline__ float plane_dist")),

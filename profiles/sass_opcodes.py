@@ -24,7 +24,8 @@ for line in sass.splitlines():
     if m and kern:
         ops[kern][m.group(1) + m.group(2)] += 1
 print(f"# {os.path.relpath(lib, ROOT)}: cubin architectures {arch}")
-MARK = ("UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "MATCH", "ATOMS", "ATOMG", "REDG", "RED", "PRMT", "VIMNMX3", "BAR", "SHFL")
+MARK = ("UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "MATCH", "ATOMS", "ATOMG", "REDG", "RED", "PRMT", "VIMNMX3", "BAR", "SHFL",
+        "UCGABAR_ARV", "UCGABAR_WAIT", "CGAERRBAR")      # UCGABAR_*: barrier.cluster of the cluster-split raster variant
 for k, c in sorted(ops.items(), key=lambda kv: -sum(kv[1].values())):
     tot = sum(c.values())
     print(f"\n== {k}: {tot} SASS instructions")
