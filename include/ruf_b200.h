@@ -212,8 +212,11 @@ RUF_API int ruf_group_filter_batch_host(ruf_group *grp, int n_frames, const void
                                         const double *view, const double *part_model, float max_diff,
                                         float replace_value, void *depth_out, uint8_t *mask_out, int frames_per_chunk);
 
-RUF_API int ruf_host_alloc(void **ptr, size_t bytes);   /* cudaHostAlloc (pinned) */
+RUF_API int ruf_host_alloc(void **ptr, size_t bytes);   /* cudaHostAlloc (pinned, mapped) */
 RUF_API int ruf_host_free(void *ptr);
+/* 1 when p lies in page-locked host memory known to the CUDA runtime (ruf_host_alloc, cudaHostAlloc, cudaHostRegister):
+ * ruf_filter takes its single-frame graph path for such buffers (see ruf_filter).  0 otherwise. */
+RUF_API int ruf_host_is_pinned(const void *p);
 
 /* Counters of the most recent completed call (debug / bench bookkeeping). */
 typedef struct ruf_stats {

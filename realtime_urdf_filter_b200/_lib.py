@@ -80,6 +80,7 @@ SIGNATURES = {
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ruf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ruf_host_free": (C.c_int, [C.c_void_p]),
+    "ruf_host_is_pinned": (C.c_int, [C.c_void_p]),
     "ruf_get_stats": (C.c_int, [C.c_void_p, C.POINTER(RufStats)]),
     "ruf_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "ruf_get_stage_times": (C.c_int, [C.c_void_p, _c_double_p, C.POINTER(C.c_int64), C.c_int]),

@@ -1118,6 +1118,7 @@ int ruf_host_free(void *ptr)
   if (ptr) cudaFreeHost(ptr);
   return RUF_OK;
 }
+int ruf_host_is_pinned(const void *p) { return p && is_pinned_host(p) ? 1 : 0; }
 
 int ruf_get_stats(ruf_context *c, ruf_stats *out)
 {

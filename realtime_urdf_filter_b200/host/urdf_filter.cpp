@@ -33,14 +33,17 @@ RealtimeURDFFilter::RealtimeURDFFilter(NodeHandle &nh, int argc, char **argv)
   // not a parameter of the reference: read the mask back as 1 bit per pixel and expand it to MONO8 here (saves 0.875
   // byte per pixel of device -> host traffic; subscribers see the same 0 / 255 image)
   if (!nh_.getParam("packed_mask_readback", packed_mask_)) packed_mask_ = false;
+  if (!nh_.getParam("pinned_staging", pinned_staging_)) pinned_staging_ = true;
   if (!nh_.getParam("filter_replace_value", filter_replace_value_)) filter_replace_value_ = 0;             // :110
   logf(LOG_INFO, "using filter replace value %f", filter_replace_value_);
 }
 
 RealtimeURDFFilter::~RealtimeURDFFilter()
 {
-  std::free(masked_depth_);
-  std::free(mask_);
+  ruf_host_free(masked_depth_);
+  ruf_host_free(mask_);
+  ruf_host_free(pin_in_);
+  ruf_host_free(pin_out_);
   for (URDFRenderer *r : renderers_) delete r;
   if (ctx_) ruf_destroy(ctx_);
 }
@@ -117,10 +120,21 @@ void RealtimeURDFFilter::initGL()
   loadModels();                                                                                            // :423
   if (renderers_.empty()) throw std::runtime_error("Could not load any models for filtering!");           // :426-427
   upload_models();
-  std::free(masked_depth_);
-  std::free(mask_);
-  masked_depth_ = (float *)std::malloc((size_t)width_ * height_ * sizeof(float));                          // :433-435
-  mask_ = (unsigned char *)std::malloc((size_t)width_ * height_);
+  // the read-back buffers of :433-435, page-locked: ruf_filter writes them from the device without a staging copy
+  ruf_host_free(masked_depth_);
+  ruf_host_free(mask_);
+  ruf_host_free(pin_in_);
+  ruf_host_free(pin_out_);
+  masked_depth_ = nullptr; mask_ = nullptr; pin_in_ = pin_out_ = nullptr;
+  pin_bytes_ = (size_t)width_ * height_ * sizeof(float);
+  void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
+  if (ruf_host_alloc(&p0, pin_bytes_) != RUF_OK || ruf_host_alloc(&p1, (size_t)width_ * height_) != RUF_OK ||
+      ruf_host_alloc(&p2, pin_bytes_) != RUF_OK || ruf_host_alloc(&p3, pin_bytes_) != RUF_OK)
+    throw std::runtime_error("Could not allocate the read-back buffers");
+  masked_depth_ = (float *)p0;
+  mask_ = (unsigned char *)p1;
+  pin_in_ = (unsigned char *)p2;
+  pin_out_ = (unsigned char *)p3;
 }
 
 void RealtimeURDFFilter::getProjectionMatrix(const CameraInfoConstPtr &info, double *glTf)
@@ -159,8 +173,17 @@ int RealtimeURDFFilter::run_device(const void *depth_in, int enc, const double *
     mask_bits_.resize((size_t)width_ * height_ / 8);
     mask_dst = mask_bits_.data();
   }
-  int rc = ruf_filter(ctx_, depth_in, enc, P, view, models.data(), (float)depth_distance_threshold_,
-                      (float)filter_replace_value_, depth_out, mask_dst);                                  // :625-631, :729-735
+  // pageable caller buffers (a message's data vector) go through the facade's page-locked staging
+  const size_t img_bytes = (size_t)width_ * height_ * (enc == RUF_ENC_F32_M ? 4 : 2);
+  const void *src = depth_in;
+  void *dst = depth_out;
+  if (pinned_staging_ && pin_in_ && img_bytes <= pin_bytes_) {
+    if (!ruf_host_is_pinned(depth_in)) { std::memcpy(pin_in_, depth_in, img_bytes); src = pin_in_; }
+    if (!ruf_host_is_pinned(depth_out)) dst = pin_out_;
+  }
+  int rc = ruf_filter(ctx_, src, enc, P, view, models.data(), (float)depth_distance_threshold_,
+                      (float)filter_replace_value_, dst, mask_dst);                                        // :625-631, :729-735
+  if (rc == RUF_OK && dst != depth_out) std::memcpy(depth_out, dst, img_bytes);
   if (rc == RUF_OK && packed_mask_ && mask_out) {
     // bit i of byte k = pixel 8 k + i -> the MONO8 bytes the reference reads back (GL_UNSIGNED_BYTE, :731-735)
     const size_t n = mask_bits_.size();

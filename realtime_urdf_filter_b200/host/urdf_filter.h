@@ -93,6 +93,13 @@ class RealtimeURDFFilter {
   void upload_models();
   const unsigned char *staged_buffer_ = nullptr;
   size_t model_parts_ = 0;
+  // page-locked staging of the facade (ruf_host_alloc): ruf_filter runs its single-frame graph -- three kernels that read
+  // and write the host buffers themselves -- only for pinned buffers, and a ROS message's data is a pageable vector.  One
+  // memcpy into / out of these is cheaper than the pageable copies the runtime would stage (`pinned_staging` parameter,
+  // default true; buffers that are pinned already are passed through).
+  bool pinned_staging_ = true;
+  unsigned char *pin_in_ = nullptr, *pin_out_ = nullptr;
+  size_t pin_bytes_ = 0;
 };
 
 // ---- the second caller of filter(): OpenNITrackerLoopback::runOnce (src/urdf_filtered_tracker.cpp:180-252) ----

@@ -15,8 +15,8 @@ PARAMS = {"fixed_frame": "/world", "camera_frame": "/camera_rgb_optical_frame",
 MODELS = [{"model": "robot_description", "tf_prefix": "/EXAMPLE", "geometry_type": "visual", "scale": 1.0}]
 
 
-def make_node(sc):
-    n = facade.FilterNode(PARAMS, MODELS, camera_offset=((0, 0, 0), (0, 0, 0, 1)))
+def make_node(sc, **extra):
+    n = facade.FilterNode(dict(PARAMS, **extra), MODELS, camera_offset=((0, 0, 0), (0, 0, 0, 1)))
     Ts = sc.link_poses(0)
     n.set_tf("/world", (0, 0, 0, 1), (0, 0, 0))
     for ln, T in zip(sc.links, Ts):
@@ -26,12 +26,15 @@ def make_node(sc):
     return n
 
 
+@pytest.mark.parametrize("pinned_staging", [True, False])
 @pytest.mark.parametrize("enc", ["u16", "f32"])
-def test_filter_callback_matches_oracle(enc):
+def test_filter_callback_matches_oracle(enc, pinned_staging):
+    """pinned_staging (default): the message's pageable data goes through the facade's page-locked staging buffers, so that
+    ruf_filter runs its single-frame graph; off: the pageable pointers go straight to ruf_filter (staged pipeline)."""
     sc = helpers.scene("example")
     fr = helpers.make_frame(sc, 0, enc)
     want_d, want_m, _ = helpers.oracle_filter(sc, fr)
-    with make_node(sc) as n:
+    with make_node(sc, pinned_staging=pinned_staging) as n:
         n.callback(fr["depth"], sc.P, stamp=1.0)
         assert n.published() == (1, 1)
         c = n.counts()
