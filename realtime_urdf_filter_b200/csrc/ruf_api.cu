@@ -89,6 +89,9 @@ struct ruf_context {
   double bg_proj[16] = {0};
   int bg_state = 0;                  // 0 = not filled, 1 = valid for bg_proj, -1 = not usable (more records than kBgSeedMax)
   bool bg_cache = true;              // RUF_BG_CACHE=0 turns it off
+  // page-locked staging of ruf_filter for callers with pageable buffers (RUF_HOST_STAGING=0 turns it off)
+  void *hs_in = nullptr, *hs_out = nullptr, *hs_mask = nullptr;
+  bool host_staging = true;
   int direct_mode = 7;               // single-frame graph: zero-copy bits (1 outputs, 2 input, 4 matrices + status), RUF_DIRECT
   uint32_t *launch_host_status = nullptr;   // set around the capture of the single-frame graph: FrameBuffers::host_status
   int fine_mode = -1;                // fine meshlet cut for small launches: -1 automatic, 0 / 1 forced (RUF_FINE_MESHLETS)
@@ -374,6 +377,7 @@ int ruf_create(ruf_context **out, int device, int width, int height, double z_ne
   if (const char *e = getenv("RUF_FINE_MESHLETS")) c->fine_mode = atoi(e) ? 1 : 0;
   if (const char *e = getenv("RUF_DIRECT")) c->direct_mode = atoi(e) & 7;
   if (const char *e = getenv("RUF_BG_CACHE")) c->bg_cache = atoi(e) != 0;
+  if (const char *e = getenv("RUF_HOST_STAGING")) c->host_staging = atoi(e) != 0;
   if (const char *e2 = getenv("RUF_SLICE_FRAMES")) {    // tuning aid
     const int v = atoi(e2);
     if (v >= 0 && v <= 65535) c->slice_frames = v;
@@ -422,6 +426,7 @@ int ruf_destroy(ruf_context *c)
   cudaFree(c->meshlets); cudaFree(c->mverts); cudaFree(c->mtris); cudaFree(c->part_aabb);
   cudaFree(c->kin_blob); cudaFree(c->fk_links); cudaFree(c->fk_pm); cudaFree(c->fk_view);
   cudaFree(c->ws.status); cudaFree(c->d_lookat); cudaFree(c->bg_seed);
+  cudaFreeHost(c->hs_in); cudaFreeHost(c->hs_out); cudaFreeHost(c->hs_mask);
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
@@ -763,10 +768,13 @@ static int fill_bg_seed(ruf_context *c, const double *proj, double *hm, size_t m
   FrameBuffers fb{};
   cudaError_t e = launch_frames(d, m, c->ws, 1, dm, dm + 16, dm + 32, c->d_lookat, RUF_ENC_U16_MM, sp, fb, sk, nullptr, nullptr, nullptr);
   if (e != cudaSuccess) return fail(c, RUF_ERR_CUDA, "background set-up failed: %s", cudaGetErrorString(e));
-  uint32_t n = 0;
-  RUF_CUDA(c, cudaMemcpyAsync(&n, c->ws.ctr + kCtrBig, sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
+  uint32_t w[kCtrWords] = {0};
+  RUF_CUDA(c, cudaMemcpyAsync(w, c->ws.ctr, sizeof(w), cudaMemcpyDeviceToHost, sk));
   RUF_CUDA(c, cudaStreamSynchronize(sk));
-  if (n > (uint32_t)kBgSeedMax || n > c->dims.cap_big) { c->bg_state = -1; return RUF_OK; }
+  const uint32_t n = w[kCtrBig];
+  // Only a quad that ends up in the big list and nowhere else can be seeded: on small images it lies inside the guard band,
+  // is not clipped, touches few tiles and is BINNED like any other triangle (kept != 0) -- then the setup kernel keeps it.
+  if (n > (uint32_t)kBgSeedMax || n > c->dims.cap_big || w[kCtrKept] != 0 || w[kCtrFlags] != 0) { c->bg_state = -1; return RUF_OK; }
   RUF_CUDA(c, cudaMemcpyAsync(c->bg_seed, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, sk));
   if (n) RUF_CUDA(c, cudaMemcpyAsync(c->bg_seed + 4, c->ws.big, n * sizeof(TriRec), cudaMemcpyDeviceToDevice, sk));
   RUF_CUDA(c, cudaStreamSynchronize(sk));
@@ -950,7 +958,37 @@ int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj
 {
   if (c && depth_in && depth_out && proj && view && (c->n_parts == 0 || part_model) && c->have_model &&
       (enc == RUF_ENC_F32_M || enc == RUF_ENC_U16_MM) && cudaSetDevice(c->device) == cudaSuccess) {
-    const int rc = single_frame_graph(c, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out, mask_out);
+    // Pageable buffers (a numpy array, a message's data vector) travel through the context's page-locked staging: one
+    // memcpy each way and the single-frame graph in between, instead of the pageable copies of the staged pipeline.
+    const size_t es = elem_size(enc), img = (size_t)c->W * c->H, mb = mask_bytes(c);
+    const bool p_in = is_pinned_host(depth_in), p_out = is_pinned_host(depth_out), p_mask = !mask_out || is_pinned_host(mask_out);
+    const void *src = depth_in;
+    void *dst = depth_out;
+    uint8_t *msk = mask_out;
+    if (!(p_in && p_out && p_mask) && c->host_staging && c->use_graph && !c->profiling && c->stream == c->own_stream &&
+        !c->slice_frames) {
+      if (!c->hs_in) {
+        const size_t cap = img * sizeof(float);
+        if (cudaHostAlloc(&c->hs_in, cap, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&c->hs_out, cap, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&c->hs_mask, img, cudaHostAllocDefault) != cudaSuccess) {
+          cudaGetLastError();
+          cudaFreeHost(c->hs_in); cudaFreeHost(c->hs_out); cudaFreeHost(c->hs_mask);
+          c->hs_in = c->hs_out = nullptr; c->hs_mask = nullptr;
+          c->host_staging = false;
+        }
+      }
+      if (c->hs_in) {
+        if (!p_in) { std::memcpy(c->hs_in, depth_in, img * es); src = c->hs_in; }
+        if (!p_out) dst = c->hs_out;
+        if (!p_mask) msk = (uint8_t *)c->hs_mask;
+      }
+    }
+    const int rc = single_frame_graph(c, src, enc, proj, view, part_model, max_diff, replace_value, dst, msk);
+    if (rc == RUF_OK) {
+      if (dst != depth_out) std::memcpy(depth_out, dst, img * es);
+      if (msk != mask_out) std::memcpy(mask_out, msk, mb);
+    }
     if (rc != 1) return rc;
   }
   return ruf_filter_batch_host(c, 1, depth_in, enc, proj, view, part_model, max_diff, replace_value, depth_out,
