@@ -566,6 +566,27 @@ def test_single_frame_graph_path_with_pinned_buffers(direct, monkeypatch):
             ruf.host_free(p)
 
 
+@pytest.mark.parametrize("env", [{}, {"RUF_HOST_STAGING": "0"}, {"RUF_NO_GRAPH": "1"}])
+@pytest.mark.parametrize("enc", ["u16", "f32"])
+def test_pageable_single_frame_paths(env, enc, monkeypatch):
+    """ruf_filter with pageable buffers (numpy arrays): by default through the context's page-locked staging around the
+    single-frame graph, with RUF_HOST_STAGING=0 or RUF_NO_GRAPH=1 through the staged pipeline -- the same bits."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc = helpers.scene("pr2_small")
+    lib = ruf.load()
+    a = np.zeros(16, np.uint8)
+    assert lib.ruf_host_is_pinned(a.ctypes.data) == 0 and lib.ruf_host_is_pinned(None) == 0
+    p = ruf.host_alloc(64)
+    assert lib.ruf_host_is_pinned(p) == 1 and lib.ruf_host_is_pinned(p + 32) == 1
+    ruf.host_free(p)
+    with ruf.Context(sc.width, sc.height) as ctx:
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        for k in (1, 6, 6):
+            run_and_compare(sc, k=k, enc=enc, ctx=ctx)
+        run_and_compare(sc, k=2, enc=enc, ctx=ctx, want_mask=False)
+
+
 @pytest.mark.parametrize("bg_cache", ["1", "0"])
 def test_single_frame_graph_background_seed_follows_the_projection_matrix(bg_cache, monkeypatch):
     """The single-frame graph seeds the big list with the background quad's records, set up once per projection matrix
