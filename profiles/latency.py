@@ -9,7 +9,10 @@ sys.path.insert(0, ROOT)
 import realtime_urdf_filter_b200 as ruf
 from realtime_urdf_filter_b200 import synth
 
-sc = synth.pr2_like_scene()
+# optional argument: c1 | c2 | c3 | c5 (bench.py's configurations; default c2)
+cfg_name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+import bench
+sc = bench.make_scene(bench.CONFIGS[cfg_name])
 proj, _, _ = sc.proj()
 views, pms = sc.frames(list(range(32)))
 lib = ruf.load()
@@ -34,4 +37,4 @@ with ruf.Context(sc.width, sc.height) as ctx:
             ts = np.array(ts[32:]) * 1e6
             out[f"{enc} {'pinned' if pinned else 'pageable'}"] = dict(median_us=round(float(np.median(ts)), 1), p99_us=round(float(np.percentile(ts, 99)), 1))
             print(enc, "pinned" if pinned else "pageable", out[f"{enc} {'pinned' if pinned else 'pageable'}"], flush=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "latency.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "latency_%s.json" % cfg_name), "w"), indent=1)

@@ -259,7 +259,10 @@ static int launch(ruf_context *c, int n_frames, const void *d_in, int enc, const
   const uintptr_t al = (uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_zbuf;
   fb.mask_bits = c->mask_format == RUF_MASK_BITS;
   fb.host_status = c->launch_host_status;
-  fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (fb.mask_bits || ((uintptr_t)d_mask & 7) == 0);
+  // 8-pixel vector accesses: 16 bytes (16UC1) / 32 bytes (32FC1: 256-bit loads and stores) per thread and row
+  const uintptr_t al_io = (uintptr_t)d_in | (uintptr_t)d_out;
+  fb.vec_ok = (c->W % 8 == 0) && ((al & 15) == 0) && (enc == RUF_ENC_U16_MM || (al_io & 31) == 0) &&
+              (fb.mask_bits || ((uintptr_t)d_mask & 7) == 0);
   if (fb.mask_bits && d_mask && !fb.vec_ok)
     return fail(c, RUF_ERR_INVALID, "RUF_MASK_BITS needs an image width that is a multiple of 8 and 16-byte aligned depth buffers");
   const ShaderParams sp = shader_params(c, max_diff, replace_value);

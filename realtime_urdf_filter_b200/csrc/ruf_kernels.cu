@@ -873,6 +873,23 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256) for the 8 float pixels a thread owns in a row: one full 32-byte
+// sector per lane and instruction.  Two 128-bit accesses with a 32-byte lane stride touch every sector twice, half each
+// time -- harmless in HBM / L2, but when the buffers are the caller's pinned host memory (single-frame graph) every half
+// sector is a PCIe transaction of its own: 32FC1 frames took 440 us instead of 260 at 1280x960.  32-byte aligned.
+__device__ __forceinline__ void ldg_nc_256(const void *p, uint4 &a, uint4 &b)
+{
+  asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_256(void *p, const float (&v)[8])
+{
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // thread-block cluster: barrier over all threads of all CTAs (release / acquire: shared-memory writes made before it are
 // visible to the other CTAs' ld.shared::cluster after it) and loads from another CTA's shared memory (DSMEM)
 __device__ __forceinline__ void cluster_sync_all()
@@ -1293,8 +1310,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
             float od[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (drawn) {
               const float thr = __uint_as_float(ti.y);
-              const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + base);
-              const uint4 s0 = __ldg(p), s1 = __ldg(p + 1);
+              uint4 s0, s1;
+              ldg_nc_256(static_cast<const float *>(fb.depth_in) + base, s0, s1);
               const float sensor[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
                                        __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
               uint32_t om[8];
@@ -1307,9 +1324,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
               mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
               mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
             }
-            float4 *po = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
-            po[0] = make_float4(od[0], od[1], od[2], od[3]);
-            po[1] = make_float4(od[4], od[5], od[6], od[7]);
+            stg_256(static_cast<float *>(fb.depth_out) + base, od);
           }
           if (fb.mask_out) store_mask(fb, base, mq);
           if (fb.zbuf_out) {
@@ -1858,8 +1873,8 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
         }
         *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(fb.depth_out) + base) = o;
       } else {
-        const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const float *>(fb.depth_in) + base);
-        const uint4 sens0 = __ldg(p), sens1 = __ldg(p + 1);
+        uint4 sens0, sens1;
+        ldg_nc_256(static_cast<const float *>(fb.depth_in) + base, sens0, sens1);
         const float sensor[8] = {__uint_as_float(sens0.x), __uint_as_float(sens0.y), __uint_as_float(sens0.z),
                                  __uint_as_float(sens0.w), __uint_as_float(sens1.x), __uint_as_float(sens1.y),
                                  __uint_as_float(sens1.z), __uint_as_float(sens1.w)};
@@ -1872,9 +1887,7 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
           od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
           om[i] = sflt ? 255u : 0u;
         }
-        float4 *po = reinterpret_cast<float4 *>(static_cast<float *>(fb.depth_out) + base);
-        po[0] = make_float4(od[0], od[1], od[2], od[3]);
-        po[1] = make_float4(od[4], od[5], od[6], od[7]);
+        stg_256(static_cast<float *>(fb.depth_out) + base, od);
         mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
         mq.y = om[4] | (om[5] << 8) | (om[6] << 16) | (om[7] << 24);
       }
