@@ -14,6 +14,15 @@ for name, kw in (("pr2_small", {}), ("example", {})):
         d, m = ctx.filter(fr["depth"], proj, fr["view"], fr["pm"], sc.max_diff, sc.replace_value)
     assert np.array_equal(d, want_d) and np.array_equal(m, want_m)
     print(name, "ok")
+# 32FC1 at full size: the 256-bit loads / stores of the float path, through ruf_filter's page-locked staging and the graph
+sc = helpers.scene("pr2_small"); proj, _, _ = sc.proj()
+fr = helpers.make_frame(sc, 4, "f32")
+want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+with ruf.Context(sc.width, sc.height) as ctx:
+    ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+    d, m = ctx.filter(fr["depth"], proj, fr["view"], fr["pm"], sc.max_diff, sc.replace_value)
+assert np.array_equal(d.view(np.uint32), want_d.view(np.uint32)) and np.array_equal(m, want_m)
+print("f32 ok")
 sc = synth.pr2_like_scene(100, 75, n_tris=3000, name="odd")
 proj, _, _ = sc.proj(); fr = helpers.make_frame(sc, 1, "f32")
 with ruf.Context(100, 75) as ctx:
