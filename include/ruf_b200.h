@@ -271,12 +271,20 @@ RUF_API int ruf_cylinder_triangle_count(int slices, int stacks);
 /* Diagnostics of the model ingest (CPU only, no device needed).  ruf_set_model cuts the soup into
  * "meshlets" (runs of consecutive triangles whose bit-identical vertices are welded, the device-side
  * replacement of the reference's VBO/IBO pairs, src/renderable.cpp:339-350); this builds them with the
- * given limits (the library uses 256 vertices, 512 triangles, 32 parts) and expands them again:
+ * given limits (the library uses 512 vertices, 1023 triangles, 32 parts, and 256 triangles for its fine cut) and expands them again:
  * out_xyz (n_tris + 2) * 9 floats, out_part n_tris + 2 -- the input soup bit for bit, followed by the
  * two triangles of the background quad (part = n_parts).  counts[3] = meshlets, welded vertices, triangles. */
 RUF_API int ruf_meshlet_roundtrip(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts,
                                   double z_far, int max_verts, int max_tris, int max_parts,
                                   float *out_xyz, uint32_t *out_part, int64_t *counts);
+
+/* The same for BOTH cuts of the model that ruf_set_model keeps in one set of arrays (the throughput cut with at most max_tris
+ * triangles per meshlet, then the fine cut with at most fine_tris, used by launches of one frame): out_xyz / out_part hold
+ * 2 * (n_tris + 2) triangles, each cut expanded to the soup + the background quad.  counts[4] = meshlets of the first cut,
+ * meshlets of the fine cut, welded vertices, index triples. */
+RUF_API int ruf_meshlet_sets_roundtrip(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts,
+                                       double z_far, int max_verts, int max_tris, int fine_tris, int max_parts,
+                                       float *out_xyz, uint32_t *out_part, int64_t *counts);
 
 RUF_API const char *ruf_version(void);
 

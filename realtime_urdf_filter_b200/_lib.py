@@ -78,6 +78,8 @@ SIGNATURES = {
                                              C.c_void_p]),
     "ruf_meshlet_roundtrip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ruf_meshlet_sets_roundtrip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ruf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ruf_host_free": (C.c_int, [C.c_void_p]),
     "ruf_host_is_pinned": (C.c_int, [C.c_void_p]),
@@ -230,6 +232,23 @@ def meshlet_roundtrip(tri_xyz, tri_part, n_parts, z_far=8.0, max_verts=256, max_
     if rc != RUF_OK:
         raise RufError(rc, "ruf_meshlet_roundtrip failed")
     return out_xyz, out_part, dict(meshlets=int(counts[0]), verts=int(counts[1]), tris=int(counts[2]))
+
+
+def meshlet_sets_roundtrip(tri_xyz, tri_part, n_parts, z_far=8.0, max_verts=512, max_tris=1023, fine_tris=256, max_parts=32):
+    """Both cuts of the model as ruf_set_model uploads them (throughput cut, then fine cut), each expanded to a soup again.
+    -> (xyz (2, T+2, 9), part (2, T+2), counts dict)."""
+    lib = load()
+    xyz = np.ascontiguousarray(tri_xyz, dtype=np.float32).reshape(-1, 9)
+    part = np.ascontiguousarray(tri_part, dtype=np.uint32)
+    n = xyz.shape[0]
+    out_xyz = np.empty((2, n + 2, 9), np.float32)
+    out_part = np.empty((2, n + 2), np.uint32)
+    counts = np.zeros(4, np.int64)
+    rc = lib.ruf_meshlet_sets_roundtrip(xyz.ctypes.data, part.ctypes.data, n, int(n_parts), float(z_far), max_verts, max_tris,
+                                        fine_tris, max_parts, out_xyz.ctypes.data, out_part.ctypes.data, counts.ctypes.data)
+    if rc != RUF_OK:
+        raise RufError(rc, "ruf_meshlet_sets_roundtrip failed")
+    return out_xyz, out_part, dict(meshlets=int(counts[0]), fine_meshlets=int(counts[1]), verts=int(counts[2]), tris=int(counts[3]))
 
 
 class Context:

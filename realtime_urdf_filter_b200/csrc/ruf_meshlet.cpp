@@ -135,20 +135,15 @@ void build_meshlet_sets(const float *tri_xyz, const uint32_t *tri_part, int64_t 
 // Diagnostics (CPU only): build the meshlets of a soup with the library's limits and expand them again.
 // out_xyz: (n_tris + 2) * 9 floats, out_part: n_tris + 2 (the background quad comes last, part = n_parts).
 // counts[0..2] = meshlets, welded vertices, triangles.  Returns RUF_OK or RUF_ERR_INVALID.
-extern "C" RUF_API int ruf_meshlet_roundtrip(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts,
-                                             double z_far, int max_verts, int max_tris, int max_parts, float *out_xyz,
-                                             uint32_t *out_part, int64_t *counts)
+// expands the meshlets [m0, m1) of a model into a soup; checks the limits and the packing on the way
+static int expand_meshlets(const ruf::MeshletModel &mm, size_t m0, size_t m1, uint32_t tri_base, int max_verts, int max_tris,
+                           int max_parts, float *out_xyz, uint32_t *out_part, int64_t &t_out)
 {
-  if (n_tris < 0 || n_parts < 0 || (n_tris > 0 && (!tri_xyz || !tri_part)) || max_verts < 3 || max_verts > 1024 ||
-      max_tris < 1 || max_tris > 1023 || max_parts < 1 || max_parts > 32)
-    return RUF_ERR_INVALID;
-  ruf::MeshletModel mm;
-  ruf::build_meshlets(tri_xyz, tri_part, n_tris, n_parts, (float)(z_far * 0.99), max_verts, max_tris, max_parts, mm);
-  int64_t t_out = 0;
-  for (size_t m = 0; m < mm.n_meshlets(); ++m) {
+  t_out = 0;
+  for (size_t m = m0; m < m1; ++m) {
     const uint32_t *h = &mm.hdr[4 * m];
     const uint32_t nv = h[2] & 1023u, nt = (h[2] >> 10) & 1023u, np = (h[2] >> 20) + 1;
-    if ((int)nv > max_verts || (int)nt > max_tris || (int)np > max_parts || h[1] != (uint32_t)t_out) return RUF_ERR_INVALID;
+    if ((int)nv > max_verts || (int)nt > max_tris || (int)np > max_parts || h[1] != tri_base + (uint32_t)t_out) return RUF_ERR_INVALID;
     for (uint32_t t = 0; t < nt; ++t, ++t_out) {
       const uint32_t ix = mm.tris[h[1] + t];
       const uint32_t id[3] = {ix & 1023u, (ix >> 10) & 1023u, ix >> 20};
@@ -166,6 +161,46 @@ extern "C" RUF_API int ruf_meshlet_roundtrip(const float *tri_xyz, const uint32_
       if (out_part) out_part[t_out] = h[3] + slot;
     }
   }
+  return RUF_OK;
+}
+
+extern "C" RUF_API int ruf_meshlet_roundtrip(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts,
+                                             double z_far, int max_verts, int max_tris, int max_parts, float *out_xyz,
+                                             uint32_t *out_part, int64_t *counts)
+{
+  if (n_tris < 0 || n_parts < 0 || (n_tris > 0 && (!tri_xyz || !tri_part)) || max_verts < 3 || max_verts > 1024 ||
+      max_tris < 1 || max_tris > 1023 || max_parts < 1 || max_parts > 32)
+    return RUF_ERR_INVALID;
+  ruf::MeshletModel mm;
+  ruf::build_meshlets(tri_xyz, tri_part, n_tris, n_parts, (float)(z_far * 0.99), max_verts, max_tris, max_parts, mm);
+  int64_t t_out = 0;
+  if (expand_meshlets(mm, 0, mm.n_meshlets(), 0u, max_verts, max_tris, max_parts, out_xyz, out_part, t_out) != RUF_OK) return RUF_ERR_INVALID;
   if (counts) { counts[0] = (int64_t)mm.n_meshlets(); counts[1] = (int64_t)(mm.verts.size() / 4); counts[2] = t_out; }
+  return RUF_OK;
+}
+
+// The same for the two cuts ruf_set_model uploads in one set of arrays (build_meshlet_sets): the throughput cut first, then
+// the fine cut.  out_xyz / out_part hold 2 * (n_tris + 2) triangles: both cuts expanded, each the soup + the background quad.
+// counts[0..3] = meshlets of the first cut, meshlets of the fine cut, welded vertices, index triples (both cuts).
+extern "C" RUF_API int ruf_meshlet_sets_roundtrip(const float *tri_xyz, const uint32_t *tri_part, int64_t n_tris, int n_parts,
+                                                  double z_far, int max_verts, int max_tris, int fine_tris, int max_parts,
+                                                  float *out_xyz, uint32_t *out_part, int64_t *counts)
+{
+  if (n_tris < 0 || n_parts < 0 || (n_tris > 0 && (!tri_xyz || !tri_part)) || max_verts < 3 || max_verts > 1024 ||
+      max_tris < 1 || max_tris > 1023 || fine_tris < 1 || fine_tris > 1023 || max_parts < 1 || max_parts > 32)
+    return RUF_ERR_INVALID;
+  ruf::MeshletModel mm;
+  ruf::build_meshlet_sets(tri_xyz, tri_part, n_tris, n_parts, (float)(z_far * 0.99), max_verts, max_tris, fine_tris, max_parts, mm);
+  int64_t t0 = 0, t1 = 0;
+  if (expand_meshlets(mm, 0, mm.n_primary, 0u, max_verts, max_tris, max_parts, out_xyz, out_part, t0) != RUF_OK) return RUF_ERR_INVALID;
+  if (t0 != n_tris + 2) return RUF_ERR_INVALID;
+  if (expand_meshlets(mm, mm.n_primary, mm.n_meshlets(), (uint32_t)t0, max_verts, fine_tris, max_parts,
+                      out_xyz ? out_xyz + 9 * t0 : nullptr, out_part ? out_part + t0 : nullptr, t1) != RUF_OK)
+    return RUF_ERR_INVALID;
+  if (t1 != n_tris + 2 || (int64_t)mm.tris.size() != t0 + t1) return RUF_ERR_INVALID;
+  if (counts) {
+    counts[0] = (int64_t)mm.n_primary; counts[1] = (int64_t)(mm.n_meshlets() - mm.n_primary);
+    counts[2] = (int64_t)(mm.verts.size() / 4); counts[3] = (int64_t)mm.tris.size();
+  }
   return RUF_OK;
 }

@@ -56,3 +56,17 @@ def test_limits_and_adversarial_order(limits):
 def test_empty_model_is_just_the_background_quad():
     xyz, part, cnt = _lib.meshlet_roundtrip(np.zeros((0, 9), np.float32), np.zeros(0, np.uint32), 0)
     assert cnt == dict(meshlets=1, verts=4, tris=2) and np.array_equal(part, [0, 0])
+
+
+@pytest.mark.parametrize("name", ["pr2_small", "example"])
+def test_both_cuts_of_the_model_hold_every_triangle_once(name):
+    """ruf_set_model keeps two cuts of the model in one set of arrays (throughput cut, then the fine cut that launches of
+    one frame use, its offsets shifted behind the first): each expands to the input soup bit for bit + the background quad."""
+    sc = helpers.scene(name)
+    xyz, part, cnt = _lib.meshlet_sets_roundtrip(sc.tri, sc.tri_part, sc.n_parts)
+    T = len(sc.tri)
+    for cut in range(2):
+        assert np.array_equal(_bits(xyz[cut, :T]), _bits(np.asarray(sc.tri, np.float32).reshape(-1, 9)))
+        assert np.array_equal(part[cut, :T], sc.tri_part)
+        assert np.all(part[cut, T:] == sc.n_parts)                  # the background quad, last in both cuts
+    assert cnt["tris"] == 2 * (T + 2) and cnt["fine_meshlets"] >= cnt["meshlets"] and cnt["fine_meshlets"] >= (T + 2) / 256
