@@ -70,7 +70,7 @@ struct ruf_context {
 
   int mask_format = RUF_MASK_BYTES;  // ruf_set_mask_format
 
-  // single-frame host call (ruf_filter with pinned buffers): the whole sequence -- uploads, memset, four kernels,
+  // single-frame host call (ruf_filter with pinned buffers): the whole sequence -- three kernels; with unmapped buffers also uploads, memset,
   // read-backs, status word -- is ONE captured CUDA graph with the depth upload running beside the pose / setup kernels
   struct FrameGraph {
     cudaGraph_t graph = nullptr;
@@ -789,7 +789,7 @@ static int fill_bg_seed(ruf_context *c, const double *proj, double *hm, size_t m
 // RUF_OK: done.  1: not applicable (pageable buffers, caller's stream, profiling) or overflow -> take the pipeline.
 //
 // Latency path.  Everything a 30 Hz caller waits for is on the critical path of ONE frame, so the graph holds as few nodes
-// as the buffers allow.  With mapped pinned buffers (cudaHostAlloc / ruf_host_alloc: the default) it is four kernel nodes
+// as the buffers allow.  With mapped pinned buffers (cudaHostAlloc / ruf_host_alloc: the default) it is three kernel nodes
 // and nothing else: the pose kernel reads the matrices from the context's pinned block and clears the frame's counters,
 // the raster kernel (cluster-split variant) reads the depth image from and writes depth + mask to the caller's buffers
 // over PCIe while it works, and its last CTA stores the status words into the host's copy.  Buffers that are pinned but

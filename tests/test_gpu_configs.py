@@ -500,7 +500,7 @@ def _pinned(shape, dtype):
 
 @pytest.mark.parametrize("direct", ["7", "3", "0", "5"])
 def test_single_frame_graph_path_with_pinned_buffers(direct, monkeypatch):
-    """ruf_filter with pinned host buffers runs as ONE captured CUDA graph.  RUF_DIRECT = 7 (default): four kernel nodes, the
+    """ruf_filter with pinned host buffers runs as ONE captured CUDA graph.  RUF_DIRECT = 7 (default): three kernel nodes, the
     kernels read / write the caller's mapped buffers, the matrices and the status words themselves; 3: matrices and status
     by copy nodes; 0: every buffer by copy nodes (uploads, memset, kernels, read-backs); 5: a mix.  Same results as the
     staged pipeline and the oracle: first call (capture), same buffers again, other buffers (copy nodes / the raster
