@@ -478,6 +478,22 @@ def run_b200(args, rank, world, local_rank):
                   "d2h_bytes_per_step": int(p_stats["d2h_bytes"]), "h2d_bytes_per_step": int(p_stats["h2d_bytes"]),
                   "matches_byte_mask": bits_ok,
                   "note": "ruf_set_mask_format(RUF_MASK_BITS): opt-in, not the reference's MONO8 wire format"}
+    # the reference's own use of the path: ONE frame per call at 30 Hz (ruf_filter, host buffers in and out, synchronous).
+    # Latency, not throughput: reported beside the e2e figure, N = 1 only.
+    single = None
+    if world == 1:
+        lat = []
+        for k in range(132):
+            f = k % n_e2e
+            t0 = time.perf_counter()
+            rc = lib.ruf_filter(ctx._h, h_in[f].data_ptr(), ruf.ENC_U16_MM, e_proj.ctypes.data, e_views[f].ctypes.data,
+                                e_pms[f].ctypes.data, MAX_DIFF, REPLACE_VALUE, h_out[f].data_ptr(), h_mask[f].data_ptr())
+            lat.append(time.perf_counter() - t0)
+            if rc != 0:
+                raise RuntimeError(lib.ruf_last_error(ctx._h).decode())
+        lat = np.array(lat[32:]) * 1e6
+        single = {"median_us": round(float(np.median(lat)), 1), "p99_us": round(float(np.percentile(lat, 99)), 1), "calls": int(lat.size),
+                  "api": "ruf_filter (pinned host buffers in and out, synchronous): one CUDA graph of three kernels that read / write the host buffers themselves"}
     # sanity: the e2e output equals the device-path output for the same frames (weak arm: ring slot 0 is frame order)
     same = None
     if not strong:
@@ -543,7 +559,7 @@ def run_b200(args, rank, world, local_rank):
                 "copy_ceiling": copy_value, "frac_of_copy_ceiling": e2e_value / copy_value,
                 "copy_ceiling_api": "ruf_host_copy_ceiling: the same chunked H2D/D2H pipeline without the kernels",
                 "pcie_gbs_at_ceiling": copy_value * (e2e_stats["h2d_bytes"] + e2e_stats["d2h_bytes"]) / n_e2e / 1e9 / world,
-                "packed_mask": packed},
+                "packed_mask": packed, "single_frame": single},
         "gpu_launches": int(args.steps * R * stats["kernel_launches"]) * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": f"ruf_{dom}_kernel", "peak_source": peak_src,

@@ -77,6 +77,11 @@ struct ruf_context {
     cudaGraphExec_t exec = nullptr;
     cudaGraphNode_t n_in = nullptr, n_out = nullptr, n_mask = nullptr, n_raster = nullptr;
     int direct = -1, bg_mode = -1;
+    // the raster kernel's launch parameters as captured (retargeting its FrameBuffers argument needs the whole list)
+    struct RasterArgs {
+      Dims d; const TriRec *big; const BinRec *bins; const uint32_t *ctr; const uint4 *tinfo; ShaderParams sp; FrameBuffers fb; uint32_t *status;
+    } ra{};
+    cudaKernelNodeParams raster_kp{};
     const void *in = nullptr; void *out = nullptr; uint8_t *mask = nullptr;
     int enc = -1, mask_format = -1, n_parts = -1, multipass = -1;
     float max_diff = 0.f, replace_value = 0.f;
@@ -903,7 +908,18 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
         else if (mask_out && p.dstPtr.ptr == mask_out) g.n_mask = nd;
       } else if (t == cudaGraphNodeTypeKernel) {
         cudaKernelNodeParams kp;
-        if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && is_raster_kernel(kp.func)) g.n_raster = nd;
+        if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && is_raster_kernel(kp.func)) {
+          g.n_raster = nd;
+          g.raster_kp = kp;
+          g.ra.d = *static_cast<const Dims *>(kp.kernelParams[0]);
+          g.ra.big = *static_cast<const TriRec *const *>(kp.kernelParams[1]);
+          g.ra.bins = *static_cast<const BinRec *const *>(kp.kernelParams[2]);
+          g.ra.ctr = *static_cast<const uint32_t *const *>(kp.kernelParams[3]);
+          g.ra.tinfo = *static_cast<const uint4 *const *>(kp.kernelParams[4]);
+          g.ra.sp = *static_cast<const ShaderParams *>(kp.kernelParams[5]);
+          g.ra.fb = *static_cast<const FrameBuffers *>(kp.kernelParams[kRasterArgFrameBuffers]);
+          g.ra.status = *static_cast<uint32_t *const *>(kp.kernelParams[7]);
+        }
       }
     }
     if ((copy_in && !g.n_in) || (copy_out && (!g.n_out || (mask_out && !g.n_mask))) || ((direct & 3) && !g.n_raster)) {
@@ -922,17 +938,14 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
     if (mask_out && g.mask != mask_out && g.n_mask)
       RUF_CUDA(c, cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_mask, mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost));
     if ((direct & 3) && (g.in != depth_in || g.out != depth_out || g.mask != mask_out)) {
-      cudaKernelNodeParams kp;
-      RUF_CUDA(c, cudaGraphKernelNodeGetParams(g.n_raster, &kp));
-      FrameBuffers fb = *static_cast<const FrameBuffers *>(kp.kernelParams[kRasterArgFrameBuffers]);
-      if (direct & 2) fb.depth_in = dev_in;
-      if (direct & 1) { fb.depth_out = dev_out; fb.mask_out = (uint8_t *)dev_mask; }
-      void *args[kRasterArgCount];
-      for (int i = 0; i < kRasterArgCount; ++i) args[i] = kp.kernelParams[i];
-      args[kRasterArgFrameBuffers] = &fb;
+      // (only the executable graph is updated, from the parameter list kept at capture time: one driver call)
+      if (direct & 2) g.ra.fb.depth_in = dev_in;
+      if (direct & 1) { g.ra.fb.depth_out = dev_out; g.ra.fb.mask_out = (uint8_t *)dev_mask; }
+      void *args[kRasterArgCount] = {&g.ra.d, &g.ra.big, &g.ra.bins, &g.ra.ctr, &g.ra.tinfo, &g.ra.sp, &g.ra.fb, &g.ra.status};
+      cudaKernelNodeParams kp = g.raster_kp;
       kp.kernelParams = args;
+      kp.extra = nullptr;
       RUF_CUDA(c, cudaGraphExecKernelNodeSetParams(g.exec, g.n_raster, &kp));
-      RUF_CUDA(c, cudaGraphKernelNodeSetParams(g.n_raster, &kp));     // the template graph follows: the next retarget starts from here
     }
     g.in = depth_in; g.out = depth_out; g.mask = mask_out;
   }
