@@ -483,7 +483,7 @@ def run_b200(args, rank, world, local_rank):
     single = None
     if world == 1:
         torch.cuda.synchronize()
-        ctx.set_stream(None)       # the context's own stream, as a ROS node uses it (the graph path is not taken on a caller's stream)
+        ctx.set_stream(None)       # the context's own stream, as a ROS node uses it
         lat = []
         nf = min(n_e2e, 8)         # a driver with a small ring of frame buffers
         ptrs = [(h_in[f].data_ptr(), e_views[f].ctypes.data, e_pms[f].ctypes.data, h_out[f].data_ptr(), h_mask[f].data_ptr())

@@ -791,7 +791,7 @@ static int fill_bg_seed(ruf_context *c, const double *proj, double *hm, size_t m
   return RUF_OK;
 }
 
-// RUF_OK: done.  1: not applicable (pageable buffers, caller's stream, profiling) or overflow -> take the pipeline.
+// RUF_OK: done.  1: not applicable (pageable buffers, profiling) or overflow -> take the pipeline.
 //
 // Latency path.  Everything a 30 Hz caller waits for is on the critical path of ONE frame, so the graph holds as few nodes
 // as the buffers allow.  With mapped pinned buffers (cudaHostAlloc / ruf_host_alloc: the default) it is three kernel nodes
@@ -804,7 +804,7 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
                               const double *part_model, float max_diff, float replace_value, void *depth_out,
                               uint8_t *mask_out)
 {
-  if (!c->use_graph || c->profiling || c->stream != c->own_stream || c->slice_frames) return 1;
+  if (!c->use_graph || c->profiling || c->slice_frames) return 1;
   if (!is_pinned_host(depth_in) || !is_pinned_host(depth_out) || (mask_out && !is_pinned_host(mask_out))) return 1;
   int rc = ensure_workspace(c, 1);
   if (rc != RUF_OK) return rc;
@@ -846,25 +846,27 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
   if (!same) {
     drop_frame_graph(c);
     if (!c->ev_fork) RUF_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    RUF_CUDA(c, cudaStreamBeginCapture(sk, cudaStreamCaptureModeRelaxed));
+    // (captured on the context's own stream -- idle while a caller's stream is in use --, launched on the current one)
+    cudaStream_t cap = c->own_stream;
+    RUF_CUDA(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
     bool ok = true;
     auto CK = [&](cudaError_t e) { if (e != cudaSuccess) ok = false; };
     const bool copy_in = !(direct & 2), copy_out = !(direct & 1);
     if (copy_in) {
-      CK(cudaEventRecord(c->ev_fork, sk));
+      CK(cudaEventRecord(c->ev_fork, cap));
       CK(cudaStreamWaitEvent(c->s_in, c->ev_fork, 0));
       CK(cudaMemcpyAsync(c->d_in[0], depth_in, img * es, cudaMemcpyHostToDevice, c->s_in));    // beside the pose / setup kernels
       CK(cudaEventRecord(c->ev_in[0], c->s_in));
     }
     double *dm = dev_mats ? dev_mats : c->d_mats[0];
-    if (!dev_mats) CK(cudaMemcpyAsync(c->d_mats[0], hm, mat_bytes, cudaMemcpyHostToDevice, sk));
+    if (!dev_mats) CK(cudaMemcpyAsync(c->d_mats[0], hm, mat_bytes, cudaMemcpyHostToDevice, cap));
     const int64_t launches_before = c->stats.kernel_launches;
     c->dims.fold_clear = 1;
     c->dims.bg_mode = bg_mode;
     c->ws.bg_seed = c->bg_seed;
     c->launch_host_status = dev_status;
     if (ok && launch(c, 1, copy_in ? c->d_in[0] : dev_in, enc, dm, dm + 16, dm + 32, max_diff, replace_value,
-                     copy_out ? c->d_out[0] : dev_out, mask_out ? (copy_out ? c->d_mask[0] : (uint8_t *)dev_mask) : nullptr, nullptr, sk,
+                     copy_out ? c->d_out[0] : dev_out, mask_out ? (copy_out ? c->d_mask[0] : (uint8_t *)dev_mask) : nullptr, nullptr, cap,
                      copy_in ? c->ev_in[0] : nullptr) != RUF_OK)
       ok = false;
     c->dims.fold_clear = 0;
@@ -872,19 +874,19 @@ static int single_frame_graph(ruf_context *c, const void *depth_in, int enc, con
     c->launch_host_status = nullptr;
     c->stats.kernel_launches = launches_before;
     if (copy_out) {
-      CK(cudaEventRecord(c->ev_k[0], sk));
+      CK(cudaEventRecord(c->ev_k[0], cap));
       CK(cudaStreamWaitEvent(c->s_out, c->ev_k[0], 0));
       if (mask_out) CK(cudaMemcpyAsync(mask_out, c->d_mask[0], mb, cudaMemcpyDeviceToHost, c->s_out));   // beside the depth read-back
       CK(cudaEventRecord(c->ev_out[0], c->s_out));
-      CK(cudaMemcpyAsync(depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost, sk));
+      CK(cudaMemcpyAsync(depth_out, c->d_out[0], img * es, cudaMemcpyDeviceToHost, cap));
     }
     if (!dev_status) {
-      CK(cudaMemcpyAsync(c->h_status, c->ws.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
-      CK(cudaMemsetAsync(c->ws.status + 1, 0, 2 * sizeof(uint32_t), sk));
+      CK(cudaMemcpyAsync(c->h_status, c->ws.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cap));
+      CK(cudaMemsetAsync(c->ws.status + 1, 0, 2 * sizeof(uint32_t), cap));
     }
-    if (copy_out) CK(cudaStreamWaitEvent(sk, c->ev_out[0], 0));
+    if (copy_out) CK(cudaStreamWaitEvent(cap, c->ev_out[0], 0));
     cudaGraph_t graph = nullptr;
-    const cudaError_t ee = cudaStreamEndCapture(sk, &graph);
+    const cudaError_t ee = cudaStreamEndCapture(cap, &graph);
     if (!ok || ee != cudaSuccess || !graph) {
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError();
@@ -981,8 +983,7 @@ int ruf_filter(ruf_context *c, const void *depth_in, int enc, const double *proj
     const void *src = depth_in;
     void *dst = depth_out;
     uint8_t *msk = mask_out;
-    if (!(p_in && p_out && p_mask) && c->host_staging && c->use_graph && !c->profiling && c->stream == c->own_stream &&
-        !c->slice_frames) {
+    if (!(p_in && p_out && p_mask) && c->host_staging && c->use_graph && !c->profiling && !c->slice_frames) {
       if (!c->hs_in) {
         const size_t cap = img * sizeof(float);
         if (cudaHostAlloc(&c->hs_in, cap, cudaHostAllocDefault) != cudaSuccess ||

@@ -566,6 +566,43 @@ def test_single_frame_graph_path_with_pinned_buffers(direct, monkeypatch):
             ruf.host_free(p)
 
 
+def test_single_frame_graph_on_a_callers_stream():
+    """ruf_set_stream + ruf_filter with pinned buffers: the graph is captured on the context's own (idle) stream and
+    launched on the caller's, behind whatever the caller queued there (here: a device batch that uses the same workspace)."""
+    import torch
+    sc = helpers.scene("pr2_small")
+    proj, _, _ = sc.proj()
+    lib = ruf.load()
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    frs = [helpers.make_frame(sc, k, "u16") for k in (2, 7, 13)]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_in = t(np.stack([f["depth"] for f in frs]).view(np.int16)); d_out = torch.empty_like(d_in)
+    d_mask = torch.empty(d_in.shape, dtype=torch.uint8, device=dev)
+    d_proj, d_view, d_pm = t(proj), t(np.stack([f["view"] for f in frs])), t(np.stack([f["pm"] for f in frs]))
+    h_in = torch.empty((sc.height, sc.width), dtype=torch.int16).pin_memory()
+    h_out, h_mask = torch.empty_like(h_in).pin_memory(), torch.empty((sc.height, sc.width), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    with ruf.Context(sc.width, sc.height) as ctx, torch.cuda.stream(stream):
+        ctx.set_model(sc.tri, sc.tri_part, sc.n_parts)
+        ctx.set_stream(stream.cuda_stream)
+        for rep in range(3):
+            ctx.filter_batch_device(3, d_in.data_ptr(), ruf.ENC_U16_MM, d_proj.data_ptr(), d_view.data_ptr(), d_pm.data_ptr(),
+                                    sc.max_diff, sc.replace_value, d_out.data_ptr(), d_mask.data_ptr(), 0)      # asynchronous
+            fr = frs[rep]
+            h_in.numpy()[:] = fr["depth"].view(np.int16)
+            v, pm, pr = [np.ascontiguousarray(a, np.float64) for a in (fr["view"], fr["pm"], proj)]
+            rc = lib.ruf_filter(ctx._h, h_in.data_ptr(), ruf.ENC_U16_MM, pr.ctypes.data, v.ctypes.data, pm.ctypes.data, sc.max_diff,
+                                sc.replace_value, h_out.data_ptr(), h_mask.data_ptr())
+            assert rc == 0, lib.ruf_last_error(ctx._h)
+            want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+            assert np.array_equal(h_out.numpy().view(np.uint16), want_d) and np.array_equal(h_mask.numpy(), want_m)
+        ctx.sync()
+    for i, fr in enumerate(frs):
+        want_d, want_m, _ = helpers.oracle_filter(sc, fr)
+        assert np.array_equal(d_out[i].cpu().numpy().view(np.uint16), want_d) and np.array_equal(d_mask[i].cpu().numpy(), want_m)
+
+
 @pytest.mark.parametrize("env", [{}, {"RUF_HOST_STAGING": "0"}, {"RUF_NO_GRAPH": "1"}])
 @pytest.mark.parametrize("enc", ["u16", "f32"])
 def test_pageable_single_frame_paths(env, enc, monkeypatch):
