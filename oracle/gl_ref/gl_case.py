@@ -1,7 +1,7 @@
 """Case files for the GL cross-check harness (oracle/gl_ref/gl_crosscheck.cpp) and the comparison of its dump with
 the CPU oracle.  TEST INFRASTRUCTURE ONLY (same rules as oracle_py.py).
 
-    python oracle/gl_ref/gl_case.py make  <scene: example|pr2_small|walls> <frame> <case.bin>
+    python oracle/gl_ref/gl_case.py make  <scene: example|pr2_small|pr2|walls|small:<scene>> <frame> <case.bin>
     python oracle/gl_ref/gl_case.py compare <case.bin> <dump.bin>      # prints the differing-pixel report as JSON
 
 The case keeps the GL matrix-stack operands SEPARATE (projection, inverse(camera_offset), camera transform, per part
@@ -83,6 +83,23 @@ def write_case(path, sc, k, depth_f32, max_diff=None, replace_value=None):
         f.write(np.ascontiguousarray(depth_f32, np.float32).tobytes())
 
 
+def write_case_raw(path, W, H, proj, off_inv, cam, part_models, tri, tri_part, depth_f32, z_near, z_far, max_diff, replace_value):
+    """The same file from raw operands (random soups: no Scene behind them); part_models: (P, 16) column-major doubles."""
+    tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
+    tri_part = np.ascontiguousarray(tri_part, np.uint32)
+    order = np.argsort(tri_part, kind="stable")
+    with open(path, "wb") as f:
+        f.write(b"RUFGLC01")
+        f.write(struct.pack("<4i", W, H, len(part_models), len(tri)))
+        f.write(np.asarray(proj, np.float64).tobytes() + np.asarray(off_inv, np.float64).tobytes() + np.asarray(cam, np.float64).tobytes())
+        f.write(struct.pack("<4f", z_near, z_far, max_diff, replace_value))
+        for m in part_models:
+            f.write(np.asarray(m, np.float64).reshape(-1).tobytes() + struct.pack("<i3f", 0, 0.0, 0.0, 0.0))
+        f.write(tri[order].tobytes())
+        f.write(tri_part[order].tobytes())
+        f.write(np.ascontiguousarray(depth_f32, np.float32).tobytes())
+
+
 def read_case_header(path):
     with open(path, "rb") as f:
         assert f.read(8) == b"RUFGLC01"
@@ -128,7 +145,11 @@ def compare(sc, k, depth_f32, gl_depth, gl_mask, max_diff=None, replace_value=No
 
 def _scene(name):
     from realtime_urdf_filter_b200 import synth
-    return {"example": synth.example_scene, "walls": synth.walls_scene,
+    if name.startswith("small:"):                      # small:<scene>: the same scene at 160 x 120 (golden fixtures)
+        base = name.split(":", 1)[1]
+        return {"example": lambda: synth.example_scene(160, 120), "walls": lambda: synth.walls_scene(160, 120),
+                "pr2_small": lambda: synth.pr2_like_scene(160, 120, n_tris=6000, name="pr2_like_small_160")}[base]()
+    return {"example": synth.example_scene, "walls": synth.walls_scene, "pr2": synth.pr2_like_scene,
             "pr2_small": lambda: synth.pr2_like_scene(n_tris=6000, name="pr2_like_small")}[name]()
 
 

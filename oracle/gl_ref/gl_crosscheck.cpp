@@ -8,7 +8,11 @@
 // exists.  Neither this image nor the GPU box has any GL library, so here the file is only syntax-checked against
 // oracle/gl_ref/stubs (tests/test_gl_crosscheck.py); with Mesa: `make -C oracle/gl_ref` builds it into oracle/_ref/.
 //
-//   gl_crosscheck <case.bin> <shader_dir> <out.bin>
+//   gl_crosscheck <case.bin> <shader_dir> <out.bin> [frames]
+//
+// With a frame count the frame (upload of the sensor depth, render, both read-backs: what RealtimeURDFFilter::filter does per
+// call, src/urdf_filter.cpp:234-237 + :729-735) is repeated and timed from the second one on: the reference's own CPU
+// figure on this machine's cores (llvmpipe renders with LP_NUM_THREADS threads, default = all cores).
 //
 // Sequence kept from the reference: 4 x RGBA32F rectangle-texture attachments + a 24-bit depth texture
 // (src/FrameBufferObject.cpp:868-880,1003-1023), sensor depth in a GL_R32F buffer texture re-specified per frame
@@ -18,19 +22,37 @@
 // MODELVIEW *= inverse(camera_offset) * camera_transform (:602-614), then per part glPushMatrix, glMultMatrixd
 // (link_to_fixed * link_offset, src/renderable.cpp:59-68), the optional glTranslatef / glScalef suffix (:95,128,427),
 // the triangles, glPopMatrix.  The matrix stack lives inside GL (float), exactly what the oracle can only approximate.
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #define GL_GLEXT_PROTOTYPES 1
 #include <GL/gl.h>
 #include <GL/glext.h>
+#ifdef RUF_GL_VIA_GLX
+// Mesa's xlib software GLX on top of oracle/gl_ref/fakex11 (no X server, no X11 headers in the image): the handful of GLX
+// declarations this file needs, spelled out.  See fakex11/fakex11.c and the Makefile's `glx` target.
+extern "C" {
+typedef struct _XDisplay Display;
+typedef struct __GLXcontextRec *GLXContext;
+typedef struct { void *visual; unsigned long visualid; int screen; int depth; int c_class; unsigned long red_mask, green_mask, blue_mask;
+                 int colormap_size; int bits_per_rgb; } XVisualInfo;
+Display *fakex_open_display(int width, int height);
+unsigned long fakex_window(void);
+XVisualInfo *glXChooseVisual(Display *, int, int *);
+GLXContext glXCreateContext(Display *, XVisualInfo *, GLXContext, int);
+int glXMakeCurrent(Display *, unsigned long, GLXContext);
+}
+#else
 #include <GL/osmesa.h>
+#endif
 
 namespace {
 
@@ -108,16 +130,25 @@ void check(const char *what)
 
 int main(int argc, char **argv)
 {
-  if (argc != 4) { std::fprintf(stderr, "usage: %s case.bin shader_dir out.bin\n", argv[0]); return 1; }
+  if (argc != 4 && argc != 5) { std::fprintf(stderr, "usage: %s case.bin shader_dir out.bin [frames]\n", argv[0]); return 1; }
+  const int n_frames = argc == 5 ? std::max(2, std::atoi(argv[4])) : 2;
   Case c;
   if (!load_case(argv[1], c)) { std::fprintf(stderr, "bad case file %s\n", argv[1]); return 1; }
 
   // headless compatibility-profile context (the shaders use gl_ModelViewProjectionMatrix / gl_Vertex / gl_FragData)
+#ifdef RUF_GL_VIA_GLX
+  Display *dpy = fakex_open_display(c.W, c.H);
+  int visual_attribs[] = {4 /* GLX_RGBA */, 8 /* GLX_RED_SIZE */, 8, 9, 8, 10, 8, 12 /* GLX_DEPTH_SIZE */, 24, 0};
+  XVisualInfo *vi = glXChooseVisual(dpy, 0, visual_attribs);
+  GLXContext ctx = vi ? glXCreateContext(dpy, vi, nullptr, 1) : nullptr;
+  if (!ctx || !glXMakeCurrent(dpy, fakex_window(), ctx)) { std::fprintf(stderr, "no GLX context\n"); return 5; }
+#else
   const int attribs[] = {OSMESA_FORMAT, OSMESA_RGBA, OSMESA_DEPTH_BITS, 24, OSMESA_PROFILE, OSMESA_COMPAT_PROFILE,
                          OSMESA_CONTEXT_MAJOR_VERSION, 3, OSMESA_CONTEXT_MINOR_VERSION, 1, 0};
   OSMesaContext ctx = OSMesaCreateContextAttribs(attribs, nullptr);
   std::vector<unsigned char> window((size_t)c.W * c.H * 4);
   if (!ctx || !OSMesaMakeCurrent(ctx, window.data(), GL_UNSIGNED_BYTE, c.W, c.H)) { std::fprintf(stderr, "no OSMesa context\n"); return 5; }
+#endif
   std::fprintf(stderr, "GL_RENDERER %s | GL_VERSION %s\n", (const char *)glGetString(GL_RENDERER), (const char *)glGetString(GL_VERSION));
 
   // FramebufferObject("rgba=4x32t depth=24t stencil=8t"): 4 RGBA32F rectangle textures + a D24 texture
@@ -153,7 +184,12 @@ int main(int argc, char **argv)
   glGetProgramiv(prog, GL_LINK_STATUS, &linked);
   if (!linked) { std::fprintf(stderr, "program does not link\n"); return 7; }
 
-  for (int frame = 0; frame < 2; ++frame) {       // frame 0 shades the background quad with default uniforms (see header)
+  std::vector<float> masked((size_t)c.W * c.H);
+  std::vector<unsigned char> mask((size_t)c.W * c.H);
+  glPixelStorei(GL_PACK_ALIGNMENT, 1);            // the reference relies on W % 4 == 0 with the default 4
+  std::chrono::steady_clock::time_point t_start;
+  for (int frame = 0; frame < n_frames; ++frame) {       // frame 0 shades the background quad with default uniforms (see header)
+    if (frame == 1) t_start = std::chrono::steady_clock::now();
     glBindBuffer(GL_TEXTURE_BUFFER, tbo);
     glBufferData(GL_TEXTURE_BUFFER, (GLsizeiptr)(c.depth.size() * sizeof(float)), c.depth.data(), GL_DYNAMIC_DRAW);
     glActiveTexture(GL_TEXTURE0);
@@ -209,19 +245,17 @@ int main(int argc, char **argv)
     glDisableClientState(GL_VERTEX_ARRAY);
     glUseProgram(0);
     glBindFramebuffer(GL_FRAMEBUFFER, 0);
-    glFinish();
+    // readback exactly as :729-735 (bottom-up GL rows = the same memory order as the input image)
+    glBindTexture(GL_TEXTURE_RECTANGLE, col[1]);
+    glGetTexImage(GL_TEXTURE_RECTANGLE, 0, GL_RED, GL_FLOAT, masked.data());
+    glBindTexture(GL_TEXTURE_RECTANGLE, col[3]);
+    glGetTexImage(GL_TEXTURE_RECTANGLE, 0, GL_RED, GL_UNSIGNED_BYTE, mask.data());
     check("frame");
   }
-
-  // readback exactly as :729-735 (bottom-up GL rows = the same memory order as the input image)
-  std::vector<float> masked((size_t)c.W * c.H);
-  std::vector<unsigned char> mask((size_t)c.W * c.H);
-  glPixelStorei(GL_PACK_ALIGNMENT, 1);            // the reference relies on W % 4 == 0 with the default 4
-  glBindTexture(GL_TEXTURE_RECTANGLE, col[1]);
-  glGetTexImage(GL_TEXTURE_RECTANGLE, 0, GL_RED, GL_FLOAT, masked.data());
-  glBindTexture(GL_TEXTURE_RECTANGLE, col[3]);
-  glGetTexImage(GL_TEXTURE_RECTANGLE, 0, GL_RED, GL_UNSIGNED_BYTE, mask.data());
-  check("readback");
+  if (argc == 5) {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count() / (n_frames - 1);
+    std::fprintf(stderr, "TIMING frames %d ms_per_frame %.4f frames_per_s %.2f\n", n_frames - 1, ms, 1000.0 / ms);
+  }
 
   std::ofstream out(argv[3], std::ios::binary);
   out.write("RUFGLO01", 8);
@@ -229,6 +263,8 @@ int main(int argc, char **argv)
   out.write(reinterpret_cast<const char *>(hdr), sizeof(hdr));
   out.write(reinterpret_cast<const char *>(masked.data()), (std::streamsize)(masked.size() * sizeof(float)));
   out.write(reinterpret_cast<const char *>(mask.data()), (std::streamsize)mask.size());
+#ifndef RUF_GL_VIA_GLX
   OSMesaDestroyContext(ctx);
+#endif
   return out ? 0 : 8;
 }

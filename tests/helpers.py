@@ -52,3 +52,31 @@ def oracle_filter(sc, fr, want_mask=True, nthreads=4, max_diff=None, replace_val
                                        np.float32(synth.Z_NEAR), np.float32(synth.Z_FAR), np.float32(md),
                                        np.float32(rv), want_mask=want_mask, nthreads=nthreads, want_zbuf=True)
     return out, mask, zbuf
+
+
+def fuzz_case(seed):
+    """One hostile random soup of tests/test_gpu_fuzz.py with its matrices and a random float depth image, sized so that the
+    reference's GL read-back (default GL_PACK_ALIGNMENT) is happy: W % 4 == 0.  Deterministic in `seed`."""
+    import realtime_urdf_filter_b200 as ruf
+    import test_gpu_fuzz as fz
+    rng = np.random.default_rng(1000 + seed)
+    W, H = [(640, 480), (200, 152), (336, 76), (96, 200), (1280, 96), (64, 64)][(seed - 1) % 6]
+    n_parts = int(rng.integers(3, 14))
+    tri, part = fz._soup(rng, n_parts)
+    P = synth.kinect_P(W, H, fx=float(rng.uniform(0.5, 1.6)) * 525.0 * W / 640.0)
+    proj = orc.projection_matrix(P, W, H)[0]
+    ex = synth.example_scene()
+    Tinv = np.linalg.inv(synth.make_T(ex.cam_R, (0.0, 0.0, 0.0)))
+    view = ruf.view_matrix((0, 0, 0, 1), (0, 0, 0), synth.quat_from_matrix(Tinv[:3, :3]), Tinv[:3, 3], 0.0, 0.0)
+    world_from_cam = synth.make_T(ex.cam_R, (0.0, 0.0, 0.0)).T.reshape(-1)
+    pm = np.stack([(world_from_cam.reshape(4, 4).T @ m.reshape(4, 4).T).T.reshape(-1) for m in fz._part_models(rng, n_parts)])
+    depth = rng.uniform(0.0, 9.0, (H, W)).astype(np.float32)
+    return dict(W=W, H=H, n_parts=n_parts, tri=tri, part=part, proj=proj, view=view, pm=pm, depth=depth,
+                z_near=0.1, z_far=8.0, max_diff=0.05, replace_value=5.0)
+
+
+def fuzz_oracle(fc, nthreads=8):
+    mvp = orc.compose_mvp(fc["proj"], fc["view"], fc["pm"], fc["n_parts"])
+    d, m, _ = orc.filter_frame(fc["depth"], fc["tri"], fc["part"], mvp, np.float32(fc["z_near"]), np.float32(fc["z_far"]),
+                               np.float32(fc["max_diff"]), np.float32(fc["replace_value"]), want_mask=True, nthreads=nthreads)
+    return d, m
