@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  May be imported from tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py -- never from the realtime_urdf_filter_b200
-package.  PARITY STATUS of the oracle itself: "parity unpinned" for the fixed-function raster
-rules (see the header of ruf_oracle.c and DESIGN.md).
+package.  PARITY STATUS of the oracle itself: pinned against the reference's own shaders run on Mesa
+llvmpipe (oracle/gl_ref, tests/golden/gl_llvmpipe.npz; see the header of ruf_oracle.c and DESIGN.md section 2).
 """
 from __future__ import annotations
 

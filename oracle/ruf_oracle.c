@@ -24,16 +24,19 @@
  *   src/urdf_renderer.cpp:173-190 (per-frame tf lookups) -> orc_fk / orc_fk_outputs: forward kinematics
  *                                        from joint positions (robot_state_publisher + tf, restated)
  *
- * PARITY STATUS: **parity unpinned** for everything except the 16UC1<->32FC1
- * encodings.  The reference has no tests, golden images or fixtures
- *  and cannot be built or run in this image (it needs
- * OpenGL/GLEW/freeglut/ROS/Assimp), so the fixed-function
- * part of the path (clipping, rasterisation rule, depth interpolation) is a
- * documented choice (DESIGN.md "Raster specification"), not a measured GL
- * behaviour.  What IS pinned: the encodings against OpenCV's real
- * Mat::convertTo (tests/golden/cv_convert.npz), the matrices and shader by
- * analytic known-answer tests, and the geometry by an independent float64
- * ray-caster in tests/.
+ * PARITY STATUS: pinned against the reference itself.  The reference has no tests,
+ * golden images or fixtures and its C++/ROS program cannot be
+ * built in this image, but its GLSL path can be run: oracle/gl_ref replays the GL
+ * call sequence of RealtimeURDFFilter::render with the reference's two shader files
+ * UNMODIFIED in a real GL driver (the Mesa 18.1.9 llvmpipe libGL inside Nsight
+ * Compute, on a 30-call fake Xlib), and this file reproduces that driver's filtered
+ * depth and mask bit for bit on every synthetic scene (0 - 3 mask pixels of 1.2 M on
+ * the 1280x960 frames) and within 9 mask pixels per image on hostile random soups
+ * (tests/test_gl_crosscheck.py here; golden vectors from the driver in
+ * tests/golden/gl_llvmpipe.npz, tests/test_gl_golden.py everywhere).  Also pinned: the
+ * encodings against OpenCV's real Mat::convertTo (tests/golden/cv_convert.npz), the
+ * matrices and shader by analytic known-answer tests, the geometry by an independent
+ * float64 ray-caster in tests/.  Not measured: hardware GL drivers.
  *
  * Third-party arithmetic restated here from its published algorithm (absent from
  * /root/reference, all unpinned in package.xml):
