@@ -207,8 +207,47 @@ class OracleWorkload:
                               native=True)
 
 
+def gl_reference_arm(args, cfg, sc):
+    """The reference's OWN implementation of the path where it can run: its two shader files (compiled into
+    oracle/_ref/gl_crosscheck_glx when the checkout was present at build time) in Mesa llvmpipe -- the libGL inside Nsight
+    Compute on oracle/gl_ref/fakex11 --, driven through the GL call sequence of RealtimeURDFFilter::render: sensor upload,
+    render, both read-backs per frame.  One harness run per step (another frame of the stream each), timed inside the
+    harness in steady state.  -> (frames/s, ms per step, threads, description) or None when any piece is missing."""
+    import glob
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "gl_crosscheck_glx")
+    mesa = sorted(glob.glob("/opt/nvidia/nsight-compute/*/host/linux-desktop-glibc_2_11_3-x64/Mesa"))
+    if not os.path.exists(exe) or not mesa or os.environ.get("RUF_NO_GL_REFERENCE"):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "gl_ref"))
+    import gl_case
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "oracle", "_ref", "fakex") + ":" + mesa[0])
+    per_step = max(8, 2 * cfg["cpu_frames"])          # ~1 s of llvmpipe per step: past the shader JIT and the thread ramp
+    ms = []
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            for s_ in range(args.warmup + args.steps):
+                case, dump = os.path.join(td, "case.bin"), os.path.join(td, "dump.bin")
+                gl_case.write_case(case, sc, s_, gl_case._frame_depth(sc, s_))
+                r = subprocess.run([exe, case, "-", dump, str(per_step + 1)], capture_output=True, text=True, env=env, timeout=600)
+                t = [l for l in r.stderr.splitlines() if l.startswith("TIMING")]
+                if r.returncode != 0 or not t:
+                    return None
+                if s_ >= args.warmup:
+                    ms.append(float(t[0].split()[4]))
+            gl_info = r.stderr.splitlines()[0]
+    except Exception:
+        return None
+    mean_ms = sum(ms) / len(ms)
+    threads = min(16, os.cpu_count() or 1)            # llvmpipe: one rasteriser thread per online core, at most 16
+    return 1e3 / mean_ms, mean_ms * per_step, threads, per_step, gl_info
+
+
 def run_reference(args, rank, world):
-    """--impl reference: CPU oracle, all host threads, K steps of a bounded sample each (rank 0 only)."""
+    """--impl reference: the reference's implementation of the path on the host cores (rank 0 only): its GLSL path on Mesa
+    llvmpipe where the harness and the driver exist (kind "reference"), else the CPU oracle on all host threads (kind
+    "port"); K steps of a bounded sample each."""
     if rank != 0:
         return
     orc = load_oracle()
@@ -216,6 +255,27 @@ def run_reference(args, rank, world):
     synth.use_math(OracleMath(orc))
     cfg = CONFIGS[args.config]
     sc = make_scene(cfg)
+    gl = gl_reference_arm(args, cfg, sc)
+    if gl is not None:
+        fps, ms_step, threads, per_step, gl_info = gl
+        line = {
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong" if (args.config == "c5" and args.gpus > 1) else "weak",
+            "vs_baseline": None, "dtype": "f32 (GLSL)", "data": "synthetic",
+            "config": config_dict(args.config, cfg, sc.n_tris, sc.n_parts, args.gpus),
+            "run": {"frames_per_step": per_step, "distinct_frames": args.steps},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"{args.steps} steps x {per_step} frames: the reference's own shader files (unmodified) through the GL "
+                                       f"call sequence of RealtimeURDFFilter::render -- sensor upload, render, both read-backs per frame -- in "
+                                       f"{gl_info} (oracle/_ref/gl_crosscheck_glx on oracle/gl_ref/fakex11), timed in steady state"},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "native_libraries": sorted({os.path.basename(l.split()[-1]) for l in open("/proc/self/maps")
+                                        if "libruf" in l or "ruf_oracle" in l}),
+        }
+        print(json.dumps(line), flush=True)
+        return
     threads = host_threads()
     nf = min(8, cfg["cpu_frames"])
     work = OracleWorkload(orc, sc, nf, threads)
@@ -239,7 +299,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {per_step} frames of the same workload, oracle/ruf_oracle.c "
                                    f"-O3 -march=native, OpenMP over {threads} threads (sched_getaffinity; the "
-                                   "reference's GL path needs libGL/X11: absent)"},
+                                   "reference's GLSL path on llvmpipe is the `--impl reference` arm where oracle/_ref/gl_crosscheck_glx exists)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "native_libraries": sorted({os.path.basename(l.split()[-1]) for l in open("/proc/self/maps")

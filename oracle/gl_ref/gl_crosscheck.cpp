@@ -54,6 +54,12 @@ int glXMakeCurrent(Display *, unsigned long, GLXContext);
 #include <GL/osmesa.h>
 #endif
 
+#ifdef RUF_EMBEDDED_SHADERS
+// the reference's shader files as they were at build time (oracle/gl_ref/embed_shaders.py): `<shader_dir>` = "-" uses them
+extern "C" const char ruf_ref_vert_src[];
+extern "C" const char ruf_ref_frag_src[];
+#endif
+
 namespace {
 
 struct Part { double model[16]; int32_t suffix_kind; float sx, sy, sz; };   // suffix: 0 none, 1 glTranslatef, 2 glScalef
@@ -176,9 +182,18 @@ int main(int argc, char **argv)
   glGenTextures(1, &tex);
 
   const std::string dir = argv[2];
+  std::string vert_src, frag_src;
+  if (dir == "-") {
+#ifdef RUF_EMBEDDED_SHADERS
+    vert_src = ruf_ref_vert_src; frag_src = ruf_ref_frag_src;
+#endif
+    if (vert_src.empty() || frag_src.empty()) { std::fprintf(stderr, "this binary was built without the reference's shader files\n"); return 2; }
+  } else {
+    vert_src = slurp(dir + "/urdf_filter.vert"); frag_src = slurp(dir + "/urdf_filter.frag");
+  }
   GLuint prog = glCreateProgram();
-  glAttachShader(prog, compile(GL_VERTEX_SHADER, slurp(dir + "/urdf_filter.vert")));
-  glAttachShader(prog, compile(GL_FRAGMENT_SHADER, slurp(dir + "/urdf_filter.frag")));
+  glAttachShader(prog, compile(GL_VERTEX_SHADER, vert_src));
+  glAttachShader(prog, compile(GL_FRAGMENT_SHADER, frag_src));
   glLinkProgram(prog);
   GLint linked = 0;
   glGetProgramiv(prog, GL_LINK_STATUS, &linked);
