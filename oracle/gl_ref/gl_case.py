@@ -145,6 +145,12 @@ def compare(sc, k, depth_f32, gl_depth, gl_mask, max_diff=None, replace_value=No
 
 def _scene(name):
     from realtime_urdf_filter_b200 import synth
+    if name == "kinds":                                 # 160 x 120, every renderable kind: box + doubled cube (glScalef), sphere,
+        import importlib.util                           # cylinder (glTranslatef), scaled mesh -- tests/golden/make_path_golden.py
+        spec = importlib.util.spec_from_file_location("make_path_golden", os.path.join(ROOT, "tests", "golden", "make_path_golden.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.small_scene()
     if name.startswith("small:"):                      # small:<scene>: the same scene at 160 x 120 (golden fixtures)
         base = name.split(":", 1)[1]
         return {"example": lambda: synth.example_scene(160, 120), "walls": lambda: synth.walls_scene(160, 120),

@@ -28,7 +28,7 @@ import oracle_py as orc  # noqa: E402
 FUZZ_SEEDS = [2, 4, 6, 9, 12]
 
 CASES = [("small:example", 0), ("small:example", 7), ("small:pr2_small", 0), ("small:pr2_small", 7), ("small:pr2_small", 19),
-         ("small:walls", 0), ("small:walls", 7)]
+         ("small:walls", 0), ("small:walls", 7), ("kinds", 0), ("kinds", 1), ("kinds", 9)]
 SHADERS = os.environ.get("RUF_REFERENCE_SHADERS", "/root/reference/include/shaders")
 
 

@@ -83,7 +83,8 @@ def _mesa_dir():
 @pytest.mark.skipif(_mesa_dir() is None, reason="no Mesa libGL (Nsight Compute's) on this machine")
 @pytest.mark.skipif(_shader_dir() is None, reason="the reference's shader files are not on this machine "
                     "(set RUF_REFERENCE_SHADERS=<reference>/include/shaders)")
-@pytest.mark.parametrize("name,k", [("example", 0), ("example", 11), ("pr2_small", 3), ("pr2_small", 21), ("walls", 0), ("small:walls", 7)])
+@pytest.mark.parametrize("name,k", [("example", 0), ("example", 11), ("pr2_small", 3), ("pr2_small", 21), ("walls", 0), ("small:walls", 7),
+                                    ("kinds", 1)])      # kinds: box + doubled cube (glScalef), sphere, cylinder (glTranslatef), scaled mesh
 def test_reference_shaders_on_llvmpipe_against_the_oracle(tmp_path, name, k):
     """The reference's GLSL path itself (BASELINE.json's CPU arm: Mesa llvmpipe), full size: the oracle agrees with it on
     every pixel but a handful on silhouettes (observed: 0 or 1 of up to 1.2 M)."""
