@@ -853,12 +853,23 @@ static void filter_range(const void *depth_in, int enc, const float *zbuf, size_
     float sensor = (enc == ENC_U16_MM) ? (float)((const uint16_t *)depth_in)[i] * 0.001f
                                        : ((const float *)depth_in)[i];
     float out, s, virt = 0.0f;
+    /* What mix(sensor, replace, a) = sensor * (1 - a) + replace * a (frag:29) does to the exotic values of a 32FC1 image,
+     * as measured in the GL driver (oracle/gl_ref on Mesa llvmpipe, tests/golden/gl_llvmpipe.npz "special" case):
+     *   |sensor| below FLT_MIN (denormals, -0.0)  ->  +0.0   (the shader runs with denormals-are-zero; -0 + 0 = +0)
+     *   sensor = +inf on a filtered pixel          ->  NaN    (inf * 0; the x86 default NaN 0xffc00000 in that driver)
+     * NaN and -inf are never filtered (the comparison is false) and pass through with their bits. */
+    if (enc != ENC_U16_MM && fabsf(sensor) < 1.17549435e-38f) sensor = 0.0f;
     if (zbuf[i] == 1.0f) {             /* never drawn: clear colour */
       out = 0.0f; s = 0.0f;
     } else {
       virt = orc_to_linear_depth(zbuf[i], z_near, z_far);            /* frag:22 */
       s = (sensor > (virt - max_diff)) ? 1.0f : 0.0f;                 /* frag:23 */
-      out = (s != 0.0f) ? replace_value : sensor;                     /* frag:29, mix with a in {0,1} */
+      if (s != 0.0f) {                                                /* frag:29, mix with a in {0,1} */
+        out = replace_value;
+        if (sensor > 3.40282347e+38f) { const uint32_t qnan = 0xffc00000u; memcpy(&out, &qnan, 4); }
+      } else {
+        out = sensor;
+      }
     }
     if (enc == ENC_U16_MM) ((uint16_t *)depth_out)[i] = f32_to_u16_one(out);
     else ((float *)depth_out)[i] = out;

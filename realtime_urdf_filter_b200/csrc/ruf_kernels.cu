@@ -1015,6 +1015,15 @@ __device__ __forceinline__ void store_mask(const FrameBuffers &fb, size_t base, 
   else *reinterpret_cast<uint2 *>(fb.mask_out + base) = mq;
 }
 
+// mix(sensor, replace, a) = sensor * (1 - a) + replace * a (frag:29) on the exotic values of a 32FC1 image, as the GL driver
+// computes it (measured on Mesa llvmpipe with the reference's shaders): the shader runs with denormals-are-zero and
+// -0 + 0 = +0, so |sensor| < FLT_MIN reads as +0.0; +inf on a filtered pixel gives inf * 0 = NaN (that driver's 0xffc00000).
+__device__ __forceinline__ float sensor_daz(float x) { return (fabsf(x) < 1.17549435e-38f) ? 0.0f : x; }
+__device__ __forceinline__ float mix_filtered(float sensor, float replace)
+{
+  return (sensor > 3.40282347e+38f) ? __int_as_float((int)0xffc00000u) : replace;
+}
+
 struct FragOut { float depth; uint32_t mask; };
 // include/shaders/urdf_filter.frag:19-35 for the fragment that survived GL_LESS.
 __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const ShaderParams &sp)
@@ -1023,7 +1032,7 @@ __device__ __forceinline__ FragOut fragment(float sensor, float zwin, const Shad
   if (zwin == 1.0f) { o.depth = 0.0f; o.mask = 0u; return o; }   // never drawn: clear colour (:566)
   const float virt = sp.k1 / (zwin - sp.k2);                      // frag:14-17,22
   const bool s = sensor > (virt - sp.max_diff);                   // frag:23
-  o.depth = s ? sp.replace_value : sensor;                        // frag:29, mix() with a in {0,1}
+  o.depth = s ? mix_filtered(sensor, sp.replace_value) : sensor;  // frag:29, mix() with a in {0,1}
   o.mask = s ? 255u : 0u;                                         // frag:35 read back as UNSIGNED_BYTE
   return o;
 }
@@ -1040,7 +1049,7 @@ __device__ __forceinline__ void shade_scalar(const FrameBuffers &fb, const Shade
     const float z = zw[i * zstride];
     float sensor;
     if (ENC == 1) sensor = (float)static_cast<const uint16_t *>(fb.depth_in)[base + i] * 0.001f;
-    else sensor = static_cast<const float *>(fb.depth_in)[base + i];
+    else sensor = sensor_daz(static_cast<const float *>(fb.depth_in)[base + i]);
     const FragOut o = fragment(sensor, z, sp);
     if (ENC == 1) static_cast<uint16_t *>(fb.depth_out)[base + i] = (uint16_t)f32_to_u16(o.depth);
     else static_cast<float *>(fb.depth_out)[base + i] = o.depth;
@@ -1317,8 +1326,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
               uint32_t om[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const bool sflt = sensor[i] > thr;                      // frag:23
-                od[i] = sflt ? sp.replace_value : sensor[i];            // frag:29
+                const float sv = sensor_daz(sensor[i]);
+                const bool sflt = sv > thr;                             // frag:23
+                od[i] = sflt ? mix_filtered(sv, sp.replace_value) : sv; // frag:29
                 om[i] = sflt ? 255u : 0u;
               }
               mq.x = om[0] | (om[1] << 8) | (om[2] << 16) | (om[3] << 24);
@@ -1883,8 +1893,9 @@ ruf_raster_filter_kernel(Dims d, const TriRec *__restrict__ big_all, const BinRe
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const bool drawn = zw[i] != 1.0f;
-          const bool sflt = sensor[i] > thr[i];
-          od[i] = drawn ? (sflt ? sp.replace_value : sensor[i]) : 0.0f;    // frag:29, mix() with a in {0,1}
+          const float sv = sensor_daz(sensor[i]);
+          const bool sflt = sv > thr[i];
+          od[i] = drawn ? (sflt ? mix_filtered(sv, sp.replace_value) : sv) : 0.0f;    // frag:29, mix() with a in {0,1}
           om[i] = sflt ? 255u : 0u;
         }
         stg_256(static_cast<float *>(fb.depth_out) + base, od);

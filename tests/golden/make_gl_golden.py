@@ -64,14 +64,14 @@ if __name__ == "__main__":
         meta["gl"] = gl_info
         print(name, k, rep)
     meta["fuzz"] = []
-    for j, seed in enumerate(FUZZ_SEEDS):
-        fc = helpers.fuzz_case(seed)
+    for j, (seed, special) in enumerate([(sd, False) for sd in FUZZ_SEEDS] + [(6, True), (9, True)]):
+        fc = helpers.fuzz_case(seed, special=special)
         d, m, _ = run_gl(None, 0, None, raw=fc)
         want_d, want_m = helpers.fuzz_oracle(fc)
         dm = m != want_m
         assert np.array_equal(d.view(np.uint32)[~dm], want_d.view(np.uint32)[~dm])
         out[f"fuzz_depth_{j}"], out[f"fuzz_mask_{j}"] = d.view(np.uint32), m
-        meta["fuzz"].append(dict(seed=seed, width=fc["W"], height=fc["H"], triangles=int(len(fc["tri"])), mask_pixels_differing_from_oracle=int(dm.sum())))
+        meta["fuzz"].append(dict(seed=seed, special=special, width=fc["W"], height=fc["H"], triangles=int(len(fc["tri"])), mask_pixels_differing_from_oracle=int(dm.sum())))
         print("fuzz", seed, meta["fuzz"][-1])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "gl_llvmpipe.npz"), meta=np.frombuffer(json.dumps(meta).encode(), np.uint8), **out)
     print(meta["gl"])

@@ -54,9 +54,11 @@ def oracle_filter(sc, fr, want_mask=True, nthreads=4, max_diff=None, replace_val
     return out, mask, zbuf
 
 
-def fuzz_case(seed):
+def fuzz_case(seed, special=False):
     """One hostile random soup of tests/test_gpu_fuzz.py with its matrices and a random float depth image, sized so that the
-    reference's GL read-back (default GL_PACK_ALIGNMENT) is happy: W % 4 == 0.  Deterministic in `seed`."""
+    reference's GL read-back (default GL_PACK_ALIGNMENT) is happy: W % 4 == 0.  Deterministic in `seed`.
+    special: 15 % of the sensor pixels are NaN, +-inf, +-0.0, negative, 3e38 or denormal (what a REP-117 float depth image
+    may hold, and what mix() in the reference's shader treats in its own way)."""
     import realtime_urdf_filter_b200 as ruf
     import test_gpu_fuzz as fz
     rng = np.random.default_rng(1000 + seed)
@@ -71,6 +73,11 @@ def fuzz_case(seed):
     world_from_cam = synth.make_T(ex.cam_R, (0.0, 0.0, 0.0)).T.reshape(-1)
     pm = np.stack([(world_from_cam.reshape(4, 4).T @ m.reshape(4, 4).T).T.reshape(-1) for m in fz._part_models(rng, n_parts)])
     depth = rng.uniform(0.0, 9.0, (H, W)).astype(np.float32)
+    if special:
+        sel = np.random.default_rng(seed).random(depth.shape)
+        for lo, hi, v in ((0.00, 0.03, np.nan), (0.03, 0.05, np.inf), (0.05, 0.07, -np.inf), (0.07, 0.09, 0.0), (0.09, 0.11, -1.5),
+                          (0.11, 0.12, 3.0e38), (0.12, 0.13, 1e-42), (0.13, 0.14, -1e-42), (0.14, 0.15, -0.0)):
+            depth[(sel >= lo) & (sel < hi)] = np.float32(v)
     return dict(W=W, H=H, n_parts=n_parts, tri=tri, part=part, proj=proj, view=view, pm=pm, depth=depth,
                 z_near=0.1, z_far=8.0, max_diff=0.05, replace_value=5.0)
 

@@ -56,7 +56,7 @@ def test_oracle_against_the_gl_driver_on_hostile_soups(j):
     pixels (GL multiplies its matrix stack and clips in float) -- never more than 5 in 10000."""
     import helpers
     f, gl_depth, gl_mask = FUZZ[j]
-    fc = helpers.fuzz_case(f["seed"])
+    fc = helpers.fuzz_case(f["seed"], special=f.get("special", False))
     want_d, want_m = helpers.fuzz_oracle(fc)
     dm = want_m != gl_mask
     assert int(dm.sum()) == f["mask_pixels_differing_from_oracle"] <= max(4, 5e-4 * dm.size)

@@ -38,7 +38,7 @@ def test_cuda_path_reproduces_the_gl_driver_bit_for_bit(i, cluster, monkeypatch)
 @pytest.mark.parametrize("j", range(len(FUZZ)))
 def test_cuda_path_against_the_gl_driver_on_hostile_soups(j):
     f, gl_depth, gl_mask = FUZZ[j]
-    fc = helpers.fuzz_case(f["seed"])
+    fc = helpers.fuzz_case(f["seed"], special=f.get("special", False))
     with ruf.Context(fc["W"], fc["H"]) as ctx:
         ctx.set_model(fc["tri"], fc["part"], fc["n_parts"])
         got_d, got_m = ctx.filter(fc["depth"], fc["proj"], fc["view"], fc["pm"], fc["max_diff"], fc["replace_value"])
