@@ -155,7 +155,7 @@ def _scene(name):
         base = name.split(":", 1)[1]
         return {"example": lambda: synth.example_scene(160, 120), "walls": lambda: synth.walls_scene(160, 120),
                 "pr2_small": lambda: synth.pr2_like_scene(160, 120, n_tris=6000, name="pr2_like_small_160")}[base]()
-    return {"example": synth.example_scene, "walls": synth.walls_scene, "pr2": synth.pr2_like_scene,
+    return {"example": synth.example_scene, "walls": synth.walls_scene, "pr2": synth.pr2_like_scene, "multi": synth.multi_robot_scene,
             "pr2_small": lambda: synth.pr2_like_scene(n_tris=6000, name="pr2_like_small")}[name]()
 
 
